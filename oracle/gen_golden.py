@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz by running the REAL reference modules (this container only).
+
+    python -m oracle.gen_golden
+
+For every case: build a seeded state_dict with oracle.nets.make_state_dict (own deterministic
+procedure), load it (strict) into the module returned by the reference's own
+define_G / define_D (/root/reference/deepliif/models/networks.py:142-238), switch it to the
+reference's inference mode (eval + disable_batchnorm_tracking_stats, util/__init__.py:743-755),
+run it per sample at N=1 (reference inference semantics) on a seeded input, and store
+(input seed, config, output[, subsampled]) as a small fixture.  The same script asserts the
+functional oracle (oracle/nets.py) reproduces the reference output to <= 2e-5 max-abs before a
+fixture is written, so a committed fixture always pins the oracle.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import nets, pixel
+from .ref_shim import import_reference, reference_networks
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def seeded_input(seed, n, c, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand((n, c, h, w), generator=g) * 2 - 1
+
+
+def ref_eval(net, x):
+    import deepliif.util as U
+    net.eval()
+    U.disable_batchnorm_tracking_stats(net)
+    with torch.no_grad():
+        return torch.cat([net(x[i:i + 1]) for i in range(x.shape[0])])
+
+
+def save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrs.items()})
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    N = reference_networks()
+    import_reference()
+    cases = []
+
+    # ---- ResnetGenerator -------------------------------------------------------------------
+    for name, cfg, hw, n, seed, init in [
+        ("resnet9_batch_zero_64", dict(n_blocks=9, norm="batch", use_dropout=True, padding_type="zero"), 64, 2, 11, "stress"),
+        ("resnet9_inst_zero_64", dict(n_blocks=9, norm="instance", use_dropout=False, padding_type="zero"), 64, 2, 12, "stress"),
+        ("resnet9_batch_reflect_64", dict(n_blocks=9, norm="batch", use_dropout=False, padding_type="reflect"), 64, 1, 13, "stress"),
+        ("resnet2_inst_reflect_32", dict(n_blocks=2, norm="instance", use_dropout=True, padding_type="reflect"), 32, 2, 14, "stress"),
+        ("resnet9_batch_zero_512", dict(n_blocks=9, norm="batch", use_dropout=True, padding_type="zero"), 512, 1, 0, "reference"),
+        ("resnet9_inst_zero_512", dict(n_blocks=9, norm="instance", use_dropout=False, padding_type="zero"), 512, 1, 1, "reference"),
+    ]:
+        shapes = nets.resnet_param_shapes(3, 3, 64, cfg["n_blocks"], cfg["norm"], cfg["use_dropout"], cfg["padding_type"])
+        sd = nets.make_state_dict(shapes, seed, init)
+        net = N.define_G(3, 3, 64, f"resnet_{cfg['n_blocks']}blocks", cfg["norm"], cfg["use_dropout"],
+                         "normal", 0.02, [], cfg["padding_type"])
+        assert list(net.state_dict().keys()) == list(sd.keys()), "state_dict key order mismatch"
+        net.load_state_dict(sd, strict=True)
+        x = seeded_input(1000 + seed, n, 3, hw, hw)
+        y_ref = ref_eval(net, x)
+        y_orc = nets.resnet_forward(x, sd, norm_mode="sample", **cfg)
+        err = (y_ref - y_orc).abs().max().item()
+        print(f"{name}: oracle-vs-reference max|d| = {err:.3e}")
+        assert err <= 2e-5, name
+        y = y_ref.numpy()
+        if hw > 128:
+            y = y[:, :, ::8, ::8]          # strided subsample keeps the fixture small
+        save(name, y=y.astype(np.float32), meta=np.array(json.dumps(
+            dict(arch="resnet", cfg=cfg, hw=hw, n=n, seed=seed, init=init, x_seed=1000 + seed,
+                 subsample=8 if hw > 128 else 1, mean_abs=float(y_ref.abs().mean()),
+                 sum=float(y_ref.double().sum())))))
+
+    # ---- UnetGenerator ---------------------------------------------------------------------
+    for name, netG, nd, norm, hw, n, seed in [
+        ("unet256_batch_256", "unet_256", 8, "batch", 256, 1, 21),
+        ("unet512_batch_512", "unet_512", 9, "batch", 512, 1, 22),
+        ("unet128_inst_128", "unet_128", 7, "instance", 128, 2, 23),
+    ]:
+        shapes = nets.unet_param_shapes(nd, 64, 3, 3, norm)
+        sd = nets.make_state_dict(shapes, seed, "stress")
+        net = N.define_G(3, 3, 64, netG, norm, True, "normal", 0.02, [])
+        assert list(net.state_dict().keys()) == list(sd.keys()), "unet key order mismatch"
+        net.load_state_dict(sd, strict=True)
+        x = seeded_input(1000 + seed, n, 3, hw, hw)
+        y_ref = ref_eval(net, x)
+        y_orc = nets.unet_forward(x, sd, num_downs=nd, norm=norm, norm_mode="sample")
+        err = (y_ref - y_orc).abs().max().item()
+        print(f"{name}: oracle-vs-reference max|d| = {err:.3e}")
+        assert err <= 2e-5, name
+        y = y_ref.numpy()
+        sub = 4 if hw > 128 else 1
+        save(name, y=y[:, :, ::sub, ::sub].astype(np.float32), meta=np.array(json.dumps(
+            dict(arch="unet", num_downs=nd, norm=norm, hw=hw, n=n, seed=seed, init="stress",
+                 x_seed=1000 + seed, subsample=sub, sum=float(y_ref.double().sum())))))
+
+    # ---- NLayerDiscriminator (training-mode batch statistics, N=2) ---------------------------
+    for name, netD, nl, norm, hw, n, seed in [
+        ("dbasic_batch_128", "basic", 3, "batch", 128, 2, 31),
+        ("dn4_inst_128", "n_layers", 4, "instance", 128, 2, 32),
+    ]:
+        shapes = nets.nlayer_d_param_shapes(nl, 64, 6, norm)
+        sd = nets.make_state_dict(shapes, seed, "stress")
+        net = N.define_D(6, 64, netD, nl, norm, "normal", 0.02, [])
+        assert list(net.state_dict().keys()) == list(sd.keys()), "D key order mismatch"
+        net.load_state_dict(sd, strict=True)
+        net.train()
+        x = seeded_input(1000 + seed, n, 6, hw, hw)
+        with torch.no_grad():
+            y_ref = net(x)
+        y_orc = nets.nlayer_d_forward(x, sd, n_layers=nl, norm=norm, norm_mode="batch")
+        err = (y_ref - y_orc).abs().max().item()
+        print(f"{name}: oracle-vs-reference max|d| = {err:.3e}")
+        assert err <= 2e-5, name
+        save(name, y=y_ref.numpy().astype(np.float32), meta=np.array(json.dumps(
+            dict(arch="nlayer_d", n_layers=nl, norm=norm, hw=hw, n=n, seed=seed, init="stress",
+                 x_seed=1000 + seed))))
+
+    # ---- pixel ends: transform / tensor2im / create_posneg_mask ------------------------------
+    from deepliif.data import transform as ref_transform
+    from deepliif.util.util import tensor2im as ref_tensor2im
+    from deepliif.postprocessing import create_posneg_mask as ref_mask
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8)
+    t_ref = ref_transform(Image.fromarray(img)).numpy()
+    assert np.array_equal(t_ref, pixel.transform(img)), "transform restatement differs"
+    f = (rng.random((1, 3, 64, 64), dtype=np.float32) * 2 - 1).astype(np.float32)
+    u8_ref = ref_tensor2im(torch.from_numpy(f))
+    assert np.array_equal(u8_ref, pixel.tensor2im(f)), "tensor2im restatement differs"
+    seg = rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8)
+    m_ref = ref_mask(seg, 120)
+    assert np.array_equal(m_ref, pixel.create_posneg_mask(seg, 120)), "posneg restatement differs"
+    save("pixel_ends", img=img, transform=t_ref.astype(np.float32), f=f, tensor2im=u8_ref,
+         seg=seg, mask=m_ref)
+    print("all fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
