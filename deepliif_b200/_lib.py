@@ -1,0 +1,69 @@
+"""ctypes binding of libdeepliif_b200.so (the C ABI in include/deepliif_b200.h).  Fails loudly when the
+library is missing or does not export a declared symbol — there is no fallback path."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdeepliif_b200.so")
+
+FMT_BF16, FMT_FP16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_TANH = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("nsrc", C.c_int), ("Cin", C.c_int * 2),
+                ("Cout", C.c_int), ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+                ("transposed", C.c_int), ("output_padding", C.c_int), ("pad_mode", C.c_int)]
+
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_cd = C.POINTER(ConvDesc)
+_vpp = C.POINTER(C.c_void_p)
+
+# symbol -> (restype, argtypes); mirrors include/deepliif_b200.h one to one
+SIGNATURES = {
+    "dlb_last_error": (C.c_char_p, []),
+    "dlb_version": (_i, []),
+    "dlb_conv_out_shape": (_i, [_cd, C.POINTER(_i), C.POINTER(_i)]),
+    "dlb_pack_weights_tc": (_i, [_cd, _vp, _i, _vp, _vp, _vp]),
+    "dlb_pack_weights_direct": (_i, [_cd, _vp, _vp, _vp]),
+    "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dlb_conv_direct_fwd": (_i, [_cd, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
+    "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dlb_u8_to_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dlb_f32_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dlb_seg_finish": (_i, [_vpp, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class DeepliifB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it is not built: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DeepliifB200Error(
+            f"{LIB_PATH} not found: build it with `python -m deepliif_b200.build` (nvcc, sm_100a). "
+            "deepliif_b200 has no CPU / PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dlb_last_error().decode("utf-8", "replace")
+        raise DeepliifB200Error(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,138 @@
+// C-ABI front end: error reporting, layer geometry, and the lowering of nn.Conv2d / nn.ConvTranspose2d
+// semantics to tap-list phases executed by conv_tc.cu (tcgen05) or conv_direct.cu (fp32 CUDA cores).
+#include "internal.h"
+
+namespace dlb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return DLB_ERR_INVALID;
+}
+int set_cuda_error(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return DLB_ERR_CUDA;
+}
+
+namespace {
+
+int out_shape(const dlb_conv_desc* d, int* OH, int* OW) {
+  if (d->stride != 1 && d->stride != 2) return set_error("conv: stride must be 1 or 2");
+  if (d->transposed) {
+    *OH = (d->H - 1) * d->stride - 2 * d->pad + d->R + d->output_padding;
+    *OW = (d->W - 1) * d->stride - 2 * d->pad + d->S + d->output_padding;
+  } else {
+    *OH = (d->H + 2 * d->pad - d->R) / d->stride + 1;
+    *OW = (d->W + 2 * d->pad - d->S) / d->stride + 1;
+  }
+  if (*OH < 1 || *OW < 1) return set_error("conv: empty output");
+  return 0;
+}
+
+// Lower a layer to phases.  Element strides are given by (sn, sh, sw): strides of the full output tensor
+// for (n, h, w) in elements (NHWC: OH*OW*C, OW*C, C; NCHW plane addressing: C*OH*OW, OW, 1).
+int build_phases(const dlb_conv_desc* d, int OH, int OW, long long sn, long long sh, long long sw, PhaseGeom* out) {
+  int np = 0;
+  if (!d->transposed) {
+    PhaseGeom& g = out[np++];
+    g.N = d->N; g.H = d->H; g.W = d->W; g.OH = OH; g.OW = OW; g.stride = d->stride; g.ntaps = 0;
+    g.w_taps = d->R * d->S; g.cout = d->Cout;
+    for (int r = 0; r < d->R; ++r)
+      for (int s = 0; s < d->S; ++s) {
+        if (g.ntaps >= 64) return set_error("conv: more than 64 taps");
+        g.tap_dh[g.ntaps] = r - d->pad; g.tap_dw[g.ntaps] = s - d->pad; g.tap_widx[g.ntaps] = r * d->S + s;
+        ++g.ntaps;
+      }
+    g.ys_n = sn; g.ys_h = sh; g.ys_w = sw; g.y_base = 0;
+    return np;
+  }
+  // ConvTranspose2d: ho = hi*stride - pad + r  =>  for output parity a: r == (a + pad) mod stride,
+  // hi = i + (a + pad - r) / stride with ho = stride*i + a.  One phase per output parity class.
+  const int st = d->stride;
+  for (int a = 0; a < st; ++a)
+    for (int b = 0; b < st; ++b) {
+      PhaseGeom& g = out[np];
+      g.N = d->N; g.H = d->H; g.W = d->W; g.stride = 1; g.ntaps = 0; g.w_taps = d->R * d->S; g.cout = d->Cout;
+      g.OH = (OH - a + st - 1) / st; g.OW = (OW - b + st - 1) / st;
+      for (int r = 0; r < d->R; ++r) {
+        if (((a + d->pad - r) % st) != 0) continue;
+        for (int s = 0; s < d->S; ++s) {
+          if (((b + d->pad - s) % st) != 0) continue;
+          g.tap_dh[g.ntaps] = (a + d->pad - r) / st; g.tap_dw[g.ntaps] = (b + d->pad - s) / st;
+          g.tap_widx[g.ntaps] = r * d->S + s;
+          ++g.ntaps;
+        }
+      }
+      g.ys_n = sn; g.ys_h = sh * st; g.ys_w = sw * st; g.y_base = a * sh + b * sw;
+      if (g.ntaps == 0 || g.OH < 1 || g.OW < 1) return set_error("convT: empty phase (unsupported geometry)");
+      ++np;
+    }
+  return np;
+}
+
+}  // namespace
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" const char* dlb_last_error(void) { return g_err; }
+extern "C" int dlb_version(void) { return 100; }
+
+extern "C" int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW) { return out_shape(d, OH, OW); }
+
+extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
+                               const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split,
+                               int n_tile, dlb_stream_t stream) {
+  int OH, OW;
+  if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
+  if (d->pad_mode != DLB_PAD_ZERO) return set_error("dlb_conv_tc_fwd: zero padding only (reflect border comes from dlb_norm_apply)");
+  if (d->nsrc < 1 || d->nsrc > 2) return set_error("dlb_conv_tc_fwd: nsrc must be 1 or 2");
+  if (fmt != DLB_FMT_BF16 && fmt != DLB_FMT_FP16) return set_error("dlb_conv_tc_fwd: bad fmt");
+  PhaseGeom geo[4];
+  const long long C = d->Cout;
+  const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
+  if (np < 0) return np;
+  for (int i = 0; i < np; ++i) {
+    if (geo[i].ntaps > 16) return set_error("dlb_conv_tc_fwd: more than 16 taps per phase");
+    TcPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    static_cast<PhaseGeom&>(ph) = geo[i];
+    ph.nsrc = d->nsrc;
+    for (int s = 0; s < d->nsrc; ++s) { ph.cin[s] = d->Cin[s]; ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; }
+    ph.w_hi = w_hi; ph.w_lo = split ? w_lo : nullptr; ph.bias = bias; ph.y = y;
+    ph.fmt = fmt; ph.split = split ? 1 : 0; ph.n_tile = n_tile;
+    const int rc = launch_conv_tc_phase(ph, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, const float* in_scale,
+                                   const float* in_shift, int in_act, const float* w_packed, const float* bias,
+                                   float* y, int out_act, int out_nchw, dlb_stream_t stream) {
+  int OH, OW;
+  if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
+  if (d->nsrc != 1) return set_error("dlb_conv_direct_fwd: single source only");
+  if (d->pad_mode == DLB_PAD_REFLECT && (d->transposed || d->pad >= d->H || d->pad >= d->W))
+    return set_error("dlb_conv_direct_fwd: reflect padding needs a plain conv with pad < H, W");
+  PhaseGeom geo[4];
+  const long long C = d->Cout;
+  long long sn, sh, sw, sc;
+  if (out_nchw) { sn = C * OH * OW; sh = OW; sw = 1; sc = static_cast<long long>(OH) * OW; }
+  else { sn = static_cast<long long>(OH) * OW * C; sh = static_cast<long long>(OW) * C; sw = C; sc = 1; }
+  const int np = build_phases(d, OH, OW, sn, sh, sw, geo);
+  if (np < 0) return np;
+  for (int i = 0; i < np; ++i) {
+    DirectPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    static_cast<PhaseGeom&>(ph) = geo[i];
+    ph.cin = d->Cin[0]; ph.x = x; ph.in_nchw = in_nchw; ph.in_scale = in_scale; ph.in_shift = in_shift;
+    ph.in_act = in_act; ph.pad_mode = d->pad_mode; ph.w = w_packed; ph.bias = bias; ph.y = y; ph.out_act = out_act;
+    ph.out_nchw = out_nchw; ph.ys_c = sc;
+    const int rc = launch_conv_direct_phase(ph, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != 0) return rc;
+  }
+  return 0;
+}

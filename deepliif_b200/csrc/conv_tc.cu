@@ -1,0 +1,390 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05) for sm_100a.
+//
+// Replaces, for every layer whose input-channel count is a multiple of 64, the cuDNN call behind
+// nn.Conv2d / nn.ConvTranspose2d in the reference generators / discriminators
+// (/root/reference/deepliif/models/networks.py:399-404 down convs, :490/:505 ResNet-block convs,
+//  :425-430 ConvTranspose upsampling, :576-600 UNet convs, :638-659 PatchGAN convs).
+//
+// Formulation.  One "phase" of a convolution is
+//     y[n, i, j, co] = sum_t sum_ci  x[n, i*st + dh_t, j*st + dw_t, ci] * w[t][co][ci]
+// over a tap list t (a stride-1/2 conv is one phase; a stride-2 ConvTranspose is four output-parity
+// phases with 1/2/2/4 (3x3) or 4 (4x4) taps each, so no zero-insertion MACs are executed).
+// GEMM view per CTA tile: M = 128 output pixels (a tile_n x tile_h x tile_w box), N = n_tile output
+// channels, K = taps x Cin, walked in 64-channel chunks.
+//
+// Data path.  Activations live in HBM as NHWC 16-bit planes (hi [, lo]); weights as [tap][Cout][Cin]
+// 16-bit planes (hi [, lo]).  One elected producer thread issues TMA tiled loads (5-D tensor map over
+// the activation: the halo / zero padding is the TMA out-of-bounds fill, the stride-2 case is a
+// (2C, W/2, 2, H/2, N) view of the same memory) into 128B-swizzled shared-memory stages guarded by
+// full/empty mbarriers.  One elected MMA thread issues tcgen05.mma (M=128, N=n_tile, K=16, fp32
+// accumulate in TMEM).  In split precision ("x3") every K step issues three MMAs
+// hi*hi + hi*lo + lo*hi, which restores ~fp32 products from 16-bit operands (the
+// 1e-3 parity gate cannot be met by single-pass TF32/BF16).  The accumulator is double-buffered in
+// TMEM (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of tile i+1.  Four epilogue
+// warps read TMEM with tcgen05.ld (one output pixel per thread), add the bias and store fp32 NHWC.
+// The kernel is persistent: grid = min(#tiles, #SMs), static round-robin tile schedule (tiles have
+// identical cost).
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace dlb {
+
+namespace {
+
+constexpr int kMaxTaps = 16;
+constexpr int kMaxStages = 8;
+constexpr int kKC = 64;                // channels per pipeline stage: 64 x 2 B = one 128 B swizzle row
+constexpr int kABytes = 128 * 128;     // one A plane of a stage: 128 pixels x 128 B
+constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kSmemLimit = 232448;     // 227 KB
+
+struct alignas(64) TcParams {
+  CUtensorMap a_hi[2];
+  CUtensorMap a_lo[2];
+  CUtensorMap b_hi;
+  CUtensorMap b_lo;
+  int ntaps, nsrc, planes, n_tile;
+  int kchunks[2];
+  int src_koff[2];
+  int dim_sel[5];                      // A-map dim i takes: 0 channel chunk, 1 w0, 2 h0, 3 n0, 4 nothing
+  int tap_off[kMaxTaps][5];
+  int tap_w[kMaxTaps];
+  int tile_w, tile_h, tile_n;
+  int tiles_w, tiles_h, tiles_n, tiles_c;
+  int N, OH, OW, cout_total;
+  long long ys_n, ys_h, ys_w, y_base;  // output addressing in elements
+  float* y;
+  const float* bias;
+  uint32_t idesc;
+  int stages;
+};
+
+struct TileCoord {
+  int w0, h0, n0, cout0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord c;
+  int tw = t % p.tiles_w; t /= p.tiles_w;
+  int th = t % p.tiles_h; t /= p.tiles_h;
+  int tn = t % p.tiles_n; t /= p.tiles_n;
+  c.w0 = tw * p.tile_w; c.h0 = th * p.tile_h; c.n0 = tn * p.tile_n; c.cout0 = t * p.n_tile;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b_bytes = p.n_tile * 128;
+  const int stage_bytes = p.planes * (kABytes + b_bytes);
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
+  const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nsrc; ++s) {
+      prefetch_tensormap(&p.a_hi[s]);
+      if (p.planes == 2) prefetch_tensormap(&p.a_lo[s]);
+    }
+    prefetch_tensormap(&p.b_hi);
+    if (p.planes == 2) prefetch_tensormap(&p.b_lo);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          int base[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const int sel = p.dim_sel[i];
+            base[i] = p.tap_off[tap][i] + (sel == 1 ? tc.w0 : sel == 2 ? tc.h0 : sel == 3 ? tc.n0 : 0);
+          }
+          for (int src = 0; src < p.nsrc; ++src) {
+            for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+              int c[5];
+#pragma unroll
+              for (int i = 0; i < 5; ++i) c[i] = base[i] + (p.dim_sel[i] == 0 ? kc * kKC : 0);
+              uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+              tma_load_5d(st, &p.a_hi[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+              if (p.planes == 2) tma_load_5d(st + kABytes, &p.a_lo[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+              const int kw = p.src_koff[src] + kc * kKC;
+              uint8_t* sb = st + p.planes * kABytes;
+              tma_load_3d(sb, &p.b_hi, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+              if (p.planes == 2) tma_load_3d(sb + b_bytes, &p.b_lo, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+              if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        uint32_t accumulate = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[s], ph);                // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + p.planes * kABytes;
+          const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int k = 0; k < kKC / 16; ++k) {
+            const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
+            const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
+            if (p.planes == 2) {
+              const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+              const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
+              umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);   // small terms first
+              umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
+              umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+            } else {
+              umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[s]);                 // smem stage free once these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> (+bias) -> fp32 NHWC =====================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_ph = 0;
+    const int m = q * 32 + lane;
+    const int w_l = m % p.tile_w;
+    const int h_l = (m / p.tile_w) % p.tile_h;
+    const int n_l = m / (p.tile_w * p.tile_h);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
+      const bool valid = (n < p.N) && (h < p.OH) && (w < p.OW);
+      float* yp = p.y + p.y_base + n * p.ys_n + h * p.ys_h + w * p.ys_w + tc.cout0;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      for (int c = 0; c < p.n_tile; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c, v);
+        tmem_ld_wait();
+        if (valid && (tc.cout0 + c) < p.cout_total) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+            if (p.bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + tc.cout0 + c + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(yp + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1; if (acc == 0) acc_ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool encode_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    set_error(buf);
+    return false;
+  }
+  return true;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+// One phase of a convolution on the tensor cores.  See internal.h for the argument contract.
+int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (num_sms == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int is_bf16 = (ph.fmt == DLB_FMT_BF16);
+  p.planes = ph.split ? 2 : 1;
+  p.nsrc = ph.nsrc;
+  p.ntaps = ph.ntaps;
+  if (ph.ntaps < 1 || ph.ntaps > kMaxTaps) return set_error("conv_tc: 1..16 taps per phase");
+  int cin_total = 0;
+  for (int s = 0; s < ph.nsrc; ++s) {
+    if (ph.cin[s] % kKC != 0) return set_error("conv_tc: every source needs Cin % 64 == 0");
+    p.kchunks[s] = ph.cin[s] / kKC;
+    p.src_koff[s] = cin_total;
+    cin_total += ph.cin[s];
+  }
+  if (ph.cout % 32 != 0) return set_error("conv_tc: Cout % 32 == 0 required");
+
+  // ---- tile shape: 128 output pixels = tile_n x tile_h x tile_w ---------------------------------
+  int tile_w = ph.OW >= 128 ? 128 : pow2_ceil(ph.OW);
+  int tile_h = 128 / tile_w; { int hp = pow2_ceil(ph.OH); if (tile_h > hp) tile_h = hp; }
+  int tile_n = 128 / (tile_w * tile_h);
+  p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n;
+  p.tiles_w = (ph.OW + tile_w - 1) / tile_w;
+  p.tiles_h = (ph.OH + tile_h - 1) / tile_h;
+  p.tiles_n = (ph.N + tile_n - 1) / tile_n;
+
+  int n_tile = ph.n_tile;
+  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : 64);
+  if (n_tile != 64 && n_tile != 128 && n_tile != 256) return set_error("conv_tc: n_tile must be 64/128/256");
+  p.n_tile = n_tile;
+  p.tiles_c = (ph.cout + n_tile - 1) / n_tile;
+  p.N = ph.N; p.OH = ph.OH; p.OW = ph.OW; p.cout_total = ph.cout;
+  p.ys_n = ph.ys_n; p.ys_h = ph.ys_h; p.ys_w = ph.ys_w; p.y_base = ph.y_base;
+  p.y = ph.y; p.bias = ph.bias;
+  p.idesc = make_idesc_f16(128, n_tile, is_bf16);
+
+  // ---- activation tensor maps ---------------------------------------------------------------------
+  for (int s = 0; s < ph.nsrc; ++s) {
+    const uint64_t C = ph.cin[s], W = ph.W, H = ph.H, N = ph.N;
+    uint64_t dims[5], strides[4]; uint32_t box[5];
+    if (ph.stride == 1) {
+      dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 1;
+      strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = H * W * C * 2; strides[3] = N * H * W * C * 2;
+      box[0] = kKC; box[1] = tile_w; box[2] = tile_h; box[3] = tile_n; box[4] = 1;
+      p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 2; p.dim_sel[3] = 3; p.dim_sel[4] = 4;
+    } else {
+      if ((W & 1) || (H & 1)) return set_error("conv_tc: stride-2 needs even H and W");
+      // x[n, 2*hh+hp, 2*ww+wp, c] viewed as (wp*C + c, ww, hp, hh, n)
+      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+      strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
+      box[0] = kKC; box[1] = tile_w; box[2] = 1; box[3] = tile_h; box[4] = tile_n;
+      p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 4; p.dim_sel[3] = 2; p.dim_sel[4] = 3;
+    }
+    if (!encode_map(&p.a_hi[s], ph.x_hi[s], is_bf16, 5, dims, strides, box)) return -1;
+    if (ph.split && !encode_map(&p.a_lo[s], ph.x_lo[s], is_bf16, 5, dims, strides, box)) return -1;
+  }
+  // ---- weight tensor map: [taps_total][Cout][Cin_total] ---------------------------------------------
+  {
+    uint64_t dims[3] = {(uint64_t)cin_total, (uint64_t)ph.cout, (uint64_t)ph.w_taps};
+    uint64_t strides[2] = {(uint64_t)cin_total * 2, (uint64_t)cin_total * ph.cout * 2};
+    uint32_t box[3] = {(uint32_t)kKC, (uint32_t)n_tile, 1};
+    if (!encode_map(&p.b_hi, ph.w_hi, is_bf16, 3, dims, strides, box)) return -1;
+    if (ph.split && !encode_map(&p.b_lo, ph.w_lo, is_bf16, 3, dims, strides, box)) return -1;
+  }
+  // ---- taps ---------------------------------------------------------------------------------------
+  for (int t = 0; t < ph.ntaps; ++t) {
+    const int dh = ph.tap_dh[t], dw = ph.tap_dw[t];
+    p.tap_w[t] = ph.tap_widx[t];
+    if (ph.stride == 1) {
+      p.tap_off[t][0] = 0; p.tap_off[t][1] = dw; p.tap_off[t][2] = dh; p.tap_off[t][3] = 0; p.tap_off[t][4] = 0;
+    } else {
+      // input row = 2*i + dh  ->  hp = dh mod 2, hh = i + floor(dh / 2)
+      const int hp = ((dh % 2) + 2) % 2, wp = ((dw % 2) + 2) % 2;
+      const int dhh = (dh - hp) / 2, dww = (dw - wp) / 2;
+      // channel offset wp*C only valid for a single source per distinct C; each source has its own map
+      p.tap_off[t][0] = 0;  // patched per source below through tap_wp
+      p.tap_off[t][1] = dww; p.tap_off[t][2] = hp; p.tap_off[t][3] = dhh; p.tap_off[t][4] = 0;
+      if (ph.nsrc != 1) return set_error("conv_tc: stride-2 supports one source");
+      p.tap_off[t][0] = wp * ph.cin[0];
+    }
+  }
+
+  const int b_bytes = n_tile * 128;
+  const int stage_bytes = p.planes * (kABytes + b_bytes);
+  int stages = (kSmemLimit - 1024 - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;
+  if (stages < 2) return set_error("conv_tc: not enough shared memory for 2 stages");
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 1024) != cudaSuccess)
+      return set_cuda_error("cudaFuncSetAttribute(conv_tc_kernel)");
+    attr_set = true;
+  }
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
+  int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("conv_tc_kernel launch");
+  return 0;
+}
+
+}  // namespace dlb

@@ -1,0 +1,65 @@
+// Internal (non-ABI) declarations shared by the translation units of libdeepliif_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/deepliif_b200.h"
+
+namespace dlb {
+
+int set_error(const char* msg);            // records msg for dlb_last_error(); returns DLB_ERR_INVALID
+int set_cuda_error(const char* where);     // records where + cudaGetErrorString; returns DLB_ERR_CUDA
+
+// One phase of a convolution in tap-list form:
+//   y[n,i,j,co] = sum_t sum_ci x[n, i*stride + dh_t, j*stride + dw_t, ci] * w[widx_t][co][ci]
+struct PhaseGeom {
+  int N, H, W;                 // input extents (per source; sources share N,H,W)
+  int OH, OW;                  // logical output extents of this phase
+  int stride;                  // 1 or 2 (input step per output pixel)
+  int ntaps;
+  int tap_dh[64], tap_dw[64], tap_widx[64];   // tensor-core path uses <= 16
+  int w_taps;                  // taps in the packed weight tensor (R*S)
+  long long ys_n, ys_h, ys_w, y_base;   // output element strides / base (NHWC, possibly strided phase)
+  int cout;
+};
+
+struct TcPhase : PhaseGeom {
+  int nsrc;
+  int cin[2];
+  const void* x_hi[2];
+  const void* x_lo[2];
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias;
+  float* y;
+  int fmt;                     // DLB_FMT_BF16 / DLB_FMT_FP16
+  int split;                   // 1: hi+lo planes, 3 MMAs per K step; 0: single pass
+  int n_tile;                  // 0 = auto
+  int max_stages;              // 0 = as many as fit
+  int max_ctas;                // 0 = #SMs
+};
+
+int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream);
+
+struct DirectPhase : PhaseGeom {
+  int cin;
+  const float* x;              // fp32 NHWC (or NCHW if in_nchw)
+  int in_nchw;
+  const float* in_scale;       // [N][cin] or null: fused input transform act(x*scale+shift)
+  const float* in_shift;
+  int in_act;
+  int pad_mode;                // DLB_PAD_ZERO / DLB_PAD_REFLECT
+  const float* w;              // fp32 [tap][cin][cout]
+  const float* bias;
+  float* y;
+  int out_act;
+  int out_nchw;                // y is NCHW [N][cout][OHf][OWf]; ys_* then address the (h,w) plane
+  long long ys_c;              // channel stride in elements (1 for NHWC)
+};
+
+int launch_conv_direct_phase(const DirectPhase& ph, cudaStream_t stream);
+
+}  // namespace dlb

@@ -1,0 +1,109 @@
+// Byte/integer ends of the path: the uint8 <-> fp32 tile conversions and the fused segmentation finish.
+//   dlb_u8_to_f32   deepliif.data.transform (data/__init__.py:133-138): ToTensor (/255) + Normalize(0.5, 0.5)
+//   dlb_f32_to_u8   util.tensor2im (util/util.py:130-135): trunc((x + 1) / 2 * 255) in fp32
+//   dlb_seg_finish  run_dask aggregation (models/__init__.py:338) + tensor2im + create_posneg_mask
+//                   (postprocessing.py:163-190, labels :87-95)
+// Pure HBM streams; bit-exact against oracle/pixel.py (same fp32 operation order, no FMA contraction).
+#include "internal.h"
+
+namespace dlb {
+namespace {
+
+__device__ __forceinline__ uint8_t quant_u8(float x) {
+  // numpy: (x + 1) / 2.0 * 255.0 in float32, then astype(uint8) (truncation toward zero)
+  float v = __fmul_rn(__fdiv_rn(__fadd_rn(x, 1.0f), 2.0f), 255.0f);
+  int i = static_cast<int>(v);            // trunc
+  return static_cast<uint8_t>(i);         // numpy wraps out-of-range modulo 256 on x86; inputs are tanh-bounded
+}
+
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int N, int H, int W) {
+  const long long total = static_cast<long long>(N) * H * W;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = idx / (static_cast<long long>(H) * W);
+    const long long hw = idx % (static_cast<long long>(H) * W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn(static_cast<float>(img[idx * 3 + c]), 255.0f);
+      out[(n * 3 + c) * H * W + hw] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    }
+  }
+}
+
+__global__ void f32_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int N, int H, int W) {
+  const long long total = static_cast<long long>(N) * H * W;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = idx / (static_cast<long long>(H) * W);
+    const long long hw = idx % (static_cast<long long>(H) * W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[idx * 3 + c] = quant_u8(x[(n * 3 + c) * H * W + hw]);
+  }
+}
+
+struct SegParams {
+  const float* segs[8];
+  float w[8];
+  int nseg, N, H, W, thresh;
+  float* seg_f32; uint8_t* seg_u8; uint8_t* mask;
+};
+
+__global__ void seg_finish_kernel(const SegParams p) {
+  const long long plane = static_cast<long long>(p.H) * p.W;
+  const long long total = static_cast<long long>(p.N) * plane;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = idx / plane, hw = idx % plane;
+    int u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long off = (n * 3 + c) * plane + hw;
+      float acc = 0.f;
+      for (int k = 0; k < p.nseg; ++k) acc = __fadd_rn(acc, __fmul_rn(p.segs[k][off], p.w[k]));
+      if (p.seg_f32) p.seg_f32[off] = acc;
+      const uint8_t q = quant_u8(acc);
+      u[c] = q;
+      if (p.seg_u8) p.seg_u8[idx * 3 + c] = q;
+    }
+    if (p.mask) {
+      uint8_t m = 50;                                   // LABEL_UNKNOWN
+      if (u[0] + u[2] > p.thresh && u[1] <= 80) m = (u[0] >= u[2]) ? 200 : 150;   // POSITIVE : NEGATIVE
+      p.mask[idx] = m;
+    }
+  }
+}
+
+int grid1d(long long total) {
+  long long g = (total + 255) / 256;
+  return static_cast<int>(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8);
+}
+
+}  // namespace
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int dlb_u8_to_f32(const uint8_t* img_nhwc, float* out_nchw, int N, int H, int W, dlb_stream_t stream) {
+  u8_to_f32_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(img_nhwc, out_nchw, N, H, W);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("u8_to_f32_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_f32_to_u8(const float* x_nchw, uint8_t* out_nhwc, int N, int H, int W, dlb_stream_t stream) {
+  f32_to_u8_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(x_nchw, out_nhwc, N, H, W);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("f32_to_u8_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_seg_finish(const float* const* segs, const float* weights, int nseg, int N, int H, int W, int thresh,
+                              float* seg_f32_nchw, uint8_t* seg_u8_nhwc, uint8_t* mask, dlb_stream_t stream) {
+  if (nseg < 1 || nseg > 8) return set_error("dlb_seg_finish: 1..8 seg inputs");
+  SegParams p;
+  memset(&p, 0, sizeof(p));
+  for (int k = 0; k < nseg; ++k) { p.segs[k] = segs[k]; p.w[k] = weights[k]; }
+  p.nseg = nseg; p.N = N; p.H = H; p.W = W; p.thresh = thresh;
+  p.seg_f32 = seg_f32_nchw; p.seg_u8 = seg_u8_nhwc; p.mask = mask;
+  seg_finish_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("seg_finish_kernel launch");
+  return 0;
+}

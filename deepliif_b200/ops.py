@@ -1,0 +1,168 @@
+"""Thin torch-tensor wrappers over the C ABI (include/deepliif_b200.h).
+
+PyTorch is used for device memory (caching allocator) and streams only; every wrapper enqueues exactly the
+library call on torch's current CUDA stream.  No wrapper has a PyTorch-op fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16, PAD_REFLECT, PAD_ZERO,
+                   ConvDesc, check)
+
+__all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
+           "conv_direct", "norm_stats", "norm_apply", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
+
+# kernel-launch counter (bench.py reports gpu_launches from this)
+LAUNCHES = {"count": 0}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dtype(fmt):
+    return torch.bfloat16 if fmt == FMT_BF16 else torch.float16
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise _lib.DeepliifB200Error("deepliif_b200 ops need contiguous CUDA tensors (no CPU path exists)")
+
+
+def conv_desc(N, H, W, cins, Cout, R, S, stride=1, pad=0, transposed=False, output_padding=0, pad_mode=PAD_ZERO):
+    cins = list(cins) if isinstance(cins, (list, tuple)) else [cins]
+    arr = (C.c_int * 2)(*(cins + [0] * (2 - len(cins))))
+    return ConvDesc(N, H, W, len(cins), arr, Cout, R, S, stride, pad, int(transposed), output_padding, pad_mode)
+
+
+def conv_out_shape(d):
+    oh, ow = C.c_int(), C.c_int()
+    check(_lib.load().dlb_conv_out_shape(C.byref(d), C.byref(oh), C.byref(ow)), "dlb_conv_out_shape")
+    return oh.value, ow.value
+
+
+def _cin_total(d):
+    return sum(d.Cin[i] for i in range(d.nsrc))
+
+
+def pack_weights_tc(d, w, fmt=FMT_BF16, split=True):
+    """w: fp32 CUDA, Conv2d (Cout,Cin,R,S) or ConvTranspose2d (Cin,Cout,R,S) -> (hi, lo) [R*S, Cout, Cin]."""
+    _need_cuda(w)
+    shape = (d.R * d.S, d.Cout, _cin_total(d))
+    hi = torch.empty(shape, dtype=_dtype(fmt), device=w.device)
+    lo = torch.empty(shape, dtype=_dtype(fmt), device=w.device) if split else None
+    check(_lib.load().dlb_pack_weights_tc(C.byref(d), _p(w), fmt, _p(hi), _p(lo), _stream()), "dlb_pack_weights_tc")
+    LAUNCHES["count"] += 1
+    return hi, lo
+
+
+def pack_weights_direct(d, w):
+    _need_cuda(w)
+    out = torch.empty((d.R * d.S, _cin_total(d), d.Cout), dtype=torch.float32, device=w.device)
+    check(_lib.load().dlb_pack_weights_direct(C.byref(d), _p(w), _p(out), _stream()), "dlb_pack_weights_direct")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_tile=0, out=None):
+    """Tensor-core conv.  xs_hi/xs_lo: lists (one per source) of NHWC 16-bit planes.  Returns fp32 NHWC."""
+    xs_hi = list(xs_hi) if isinstance(xs_hi, (list, tuple)) else [xs_hi]
+    xs_lo = (list(xs_lo) if isinstance(xs_lo, (list, tuple)) else [xs_lo]) if split else [None] * len(xs_hi)
+    _need_cuda(*xs_hi, *xs_lo, w_hi, w_lo, bias)
+    oh, ow = conv_out_shape(d)
+    if out is None:
+        out = torch.empty((d.N, oh, ow, d.Cout), dtype=torch.float32, device=w_hi.device)
+    hi_arr = (C.c_void_p * 2)(*[x.data_ptr() for x in xs_hi] + [None] * (2 - len(xs_hi)))
+    lo_arr = (C.c_void_p * 2)(*[(x.data_ptr() if x is not None else None) for x in xs_lo] + [None] * (2 - len(xs_lo)))
+    check(_lib.load().dlb_conv_tc_fwd(C.byref(d), hi_arr, lo_arr, _p(w_hi), _p(w_lo) if split else None, _p(bias),
+                                      _p(out), fmt, int(split), n_tile, _stream()), "dlb_conv_tc_fwd")
+    LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    return out
+
+
+def conv_direct(d, x, w_packed, bias=None, in_nchw=False, in_scale=None, in_shift=None, in_act=ACT_NONE,
+                out_act=ACT_NONE, out_nchw=False, out=None):
+    _need_cuda(x, w_packed, bias, in_scale, in_shift)
+    oh, ow = conv_out_shape(d)
+    if out is None:
+        shape = (d.N, d.Cout, oh, ow) if out_nchw else (d.N, oh, ow, d.Cout)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    check(_lib.load().dlb_conv_direct_fwd(C.byref(d), _p(x), int(in_nchw), _p(in_scale), _p(in_shift), in_act,
+                                          _p(w_packed), _p(bias), _p(out), out_act, int(out_nchw), _stream()),
+          "dlb_conv_direct_fwd")
+    LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    return out
+
+
+def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5):
+    """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift."""
+    _need_cuda(y, gamma, beta)
+    N, H, W, Cc = y.shape
+    lib = _lib.load()
+    ws_bytes = lib.dlb_norm_stats_workspace(N, H * W, Cc)
+    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=y.device)
+    scale = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
+    shift = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
+    check(lib.dlb_norm_stats(_p(y), N, H * W, Cc, int(pooled), _p(gamma), _p(beta), float(eps), _p(scale), _p(shift),
+                             _p(ws), ws_bytes, _stream()), "dlb_norm_stats")
+    LAUNCHES["count"] += 2
+    return scale, shift
+
+
+def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=False, want_split=True,
+               fmt=FMT_BF16, pad=0, pad_mode=PAD_ZERO, need_lo=True):
+    """out = act(y*scale+shift) (+ residual) -> (out_f32 | None, hi | None, lo | None)."""
+    _need_cuda(y, scale, shift, residual)
+    N, H, W, Cc = y.shape
+    f32 = torch.empty_like(y) if want_f32 else None
+    hi = lo = None
+    if want_split:
+        shp = (N, H + 2 * pad, W + 2 * pad, Cc)
+        hi = torch.empty(shp, dtype=_dtype(fmt), device=y.device)
+        lo = torch.empty(shp, dtype=_dtype(fmt), device=y.device) if need_lo else None
+    check(_lib.load().dlb_norm_apply(_p(y), _p(scale), _p(shift), act, _p(residual), _p(f32), _p(hi), _p(lo), fmt,
+                                     N, H, W, Cc, pad, pad_mode, _stream()), "dlb_norm_apply")
+    LAUNCHES["count"] += 1
+    return f32, hi, lo
+
+
+def u8_to_f32(img_nhwc):
+    _need_cuda(img_nhwc)
+    N, H, W, _ = img_nhwc.shape
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=img_nhwc.device)
+    check(_lib.load().dlb_u8_to_f32(_p(img_nhwc), _p(out), N, H, W, _stream()), "dlb_u8_to_f32")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def f32_to_u8(x_nchw):
+    _need_cuda(x_nchw)
+    N, _, H, W = x_nchw.shape
+    out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x_nchw.device)
+    check(_lib.load().dlb_f32_to_u8(_p(x_nchw), _p(out), N, H, W, _stream()), "dlb_f32_to_u8")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def seg_finish(segs, weights, thresh=120, want_f32=True, want_u8=True, want_mask=True):
+    """segs: list of fp32 NCHW [N,3,H,W]; returns (seg_f32 NCHW, seg_u8 NHWC, mask [N,H,W])."""
+    _need_cuda(*segs)
+    N, _, H, W = segs[0].shape
+    dev = segs[0].device
+    f32 = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev) if want_f32 else None
+    u8 = torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+    mask = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    ptrs = (C.c_void_p * len(segs))(*[s.data_ptr() for s in segs])
+    ws = (C.c_float * len(segs))(*[float(w) for w in weights])
+    check(_lib.load().dlb_seg_finish(ptrs, ws, len(segs), N, H, W, int(thresh), _p(f32), _p(u8), _p(mask), _stream()),
+          "dlb_seg_finish")
+    LAUNCHES["count"] += 1
+    return f32, u8, mask

@@ -1,0 +1,117 @@
+/* deepliif_b200 — C ABI of the B200-native (sm_100a) kernels behind the DeepLIIF tile-parallel cGAN path.
+ *
+ * The reference (nadeemlab/DeepLIIF) has no FFI / plugin registry: its hot path is
+ * nn.Sequential.forward over nn.Conv2d / nn.ConvTranspose2d / BatchNorm2d|InstanceNorm2d / ReLU /
+ * LeakyReLU / Tanh modules (deepliif/models/networks.py:386-446, 479-513, 576-615, 638-660).  The seam
+ * a maintainer would bind is therefore "one library call per nn.Module group"; every entry point below
+ * names the reference module(s) whose forward it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch caching allocator in practice);
+ *     no entry point allocates, frees or synchronises; every call only enqueues work on `stream`;
+ *   - activations are NHWC.  fp32 tensors are plain float; "split" tensors are two 16-bit planes
+ *     (hi, lo) with hi = round16(x), lo = round16(x - hi), format DLB_FMT_BF16 or DLB_FMT_FP16;
+ *   - return value 0 = ok, negative = error (message via dlb_last_error(), thread-local);
+ *   - re-entrant across streams; one process per GPU is the expected deployment.
+ */
+#ifndef DEEPLIIF_B200_H_
+#define DEEPLIIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dlb_stream_t;
+
+#define DLB_OK 0
+#define DLB_ERR_INVALID (-1)
+#define DLB_ERR_CUDA (-2)
+
+enum { DLB_FMT_BF16 = 0, DLB_FMT_FP16 = 1 };
+enum { DLB_ACT_NONE = 0, DLB_ACT_RELU = 1, DLB_ACT_LRELU02 = 2, DLB_ACT_TANH = 3 };
+enum { DLB_PAD_ZERO = 0, DLB_PAD_REFLECT = 1 };
+
+/* Geometry of one nn.Conv2d (transposed = 0) or nn.ConvTranspose2d (transposed = 1).
+ * `nsrc`/`Cin[]`: the input may be given as up to two tensors concatenated along channels (the UNet
+ * skip connection torch.cat([x, model(x)], 1), networks.py:615, is consumed without materialising it). */
+typedef struct dlb_conv_desc {
+  int N, H, W;
+  int nsrc;
+  int Cin[2];
+  int Cout;
+  int R, S;
+  int stride;          /* 1 or 2 */
+  int pad;             /* Conv2d/ConvTranspose2d `padding` */
+  int transposed;
+  int output_padding;  /* ConvTranspose2d only */
+  int pad_mode;        /* DLB_PAD_ZERO, or DLB_PAD_REFLECT (= nn.ReflectionPad2d(pad) + conv padding 0) */
+} dlb_conv_desc;
+
+const char* dlb_last_error(void);
+int dlb_version(void);
+
+/* Output extent of the layer (PyTorch formulas). */
+int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW);
+
+/* ---- weight repacking (once per checkpoint load) ---------------------------------------------------
+ * w: fp32, PyTorch layout: Conv2d (Cout, Cin_total, R, S); ConvTranspose2d (Cin_total, Cout, R, S).
+ * tc:     two 16-bit planes [R*S][Cout][Cin_total]  (K-major B operand of tcgen05.mma)
+ * direct: fp32 [R*S][Cin_total][Cout] */
+int dlb_pack_weights_tc(const dlb_conv_desc* d, const float* w, int fmt, void* w_hi, void* w_lo, dlb_stream_t stream);
+int dlb_pack_weights_direct(const dlb_conv_desc* d, const float* w, float* w_packed, dlb_stream_t stream);
+
+/* ---- convolution forward ---------------------------------------------------------------------------
+ * Replaces nn.Conv2d.forward / nn.ConvTranspose2d.forward (+bias) of networks.py:399-404, 425-430,
+ * 490, 505, 576-600, 638-659 on the tcgen05 tensor cores.  Requires Cin[i] % 64 == 0, Cout % 32 == 0,
+ * zero padding (reflect padding is produced by dlb_norm_apply into a padded operand buffer).
+ * x_hi/x_lo: per source 16-bit NHWC planes; split != 0 selects the 3-MMA hi/lo scheme (fp32-grade
+ * products), split == 0 a single pass on the hi planes.  y: fp32 NHWC [N, OH, OW, Cout].
+ * n_tile: 0 = auto, or 64/128/256 (UMMA N). */
+int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo, const void* w_hi,
+                    const void* w_lo, const float* bias, float* y, int fmt, int split, int n_tile,
+                    dlb_stream_t stream);
+
+/* fp32 CUDA-core convolution for the layers tensor cores cannot tile (Cin = 3 stem, networks.py:386-397;
+ * Cout = 3 head + Tanh, :438-444; PatchGAN first/last convs, :638, :659).  Fuses the producer's
+ * normalisation + activation on the input side: x' = act_in(x * in_scale[n,c] + in_shift[n,c]) (zero /
+ * reflect padding applies to x'), bias, optional output activation, optional NCHW input / output so the
+ * network boundary needs no layout pass.  Single source (nsrc == 1). */
+int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, const float* in_scale,
+                        const float* in_shift, int in_act, const float* w_packed, const float* bias, float* y,
+                        int out_act, int out_nchw, dlb_stream_t stream);
+
+/* ---- normalisation -----------------------------------------------------------------------------------
+ * Replaces BatchNorm2d (batch statistics) / InstanceNorm2d of networks.py:25-44.
+ * dlb_norm_stats: y fp32 NHWC [N, HW, C] -> per-(n,c) scale/shift such that norm(y) = y*scale + shift,
+ *   scale = gamma * rstd, shift = beta - mean * scale (gamma/beta may be NULL = 1/0), biased variance.
+ *   pooled != 0: statistics over N*HW (training-mode BatchNorm2d, N > 1), replicated for every n.
+ *   Deterministic (fixed-order two-level reduction, no atomics).  workspace: dlb_norm_stats_workspace bytes.
+ * dlb_norm_apply: out = act(y*scale + shift) (+ residual), written as fp32 (out_f32) and/or as split
+ *   16-bit planes (out_hi/out_lo) for the next tensor-core conv; `pad` > 0 writes the planes into a
+ *   [N, H+2pad, W+2pad, C] buffer with a reflected (DLB_PAD_REFLECT) or zero border. */
+size_t dlb_norm_stats_workspace(int N, int HW, int C);
+int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
+                   float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes,
+                   dlb_stream_t stream);
+int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
+                   float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
+                   int pad_mode, dlb_stream_t stream);
+
+/* ---- pixel ends ------------------------------------------------------------------------------------
+ * dlb_u8_to_f32: deepliif.data.transform (data/__init__.py:133-138): uint8 HWC -> fp32 NCHW in [-1,1].
+ * dlb_seg_finish: run_dask seg aggregation (models/__init__.py:338) + tensor2im quantisation
+ *   (util/util.py:130-135) + create_posneg_mask (postprocessing.py:163-190) in one pass:
+ *   seg = sum_k w_k * segs[k] (fp32, list order); u8 = trunc((seg+1)/2*255); mask from u8.
+ *   segs: nseg device pointers to fp32 NCHW [N,3,H,W]; seg_f32 / seg_u8 (NHWC) / mask may be NULL. */
+int dlb_u8_to_f32(const uint8_t* img_nhwc, float* out_nchw, int N, int H, int W, dlb_stream_t stream);
+int dlb_f32_to_u8(const float* x_nchw, uint8_t* out_nhwc, int N, int H, int W, dlb_stream_t stream);
+int dlb_seg_finish(const float* const* segs, const float* weights, int nseg, int N, int H, int W, int thresh,
+                   float* seg_f32_nchw, uint8_t* seg_u8_nhwc, uint8_t* mask, dlb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPLIIF_B200_H_ */

@@ -1,0 +1,196 @@
+"""GPU parity tests (-m gpu): every kernel behind the C ABI against the fp32 CPU oracle on seeded inputs.
+
+Floating point: tolerances are written next to each assert.  Integer/byte work: bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import ops as _ops
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(shape, generator=g) * 2 - 1) * scale
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def split16(x, dtype):
+    hi = x.to(dtype)
+    lo = (x - hi.float()).to(dtype)
+    return hi, lo
+
+
+# ------------------------------------------------------------------------------------------------
+# norm statistics + apply
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W,C,pooled", [(2, 16, 16, 64, False), (1, 128, 128, 256, False), (3, 17, 9, 128, True),
+                                             (2, 8, 8, 512, False), (2, 30, 30, 4, True)])
+def test_norm_stats(ops, N, H, W, C, pooled):
+    y = _rand((N, H, W, C), 1) * 3 + _rand((1, 1, 1, C), 2) * 5     # per-channel offsets: mean >> 0
+    gamma = 1 + 0.1 * _rand((C,), 3); beta = 0.1 * _rand((C,), 4)
+    sc, sh = ops.norm_stats(y.cuda(), gamma.cuda(), beta.cuda(), pooled)
+    yd = y.double()
+    dims = (0, 1, 2) if pooled else (1, 2)
+    mean = yd.mean(dim=dims, keepdim=True); var = yd.var(dim=dims, unbiased=False, keepdim=True)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    sc_ref = (gamma.double() * rstd).expand(N, 1, 1, C).reshape(N, C)
+    sh_ref = (beta.double() - mean * gamma.double() * rstd).expand(N, 1, 1, C).reshape(N, C)
+    assert (sc.cpu().double() - sc_ref).abs().max() < 1e-5 * sc_ref.abs().max()
+    assert (sh.cpu().double() - sh_ref).abs().max() < 2e-5 * max(1.0, sh_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16", "fp16"])
+@pytest.mark.parametrize("pad,pad_mode", [(0, 0), (1, 1), (1, 0), (3, 1)])
+def test_norm_apply(ops, fmt_name, pad, pad_mode):
+    fmt = ops.FMT_BF16 if fmt_name == "bf16" else ops.FMT_FP16
+    dt = torch.bfloat16 if fmt_name == "bf16" else torch.float16
+    N, H, W, C = 2, 12, 10, 64
+    y = _rand((N, H, W, C), 5) * 2
+    sc = 1 + 0.2 * _rand((N, C), 6); sh = 0.3 * _rand((N, C), 7); res = _rand((N, H, W, C), 8)
+    f32, hi, lo = ops.norm_apply(y.cuda(), sc.cuda(), sh.cuda(), ops.ACT_RELU, res.cuda(), want_f32=True,
+                                 want_split=True, fmt=fmt, pad=pad, pad_mode=pad_mode)
+    ref = torch.relu(torch.addcmul(sh[:, None, None, :], y, sc[:, None, None, :])) + res
+    assert (f32.cpu() - ref).abs().max() < 1e-6
+    refp = nchw(ref)
+    if pad:
+        refp = F.pad(refp, (pad,) * 4, mode="reflect" if pad_mode == 1 else "constant")
+    refp = nhwc(refp)
+    # the two planes must reproduce the fp32 value to ~2^-16 (bf16) / 2^-21 (fp16) relative; use the GPU's f32
+    got = hi.float().cpu() + lo.float().cpu()
+    tol = 2 ** -15 if fmt_name == "bf16" else 2 ** -20
+    assert ((got - refp).abs() <= tol * refp.abs() + 1e-7).all()
+    h_ref, l_ref = split16(refp, dt)
+    # hi plane is exactly round-to-nearest of the value (allow the 1e-6 fp32 fma difference to flip nothing big)
+    assert (hi.float().cpu() - h_ref.float()).abs().max() <= tol * 4 * refp.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------
+# direct fp32 conv
+# ------------------------------------------------------------------------------------------------
+DIRECT_CASES = [
+    # name, N, H, Cin, Cout, R, stride, pad, transposed, outpad, pad_mode
+    ("stem7_zero", 2, 40, 3, 64, 7, 1, 3, False, 0, 0),
+    ("stem7_reflect", 1, 33, 3, 64, 7, 1, 3, False, 0, 1),
+    ("head7", 2, 40, 64, 3, 7, 1, 3, False, 0, 1),
+    ("c3s1", 1, 20, 32, 48, 3, 1, 1, False, 0, 0),
+    ("c3s2", 2, 32, 16, 24, 3, 2, 1, False, 0, 0),
+    ("c4s2", 1, 32, 6, 64, 4, 2, 1, False, 0, 0),
+    ("c4s1_last", 1, 31, 64, 1, 4, 1, 1, False, 0, 0),
+    ("ct3s2", 1, 16, 32, 16, 3, 2, 1, True, 1, 0),
+    ("ct4s2_rgb", 2, 16, 128, 3, 4, 2, 1, True, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", DIRECT_CASES, ids=[c[0] for c in DIRECT_CASES])
+def test_conv_direct(ops, case):
+    name, N, H, Cin, Cout, R, st, pad, tr, op, pm = case
+    x = _rand((N, Cin, H, H), 11)
+    w = _rand((Cin, Cout, R, R) if tr else (Cout, Cin, R, R), 12, 0.1)
+    b = _rand((Cout,), 13, 0.1)
+    d = ops.conv_desc(N, H, H, Cin, Cout, R, R, st, pad, tr, op, pm)
+    wp = ops.pack_weights_direct(d, w.cuda())
+    y = ops.conv_direct(d, nhwc(x).cuda(), wp, b.cuda())
+    if tr:
+        ref = F.conv_transpose2d(x, w, b, stride=st, padding=pad, output_padding=op)
+    elif pm == 1:
+        ref = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), w, b, stride=st)
+    else:
+        ref = F.conv2d(x, w, b, stride=st, padding=pad)
+    err = (nchw(y.cpu()) - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
+    # NCHW in / NCHW out + fused input transform + tanh
+    sc = 1 + 0.2 * _rand((N, Cin), 14); sh = 0.2 * _rand((N, Cin), 15)
+    y2 = ops.conv_direct(d, x.cuda(), wp, b.cuda(), in_nchw=True, in_scale=sc.cuda(), in_shift=sh.cuda(),
+                         in_act=ops.ACT_RELU, out_act=ops.ACT_TANH, out_nchw=True)
+    xt = torch.relu(x * sc[:, :, None, None] + sh[:, :, None, None])
+    if tr:
+        ref2 = F.conv_transpose2d(xt, w, b, stride=st, padding=pad, output_padding=op)
+    elif pm == 1:
+        ref2 = F.conv2d(F.pad(xt, (pad,) * 4, mode="reflect"), w, b, stride=st)
+    else:
+        ref2 = F.conv2d(xt, w, b, stride=st, padding=pad)
+    err2 = (y2.cpu() - torch.tanh(ref2)).abs().max().item()
+    assert err2 < 2e-5, err2
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core conv (tcgen05)
+# ------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # name, N, H, W, cins, Cout, R, stride, pad, transposed, outpad, n_tile
+    ("k3s1_64_64_w16", 1, 8, 16, [64], 64, 3, 1, 1, False, 0, 0),
+    ("k1s1_64_64", 2, 8, 16, [64], 64, 1, 1, 0, False, 0, 0),
+    ("k3s1_256_256_w128", 1, 4, 128, [256], 256, 3, 1, 1, False, 0, 0),
+    ("k3s1_256_256_n128", 1, 4, 128, [256], 256, 3, 1, 1, False, 0, 128),
+    ("k3s1_128_96_w32", 3, 32, 32, [128], 96, 3, 1, 1, False, 0, 0),
+    ("k3s2_64_128", 2, 64, 64, [64], 128, 3, 2, 1, False, 0, 0),
+    ("k4s2_128_256", 1, 32, 32, [128], 256, 4, 2, 1, False, 0, 0),
+    ("k4s1_256_512_w15", 1, 16, 16, [256], 512, 4, 1, 1, False, 0, 0),
+    ("ct3s2_256_128", 1, 16, 16, [256], 128, 3, 2, 1, True, 1, 0),
+    ("ct4s2_cat_512_128", 2, 8, 8, [256, 256], 128, 4, 2, 1, True, 0, 0),
+    ("k4s2_tiny_2x2", 5, 4, 4, [512], 512, 4, 2, 1, False, 0, 0),
+    ("ct4s2_tiny_1x1", 3, 1, 1, [512], 512, 4, 2, 1, True, 0, 0),
+    ("k3s1_w200", 1, 3, 200, [64], 64, 3, 1, 1, False, 0, 0),
+]
+
+
+def _tc_ref(x, w, b, st, pad, tr, op):
+    if tr:
+        return F.conv_transpose2d(x, w, b, stride=st, padding=pad, output_padding=op)
+    return F.conv2d(x, w, b, stride=st, padding=pad)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tc(ops, case, prec):
+    name, N, H, W, cins, Cout, R, st, pad, tr, op, n_tile = case
+    fmt = ops.FMT_FP16 if prec.startswith("fp16") else ops.FMT_BF16
+    dt = torch.float16 if prec.startswith("fp16") else torch.bfloat16
+    split = prec.endswith("x3")
+    Cin = sum(cins)
+    x = _rand((N, Cin, H, W), 21)
+    w = _rand((Cin, Cout, R, R) if tr else (Cout, Cin, R, R), 22, 0.05)
+    b = _rand((Cout,), 23, 0.1)
+    d = ops.conv_desc(N, H, W, cins, Cout, R, R, st, pad, tr, op)
+    w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), fmt, split)
+    xs = torch.split(x, cins, dim=1)
+    planes = [split16(nhwc(xi), dt) for xi in xs]
+    y = ops.conv_tc(d, [p[0].cuda() for p in planes], [p[1].cuda() for p in planes], w_hi, w_lo, b.cuda(), fmt, split,
+                    n_tile)
+    torch.cuda.synchronize()
+    got = nchw(y.cpu())
+    ref = _tc_ref(x.double(), w.double(), b.double(), st, pad, tr, op).float()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    if split:
+        # hi/lo products: dropped term lo*lo ~ 2^-16 (bf16) / 2^-22 (fp16) relative per product; measured on
+        # B200 the tensor-core fp32 accumulation itself leaves ~1e-5 relative at K = 2304..8192, so the
+        # fp16 split buys only ~2x over bf16 (first_run log: 3.3e-5 of scale 3.8 at K = 4096).
+        tol = 3e-5 * scale
+        assert err < tol, (err, scale)
+    else:
+        # single pass == conv of the rounded operands with fp32 accumulation
+        xr = torch.cat([p[0].float() for p in planes], dim=3)
+        ref1 = _tc_ref(nchw(xr).double(), w.to(dt).double(), b.double(), st, pad, tr, op).float()
+        assert (got - ref1).abs().max().item() < 2e-5 * scale

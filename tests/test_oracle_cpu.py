@@ -1,0 +1,123 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden fixtures generated from the real reference
+(oracle/gen_golden.py), and the C-ABI library's symbol table against include/deepliif_b200.h."""
+import glob
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, pixel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-5   # fp32 oracle vs fp32 reference (different CPU kernels / thread counts may reorder sums)
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def _x(meta, c=3):
+    g = torch.Generator().manual_seed(meta["x_seed"])
+    return torch.rand((meta["n"], c, meta["hw"], meta["hw"]), generator=g) * 2 - 1
+
+
+RESNET_CASES = ["resnet9_batch_zero_64", "resnet9_inst_zero_64", "resnet9_batch_reflect_64", "resnet2_inst_reflect_32"]
+
+
+@pytest.mark.parametrize("name", RESNET_CASES)
+def test_resnet_oracle_matches_reference_golden(name):
+    z, m = _load(name)
+    cfg = m["cfg"]
+    sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, cfg["n_blocks"], cfg["norm"], cfg["use_dropout"],
+                                                       cfg["padding_type"]), m["seed"], m["init"])
+    with torch.no_grad():
+        y = nets.resnet_forward(_x(m), sd, norm_mode="sample", **cfg).numpy()
+    assert np.abs(y - z["y"]).max() <= TOL
+
+
+def test_resnet_oracle_full_size_subsample():
+    z, m = _load("resnet9_inst_zero_512")
+    cfg = m["cfg"]
+    sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 9, cfg["norm"], cfg["use_dropout"], cfg["padding_type"]),
+                              m["seed"], m["init"])
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        y = nets.resnet_forward(_x(m), sd, norm_mode="sample", **cfg).numpy()
+    assert np.abs(y[:, :, ::8, ::8] - z["y"]).max() <= TOL
+    assert abs(float(y.astype(np.float64).sum()) - m["sum"]) <= 1e-2 * max(1.0, abs(m["sum"]))
+
+
+@pytest.mark.parametrize("name", ["unet256_batch_256", "unet128_inst_128"])
+def test_unet_oracle_matches_reference_golden(name):
+    z, m = _load(name)
+    sd = nets.make_state_dict(nets.unet_param_shapes(m["num_downs"], 64, 3, 3, m["norm"]), m["seed"], m["init"])
+    with torch.no_grad():
+        y = nets.unet_forward(_x(m), sd, num_downs=m["num_downs"], norm=m["norm"], norm_mode="sample").numpy()
+    s = m["subsample"]
+    assert np.abs(y[:, :, ::s, ::s] - z["y"]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", ["dbasic_batch_128", "dn4_inst_128"])
+def test_discriminator_oracle_matches_reference_golden(name):
+    z, m = _load(name)
+    sd = nets.make_state_dict(nets.nlayer_d_param_shapes(m["n_layers"], 64, 6, m["norm"]), m["seed"], m["init"])
+    with torch.no_grad():
+        y = nets.nlayer_d_forward(_x(m, 6), sd, n_layers=m["n_layers"], norm=m["norm"], norm_mode="batch").numpy()
+    assert np.abs(y - z["y"]).max() <= TOL
+
+
+def test_pixel_oracle_bit_exact():
+    z = np.load(os.path.join(GOLD, "pixel_ends.npz"))
+    assert np.array_equal(pixel.transform(z["img"]), z["transform"])
+    assert np.array_equal(pixel.tensor2im(z["f"]), z["tensor2im"])
+    assert np.array_equal(pixel.create_posneg_mask(z["seg"], 120), z["mask"])
+    # edge cases of the threshold rule (postprocessing.py:184-188)
+    seg = np.array([[[60, 80, 61], [61, 80, 60], [60, 81, 61], [60, 0, 60], [255, 0, 255], [0, 0, 0]]], np.uint8)
+    assert pixel.create_posneg_mask(seg).tolist() == [[150, 200, 50, 50, 200, 50]]
+
+
+def test_resnet_gflop_matches_survey():
+    assert abs(nets.resnet_gflop(512) - 396.41) < 0.05
+
+
+def test_state_dict_keys_match_survey_counts():
+    assert len(nets.resnet_param_shapes(norm="batch", use_dropout=True)) == 140
+    assert len(nets.resnet_param_shapes(norm="instance", use_dropout=False)) == 48
+    assert len(nets.unet_param_shapes(9, norm="batch")) == 94
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    """The C-ABI .so loads on a CPU-only box and exports exactly what include/deepliif_b200.h declares."""
+    from deepliif_b200 import _lib
+    lib = _lib.load()
+    assert lib.dlb_version() >= 100
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "include", "deepliif_b200.h")).read()
+    declared = set(re.findall(r"\b(dlb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_conv_out_shape_matches_pytorch(lib_built):
+    from deepliif_b200 import ops
+    for (H, R, st, pad, tr, op) in [(512, 7, 1, 3, False, 0), (512, 3, 2, 1, False, 0), (128, 3, 2, 1, True, 1),
+                                    (64, 4, 2, 1, True, 0), (64, 4, 1, 1, False, 0), (63, 4, 1, 1, False, 0)]:
+        d = ops.conv_desc(1, H, H, 8, 8, R, R, st, pad, tr, op)
+        x = torch.zeros(1, 8, H, H)
+        if tr:
+            ref = torch.nn.functional.conv_transpose2d(x, torch.zeros(8, 8, R, R), stride=st, padding=pad, output_padding=op)
+        else:
+            ref = torch.nn.functional.conv2d(x, torch.zeros(8, 8, R, R), stride=st, padding=pad)
+        assert ops.conv_out_shape(d) == tuple(ref.shape[2:])
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never import the oracle (tier rule)."""
+    root = os.path.join(os.path.dirname(GOLD), "..", "deepliif_b200")
+    for path in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
