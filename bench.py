@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — 512x512 IHC tiles/sec through the five-head ResNet-9 generator path (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+One step = one batch of `--batch` synthetic 512x512x3 tiles through 5 ResNet-9 generators ("flat-5":
+out_i = G_i(tile)), seg quantise + posneg mask.  Prints ONE JSON line (rank 0).
+  value : tiles/s, inputs resident in HBM (fp32 NCHW), whole job over all ranks (weak scaling: each rank
+          processes its own batch; tiles shard with no data-path collective)
+  e2e   : the same through TilePipeline.infer_u8 — pinned-host uint8 tiles in, H2D, transform, generators,
+          quantise, D2H of uint8 results inside the timed region
+  roofline : the ResNet-block conv kernel (conv_tc, 256->256 3x3 @128x128), algorithmic FLOPs / measured
+          launch time (CUDA events on the launching stream) / measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline : oracle port (plain torch fp32 CPU, N=1 per call = reference semantics) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HW = 512
+RESNET_GFLOP = 396.41          # SURVEY.md §8d, algorithmic, per tile per generator
+BLOCK_CONV_FLOP = 2 * 16384 * 256 * 2304   # one 256->256 3x3 conv @128x128, per tile
+N_HEADS = 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="tiles per step per GPU (BASELINE configs[1]: 32)")
+    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline-events", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1431.0), d.get("hbm_gbs", 6572.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_flat5_tiles_per_s(norm, steps, warmup):
+    """Bounded sample: 1 tile x 5 ResNet-9 generators, one call per generator at N=1 (reference semantics)."""
+    from oracle import nets
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = dict(n_blocks=9, norm=norm, use_dropout=False, padding_type="zero")
+    shapes = nets.resnet_param_shapes(3, 3, 64, 9, norm, False, "zero")
+    sds = [nets.make_state_dict(shapes, 100 + i) for i in range(N_HEADS)]
+    x = torch.rand((1, 3, HW, HW), generator=torch.Generator().manual_seed(1234)) * 2 - 1
+    with torch.no_grad():
+        for _ in range(warmup):
+            nets.resnet_forward(x, sds[0], norm_mode="sample", **cfg)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for sd in sds:
+                nets.resnet_forward(x, sd, norm_mode="sample", **cfg)
+        dt = time.perf_counter() - t0
+    return steps / dt, dt / steps, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 1))
+    v, s_per_step, cores = cpu_flat5_tiles_per_s(args.norm, steps, warmup)
+    sample = "1 tile (512x512x3) x 5 ResNet-9 generators per step, N=1 per call, torch fp32 CPU (oracle port)"
+    line = {"impl": "reference", "metric": "512x512 IHC tiles/sec (flat-5 ResNet-9 generators)", "value": v,
+            "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "flat-5 ResNet-9 inference, 512x512 tiles", "norm": args.norm, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from deepliif_b200 import engine as eng_mod
+    from deepliif_b200 import ops
+    from deepliif_b200.models import networks
+    from deepliif_b200.pipeline import TilePipeline
+
+    # five ResNet-9 heads, random init N(0, 0.02) exactly as the reference's define_G would (no checkpoints offline)
+    gens = []
+    for i in range(N_HEADS):
+        torch.manual_seed(i)
+        g = networks.define_G(3, 3, 64, "resnet_9blocks", args.norm, args.norm == "batch", "normal", 0.02, [], "zero")
+        g.precision = args.precision
+        g.to(dev).eval()
+        gens.append(g)
+    engines = [g.engine() for g in gens]
+    pipe = TilePipeline([e.forward for e in engines], micro_batch=args.micro_batch)
+
+    B = args.batch
+    # rotate over distinct input batches so the inputs of consecutive steps never sit in the 126 MB L2
+    n_rot = 3
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    xs = [(torch.rand((B, 3, HW, HW), generator=gen) * 2 - 1).to(dev) for _ in range(n_rot)]
+    u8s = [torch.randint(0, 256, (B, HW, HW, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_rot)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident metric ---------------------------------------------------------------------
+    for w in range(args.warmup):
+        pipe.forward_device(xs[w % n_rot])
+    barrier()
+    roof_pairs = []
+    if not args.no_roofline_events:
+        eng_mod.BLOCK_CONV_EVENTS = roof_pairs        # engine records (start, end) around block-conv launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        pipe.forward_device(xs[k % n_rot])
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES["count"] - l0
+    eng_mod.BLOCK_CONV_EVENTS = None
+    t_ms = e0.elapsed_time(e1)
+    # ---- end-to-end metric (host uint8 in, host uint8 out) ------------------------------------------------
+    out_host = pipe.infer_u8(u8s[0])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(args.steps):
+        out_host = pipe.infer_u8(u8s[k % n_rot], out_host)
+    f1.record()
+    barrier()
+    clocks = sampler.stop()
+    t2_ms = f0.elapsed_time(f1)
+    h2d = u8s[0].numel()
+    d2h = sum(v.numel() for v in out_host.values())
+
+    tt = torch.tensor([t_ms, t2_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, t2_ms = tt.tolist()
+    tiles = B * world * args.steps
+    value = tiles / (t_ms / 1e3)
+    e2e = tiles / (t2_ms / 1e3)
+
+    if rank == 0:
+        peak_tf, peak_hbm, peak_kind = peaks()
+        roof = None
+        if roof_pairs:
+            per = [a.elapsed_time(b) for a, b, _ in roof_pairs]
+            ntile = roof_pairs[0][2]
+            avg_ms = sum(per) / len(per)
+            ach = BLOCK_CONV_FLOP * ntile / (avg_ms * 1e-3) / 1e12
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "block_conv_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": traffic, "kernel": "conv_tc_kernel (ResNet block conv 256->256 3x3 @128x128)",
+                    "launch_ms": avg_ms, "tiles_per_launch": ntile, "launches_timed": len(per),
+                    "peak_kind": f"{peak_kind} cuBLAS bf16 sustained; bf16x3 executes 3 MMAs per algorithmic MAC "
+                                 f"(ceiling = 1/3)" if args.precision.endswith("x3") else peak_kind}
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, s_per, cores = cpu_flat5_tiles_per_s(args.norm, 1, 1)
+            cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
+                   "sample": "1 tile x 5 ResNet-9 generators, N=1 per call, torch fp32 CPU (oracle port), 1 warm-up"}
+        line = {
+            "metric": "512x512 IHC tiles/sec (flat-5 ResNet-9 generators)", "value": value, "unit": "tiles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 result via %s tensor-core operands, fp32 accumulate" % args.precision, "data": "synthetic",
+            "config": {"workload": "inference: 5x ResNet-9blocks generators, batch=%d/GPU, 512x512 synthetic tiles"
+                                   % B, "norm": args.norm, "padding": "zero", "micro_batch": args.micro_batch,
+                       "parallelism": "tile-sharded dp%d, no collective" % world,
+                       "l2": "3 rotating input batches (%.0f MB each) + multi-GB activations per step >> 126 MB L2"
+                             % (xs[0].numel() * 4 / 1e6),
+                       "algorithmic_gflop_per_tile": N_HEADS * RESNET_GFLOP},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t2_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu,
+            "algorithmic_tflops": value * N_HEADS * RESNET_GFLOP / 1e3,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

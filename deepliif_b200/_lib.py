@@ -28,11 +28,14 @@ SIGNATURES = {
     "dlb_conv_out_shape": (_i, [_cd, C.POINTER(_i), C.POINTER(_i)]),
     "dlb_pack_weights_tc": (_i, [_cd, _vp, _i, _vp, _vp, _vp]),
     "dlb_pack_weights_direct": (_i, [_cd, _vp, _vp, _vp]),
-    "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_direct_fwd": (_i, [_cd, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
+    "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dlb_stem_window_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dlb_head_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dlb_u8_to_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_f32_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_seg_finish": (_i, [_vpp, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

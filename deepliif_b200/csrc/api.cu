@@ -1,6 +1,7 @@
 // C-ABI front end: error reporting, layer geometry, and the lowering of nn.Conv2d / nn.ConvTranspose2d
 // semantics to tap-list phases executed by conv_tc.cu (tcgen05) or conv_direct.cu (fp32 CUDA cores).
 #include "internal.h"
+#include "stats_ws.h"
 
 namespace dlb {
 
@@ -84,7 +85,7 @@ extern "C" int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW) { re
 
 extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
                                const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split,
-                               int n_tile, dlb_stream_t stream) {
+                               int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
   int OH, OW;
   if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
   if (d->pad_mode != DLB_PAD_ZERO) return set_error("dlb_conv_tc_fwd: zero padding only (reflect border comes from dlb_norm_apply)");
@@ -94,6 +95,22 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
   const long long C = d->Cout;
   const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
   if (np < 0) return np;
+  // fused statistics: slices are 32-pixel row groups of the CTA tiles, phases concatenated
+  StatsPtrs sp; memset(&sp, 0, sizeof(sp));
+  int slice_base[4] = {0, 0, 0, 0}, S_total = 0;
+  if (stats_ws != nullptr) {
+    const StatsLayout L = stats_layout(d->N, OH * OW, d->Cout);
+    if (stats_ws_bytes < L.total) return set_error("dlb_conv_tc_fwd: statistics workspace too small");
+    sp = stats_ptrs(stats_ws, L);
+    for (int i = 0; i < np; ++i) {
+      int tw, th, tn;
+      tc_tile_shape(geo[i].OH, geo[i].OW, &tw, &th, &tn);
+      if (tn != 1) return set_error("dlb_conv_tc_fwd: fused statistics need OH*OW >= 128 per phase (use dlb_norm_stats)");
+      slice_base[i] = S_total;
+      S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw) * 4;
+    }
+    if (S_total > L.S_cap) return set_error("dlb_conv_tc_fwd: statistics workspace slice capacity exceeded");
+  }
   for (int i = 0; i < np; ++i) {
     if (geo[i].ntaps > 16) return set_error("dlb_conv_tc_fwd: more than 16 taps per phase");
     TcPhase ph;
@@ -103,6 +120,10 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     for (int s = 0; s < d->nsrc; ++s) { ph.cin[s] = d->Cin[s]; ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; }
     ph.w_hi = w_hi; ph.w_lo = split ? w_lo : nullptr; ph.bias = bias; ph.y = y;
     ph.fmt = fmt; ph.split = split ? 1 : 0; ph.n_tile = n_tile;
+    if (stats_ws != nullptr) {
+      ph.st_partial = sp.partial; ph.st_cnt = sp.cnt; ph.st_S = sp.S; ph.st_S_cap = sp.S_cap;
+      ph.st_slice_base = slice_base[i]; ph.st_S_total = S_total;
+    }
     const int rc = launch_conv_tc_phase(ph, reinterpret_cast<cudaStream_t>(stream));
     if (rc != 0) return rc;
   }

@@ -36,7 +36,9 @@ constexpr int kMaxStages = 8;
 constexpr int kKC = 64;                // channels per pipeline stage: 64 x 2 B = one 128 B swizzle row
 constexpr int kABytes = 128 * 128;     // one A plane of a stage: 128 pixels x 128 B
 constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int kSmemLimit = 232448;     // 227 KB
+constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
+constexpr int kStaticSmem = 18 * 1024; // barriers + statistics transpose buffers (static __shared__), rounded up
+constexpr int kMaxDynSmem = kSmemLimit - kStaticSmem - 1024;
 
 struct alignas(64) TcParams {
   CUtensorMap a_hi[2];
@@ -57,6 +59,11 @@ struct alignas(64) TcParams {
   const float* bias;
   uint32_t idesc;
   int stages;
+  // fused normalisation statistics (nullable): per 32-row slice (sum, M2) of y (bias included)
+  float2* st_partial;
+  float* st_cnt;
+  int* st_S;
+  int st_S_cap, st_slice_base, st_S_total;
 };
 
 struct TileCoord {
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float tr_smem[4][32][33];   // per-epilogue-warp transpose buffer for the fused column statistics
 
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     prefetch_tensormap(&p.b_hi);
     if (p.planes == 2) prefetch_tensormap(&p.b_lo);
+    if (blockIdx.x == 0 && p.st_S != nullptr) *p.st_S = p.st_S_total;
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     fence_barrier_init();
@@ -199,22 +208,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      // slice of the statistics workspace this warp's 32 rows belong to (tile_n == 1 when stats are fused)
+      const int th_i = tc.h0 / p.tile_h, tw_i = tc.w0 / p.tile_w;
+      const long long st_row = static_cast<long long>(n) * p.st_S_cap + p.st_slice_base + (th_i * p.tiles_w + tw_i) * 4 + q;
+      if (p.st_partial != nullptr && tc.cout0 == 0 && lane == 0) p.st_cnt[st_row] = static_cast<float>(__popc(vmask));
       for (int c = 0; c < p.n_tile; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
-        if (valid && (tc.cout0 + c) < p.cout_total) {
+        const bool cvalid = (tc.cout0 + c) < p.cout_total;
+        if (p.bias != nullptr && cvalid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + tc.cout0 + c + j);
+            v[j + 0] = __float_as_uint(__uint_as_float(v[j + 0]) + b.x);
+            v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+            v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+            v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+          }
+        }
+        if (valid && cvalid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o;
             o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
             o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (p.bias != nullptr) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + tc.cout0 + c + j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
             *reinterpret_cast<float4*>(yp + c + j) = o;
           }
+        }
+        if (p.st_partial != nullptr && cvalid) {
+          // column statistics over this warp's 32 pixels: transpose through shared memory, lane <-> channel
+          float (*tr)[33] = tr_smem[q];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tr[lane][j] = __uint_as_float(v[j]);
+          __syncwarp();
+          float col[32];
+          float sum = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) { col[r] = tr[r][lane]; sum += ((vmask >> r) & 1u) ? col[r] : 0.f; }
+          const float cntf = static_cast<float>(__popc(vmask));
+          const float mean = cntf > 0.f ? sum / cntf : 0.f;
+          float m2 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) { const float d = col[r] - mean; m2 += ((vmask >> r) & 1u) ? d * d : 0.f; }
+          p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(sum, m2);
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -277,6 +316,13 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
 
+// 128 output pixels per CTA tile = tile_n x tile_h x tile_w (shared with api.cu for the statistics slices)
+void tc_tile_shape(int OH, int OW, int* tile_w, int* tile_h, int* tile_n) {
+  int tw = OW >= 128 ? 128 : pow2_ceil(OW);
+  int th = 128 / tw; { int hp = pow2_ceil(OH); if (th > hp) th = hp; }
+  *tile_w = tw; *tile_h = th; *tile_n = 128 / (tw * th);
+}
+
 // One phase of a convolution on the tensor cores.  See internal.h for the argument contract.
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   static int num_sms = 0;
@@ -302,23 +348,25 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   if (ph.cout % 32 != 0) return set_error("conv_tc: Cout % 32 == 0 required");
 
   // ---- tile shape: 128 output pixels = tile_n x tile_h x tile_w ---------------------------------
-  int tile_w = ph.OW >= 128 ? 128 : pow2_ceil(ph.OW);
-  int tile_h = 128 / tile_w; { int hp = pow2_ceil(ph.OH); if (tile_h > hp) tile_h = hp; }
-  int tile_n = 128 / (tile_w * tile_h);
+  int tile_w, tile_h, tile_n;
+  tc_tile_shape(ph.OH, ph.OW, &tile_w, &tile_h, &tile_n);
   p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n;
   p.tiles_w = (ph.OW + tile_w - 1) / tile_w;
   p.tiles_h = (ph.OH + tile_h - 1) / tile_h;
   p.tiles_n = (ph.N + tile_n - 1) / tile_n;
 
   int n_tile = ph.n_tile;
-  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : 64);
-  if (n_tile != 64 && n_tile != 128 && n_tile != 256) return set_error("conv_tc: n_tile must be 64/128/256");
+  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : (ph.cout > 32 ? 64 : 32));
+  if (n_tile != 32 && n_tile != 64 && n_tile != 128 && n_tile != 256) return set_error("conv_tc: n_tile must be 32/64/128/256");
   p.n_tile = n_tile;
   p.tiles_c = (ph.cout + n_tile - 1) / n_tile;
   p.N = ph.N; p.OH = ph.OH; p.OW = ph.OW; p.cout_total = ph.cout;
   p.ys_n = ph.ys_n; p.ys_h = ph.ys_h; p.ys_w = ph.ys_w; p.y_base = ph.y_base;
   p.y = ph.y; p.bias = ph.bias;
   p.idesc = make_idesc_f16(128, n_tile, is_bf16);
+  p.st_partial = ph.st_partial; p.st_cnt = ph.st_cnt; p.st_S = ph.st_S;
+  p.st_S_cap = ph.st_S_cap; p.st_slice_base = ph.st_slice_base; p.st_S_total = ph.st_S_total;
+  if (ph.st_partial != nullptr && tile_n != 1) return set_error("conv_tc: fused statistics need H*W >= 128 per image");
 
   // ---- activation tensor maps ---------------------------------------------------------------------
   for (int s = 0; s < ph.nsrc; ++s) {
@@ -368,14 +416,14 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
 
   const int b_bytes = n_tile * 128;
   const int stage_bytes = p.planes * (kABytes + b_bytes);
-  int stages = (kSmemLimit - 1024 - 1024) / stage_bytes;
+  int stages = (kMaxDynSmem - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;
   if (stages < 2) return set_error("conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + 1024;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
       return set_cuda_error("cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
   }

@@ -40,7 +40,14 @@ struct TcPhase : PhaseGeom {
   int n_tile;                  // 0 = auto
   int max_stages;              // 0 = as many as fit
   int max_ctas;                // 0 = #SMs
+  // fused normalisation statistics (see stats_ws.h); st_partial == nullptr disables
+  float2* st_partial;
+  float* st_cnt;
+  int* st_S;
+  int st_S_cap, st_slice_base, st_S_total;
 };
+
+void tc_tile_shape(int OH, int OW, int* tile_w, int* tile_h, int* tile_n);
 
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream);
 

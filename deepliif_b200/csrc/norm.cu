@@ -9,16 +9,17 @@
 #include <cuda_fp16.h>
 
 #include "internal.h"
+#include "stats_ws.h"
 
 namespace dlb {
 namespace {
 
-constexpr int kSlicePixels = 128;   // pixels per partial-statistics slice
+constexpr int kSlicePixels = 128;   // pixels per slice of the standalone statistics kernel
 
-// ---- pass 1: per-slice (sum, M2) partials; thread = 4 channels, coalesced float4 rows -------------
-// grid (slices, N), block 256.  y: [N][HW][C].  partial: [N][slices][C] float2 (sum, M2 about slice mean).
-__global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restrict__ y, int HW, int C,
-                                                            int slices, float2* __restrict__ partial) {
+// ---- standalone pass 1: per-slice (sum, M2) partials; thread = 4 channels, coalesced float4 rows ----------
+// grid (slices, N), block 256.  y: [N][HW][C].
+__global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restrict__ y, int HW, int C, int slices,
+                                                            StatsPtrs ws) {
   __shared__ float s_sum[256 * 4];
   __shared__ float s_m2[256 * 4];
   __shared__ int s_cnt[256];
@@ -27,10 +28,13 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
   const int p0 = sl * kSlicePixels;
   const int p1 = min(p0 + kSlicePixels, HW);
   const int tid = threadIdx.x;
-  // threads are laid out as (pixel lane, channel quad): lanes = 256 / min(c4n,256)
+  if (tid == 0) {
+    ws.cnt[n * ws.S_cap + sl] = static_cast<float>(p1 - p0);
+    if (n == 0 && sl == 0) *ws.S = slices;
+  }
   for (int cq0 = 0; cq0 < c4n; cq0 += 256) {
     const int cols = min(c4n - cq0, 256);
-    const int lanes = 256 / cols;                  // C is a multiple of 4 and cols divides 256 for C in {4..1024}
+    const int lanes = 256 / cols;
     const int cq = cq0 + tid % cols;
     const int pl = tid / cols;
     float sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, shiftv[4] = {0, 0, 0, 0};
@@ -46,7 +50,6 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
         ++cnt;
       }
     }
-    // per-thread (count, mean, M2) then fixed-order merge over the pixel lanes through shared memory
     float mean[4], m2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -61,9 +64,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
     s_cnt[tid] = (pl < lanes) ? cnt : 0;
     __syncthreads();
     if (pl == 0) {
-      // Chan merge in lane order (deterministic)
       float cn = 0.f, cm[4] = {0, 0, 0, 0}, cM[4] = {0, 0, 0, 0};
-      for (int l = 0; l < lanes; ++l) {
+      for (int l = 0; l < lanes; ++l) {            // Chan merge in lane order (deterministic)
         const int o = l * cols + (tid % cols);
         const float nb = static_cast<float>(s_cnt[o]);
         if (nb == 0.f) continue;
@@ -78,43 +80,86 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        partial[(static_cast<long long>(n) * slices + sl) * C + cq * 4 + k] = make_float2(cm[k] * cn, cM[k]);
+        ws.partial[(static_cast<long long>(n) * ws.S_cap + sl) * C + cq * 4 + k] = make_float2(cm[k] * cn, cM[k]);
     }
     __syncthreads();
   }
 }
 
-// ---- pass 2: merge slices (fp64, fixed order) -> scale/shift --------------------------------------
-// thread = one (n, c) (or one c when pooled).
-__global__ void stats_finalize_kernel(const float2* __restrict__ partial, int N, int HW, int C, int slices,
-                                      int pooled, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float eps, float* __restrict__ scale, float* __restrict__ shift) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int groups = pooled ? 1 : N;
-  if (idx >= groups * C) return;
-  const int c = idx % C, g = idx / C;
-  const int n_lo = pooled ? 0 : g, n_hi = pooled ? N : g + 1;
-  double cn = 0.0, cm = 0.0, cM = 0.0;
-  for (int n = n_lo; n < n_hi; ++n) {
-    for (int s = 0; s < slices; ++s) {
-      const float2 pr = partial[(static_cast<long long>(n) * slices + s) * C + c];
-      const int p0 = s * kSlicePixels;
-      const double nb = static_cast<double>(min(kSlicePixels, HW - p0));
-      const double mb = static_cast<double>(pr.x) / nb;
-      const double nt = cn + nb;
-      const double d = mb - cm;
-      cm += d * (nb / nt);
-      cM += static_cast<double>(pr.y) + d * d * (cn * nb / nt);
-      cn = nt;
+// ---- finalize: merge slices -> scale/shift.  grid (C/32, N, G_cap), block 256 (8 warps, lane = channel). ---
+// Level 1: each block merges one group of 64 slices (8 per warp, then the 8 warps in order).  Level 2: the
+// last block to finish for a (n, channel-chunk) merges the groups in index order.  Every merge order is
+// fixed, so the result is deterministic although the identity of the last block is not.
+struct Moments { double n, mean, m2; };
+__device__ __forceinline__ void chan_merge(Moments& a, double nb, double mb, double Mb) {
+  if (nb <= 0.0) return;
+  const double nt = a.n + nb;
+  const double d = mb - a.mean;
+  a.mean += d * (nb / nt);
+  a.m2 += Mb + d * d * (a.n * nb / nt);
+  a.n = nt;
+}
+
+__global__ void __launch_bounds__(256) stats_finalize_kernel(StatsPtrs ws, int N, int C, int pooled,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double sm[8][32][3];
+  const int S = *ws.S;
+  const int G = (S + kSlicesPerGroup - 1) / kSlicesPerGroup;
+  const int g = blockIdx.z;
+  if (g >= G) return;
+  const int cchunk = blockIdx.x, n = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = cchunk * 32 + lane;
+  const bool cok = c < C;
+  Moments m{0.0, 0.0, 0.0};
+  if (cok) {
+#pragma unroll
+    for (int i = 0; i < kSlicesPerGroup / 8; ++i) {
+      const int s = g * kSlicesPerGroup + w + 8 * i;
+      if (s < S) {
+        const float nb = ws.cnt[n * ws.S_cap + s];
+        if (nb > 0.f) {
+          const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
+          chan_merge(m, nb, static_cast<double>(pr.x) / nb, pr.y);
+        }
+      }
     }
   }
-  const double var = cM / cn;                        // biased variance (PyTorch norm layers)
+  sm[w][lane][0] = m.n; sm[w][lane][1] = m.mean; sm[w][lane][2] = m.m2;
+  __syncthreads();
+  if (w != 0) return;
+  Moments t{0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) chan_merge(t, sm[k][lane][0], sm[k][lane][1], sm[k][lane][2]);
+  if (cok)
+    ws.group[(static_cast<long long>(n) * ws.G_cap + g) * C + c] =
+        make_float4(static_cast<float>(t.n), static_cast<float>(t.mean), static_cast<float>(t.m2), 0.f);
+  __threadfence();
+  int ticket = 0;
+  int* counter = ws.counters + (pooled ? N * ws.cchunks + cchunk : n * ws.cchunks + cchunk);
+  if (lane == 0) ticket = atomicAdd(counter, 1);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  const int expected = pooled ? N * G : G;
+  if (ticket != expected - 1) return;
+  __threadfence();
+  if (lane == 0) *counter = 0;                        // leave the workspace clean for the next call
+  if (!cok) return;
+  Moments f{0.0, 0.0, 0.0};
+  const int n_lo = pooled ? 0 : n, n_hi = pooled ? N : n + 1;
+  for (int nn = n_lo; nn < n_hi; ++nn)
+    for (int gg = 0; gg < G; ++gg) {
+      const float4 v = __ldcg(&ws.group[(static_cast<long long>(nn) * ws.G_cap + gg) * C + c]);
+      chan_merge(f, v.x, v.y, v.z);
+    }
+  const double var = f.m2 / f.n;                      // biased variance (PyTorch norm layers)
   const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float ga = gamma ? gamma[c] : 1.f;
   const float be = beta ? beta[c] : 0.f;
   const float sc = ga * rstd;
-  const float sh = be - static_cast<float>(cm) * sc;
-  for (int n = n_lo; n < n_hi; ++n) { scale[n * C + c] = sc; shift[n * C + c] = sh; }
+  const float sh = be - static_cast<float>(f.mean) * sc;
+  for (int nn = n_lo; nn < n_hi; ++nn) { scale[nn * C + c] = sc; shift[nn * C + c] = sh; }
 }
 
 // ---- apply: act(y*scale+shift) (+residual) -> fp32 and/or split 16-bit planes ---------------------
@@ -141,61 +186,112 @@ struct ApplyParams {
   int N, H, W, C, pad, pad_mode;
 };
 
-// One thread = one output pixel-quad (4 channels) of the (possibly padded) output grid.
+// grid (x: quads of one padded output row, y: rows n*HP + hp).  One thread = 4 channels of one output pixel;
+// 32-bit index math only; every access is a 128-bit (fp32) or 64-bit (4 x 16-bit) vector.
 template <typename T16>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
   const int c4n = p.C / 4;
   const int HP = p.H + 2 * p.pad, WP = p.W + 2 * p.pad;
-  const long long total = static_cast<long long>(p.N) * HP * WP * c4n;
+  const int row_quads = WP * c4n;
+  const int rows = p.N * HP;
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+    const int n = row / HP, hp = row - n * HP;
+    int h = hp - p.pad;
+    const bool hborder = (h < 0) || (h >= p.H);
+    if (hborder && p.pad_mode == DLB_PAD_REFLECT) { if (h < 0) h = -h; if (h >= p.H) h = 2 * p.H - 2 - h; }
+    const float* __restrict__ yrow = p.y + (static_cast<long long>(n) * p.H + h) * p.W * p.C;
+    const float* __restrict__ rrow = p.residual ? p.residual + (static_cast<long long>(n) * p.H + h) * p.W * p.C : nullptr;
+    float* __restrict__ frow = p.out_f32 ? p.out_f32 + (static_cast<long long>(n) * p.H + h) * p.W * p.C : nullptr;
+    const long long drow = (static_cast<long long>(n) * HP + hp) * WP * p.C;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < row_quads; q += gridDim.x * blockDim.x) {
+      const int wp = q / c4n, cq = q - wp * c4n;
+      int w = wp - p.pad;
+      bool border = hborder || (w < 0) || (w >= p.W);
+      bool zero = false;
+      if (border) {
+        if (p.pad_mode == DLB_PAD_REFLECT) { if (w < 0) w = -w; if (w >= p.W) w = 2 * p.W - 2 - w; }
+        else zero = true;
+      }
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!zero) {
+        const int src = w * p.C + cq * 4;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(yrow + src));
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        if (p.scale != nullptr) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n * p.C + cq * 4));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n * p.C + cq * 4));
+          o[0] = fmaf(o[0], sc.x, sh.x); o[1] = fmaf(o[1], sc.y, sh.y);
+          o[2] = fmaf(o[2], sc.z, sh.z); o[3] = fmaf(o[3], sc.w, sh.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = act1(o[k], p.act);
+        if (rrow != nullptr) {
+          const float4 rv = __ldcs(reinterpret_cast<const float4*>(rrow + src));
+          o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+        }
+        if (frow != nullptr && !border) *reinterpret_cast<float4*>(frow + src) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      if (p.out_hi != nullptr) {
+        const long long dst = drow + static_cast<long long>(q) * 4;
+        T16 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          hi[k] = Cvt<T16>::to(o[k]);
+          lo[k] = Cvt<T16>::to(o[k] - Cvt<T16>::from(hi[k]));
+        }
+        *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_hi) + dst) = *reinterpret_cast<uint2*>(hi);
+        if (p.out_lo != nullptr)
+          *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_lo) + dst) = *reinterpret_cast<uint2*>(lo);
+      }
+    }
+  }
+}
+
+// ---- stem operand: 7-wide horizontal windows of the padded input, packed into the channel dimension ------
+// Xw[n, hp, w, s*8 + c] = xpad[n, hp, w + s, c]  (s < S taps, c < C <= 8; other lanes 0), xpad = pad-`pad` border of x.
+// With this operand the Cin=3 7x7 stem (networks.py:386-397) is a 7-tap (vertical) conv with Cin = 64 on the
+// tensor cores: K = (s, c) sits in one 128-byte swizzle row.  One thread = one (n, hp, w) pixel = 64 channels.
+template <typename T16>
+__global__ void __launch_bounds__(256) stem_window_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                                          int pad, int S, int pad_mode, T16* __restrict__ out_hi,
+                                                          T16* __restrict__ out_lo) {
+  const int HP = H + 2 * pad;
+  const long long total = static_cast<long long>(N) * HP * W;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cq = static_cast<int>(idx % c4n);
-    long long r = idx / c4n;
-    const int wp = static_cast<int>(r % WP); r /= WP;
-    const int hp = static_cast<int>(r % HP);
-    const int n = static_cast<int>(r / HP);
-    int h = hp - p.pad, w = wp - p.pad;
-    bool border = (h < 0) || (h >= p.H) || (w < 0) || (w >= p.W);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    bool zero = false;
-    if (border) {
-      if (p.pad_mode == DLB_PAD_REFLECT) {
-        if (h < 0) h = -h; if (h >= p.H) h = 2 * p.H - 2 - h;
-        if (w < 0) w = -w; if (w >= p.W) w = 2 * p.W - 2 - w;
-      } else {
-        zero = true;
+    const int w = static_cast<int>(idx % W);
+    const int hp = static_cast<int>((idx / W) % HP);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * HP));
+    int h = hp - pad;
+    bool hout = (h < 0) || (h >= H);
+    if (hout && pad_mode == DLB_PAD_REFLECT) { if (h < 0) h = -h; if (h >= H) h = 2 * H - 2 - h; hout = false; }
+    __align__(16) T16 hi[64];
+    __align__(16) T16 lo[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) { hi[k] = Cvt<T16>::to(0.f); lo[k] = Cvt<T16>::to(0.f); }
+    if (!hout) {
+      for (int s = 0; s < S; ++s) {
+        int ww = w + s - pad;
+        bool wout = (ww < 0) || (ww >= W);
+        if (wout && pad_mode == DLB_PAD_REFLECT) { if (ww < 0) ww = -ww; if (ww >= W) ww = 2 * W - 2 - ww; wout = false; }
+        if (wout) continue;
+        for (int c = 0; c < C; ++c) {
+          const float v = __ldg(x + ((static_cast<long long>(n) * C + c) * H + h) * W + ww);
+          const T16 hh = Cvt<T16>::to(v);
+          hi[s * 8 + c] = hh;
+          lo[s * 8 + c] = Cvt<T16>::to(v - Cvt<T16>::from(hh));
+        }
       }
     }
-    if (!zero) {
-      const long long src = ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.C + cq * 4;
-      const float4 v = *reinterpret_cast<const float4*>(p.y + src);
-      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-      if (p.scale != nullptr) {
-        const float4 sc = *reinterpret_cast<const float4*>(p.scale + n * p.C + cq * 4);
-        const float4 sh = *reinterpret_cast<const float4*>(p.shift + n * p.C + cq * 4);
-        o[0] = fmaf(o[0], sc.x, sh.x); o[1] = fmaf(o[1], sc.y, sh.y);
-        o[2] = fmaf(o[2], sc.z, sh.z); o[3] = fmaf(o[3], sc.w, sh.w);
-      }
+    uint4* dh = reinterpret_cast<uint4*>(out_hi + idx * 64);
+    const uint4* sh = reinterpret_cast<const uint4*>(hi);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = act1(o[k], p.act);
-      if (p.residual != nullptr) {
-        const float4 rv = *reinterpret_cast<const float4*>(p.residual + src);
-        o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-      }
-      if (p.out_f32 != nullptr && !border)
-        *reinterpret_cast<float4*>(p.out_f32 + src) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-    if (p.out_hi != nullptr) {
-      const long long dst = ((static_cast<long long>(n) * HP + hp) * WP + wp) * p.C + cq * 4;
-      T16 hi[4], lo[4];
+    for (int k = 0; k < 8; ++k) dh[k] = sh[k];
+    if (out_lo != nullptr) {
+      uint4* dl = reinterpret_cast<uint4*>(out_lo + idx * 64);
+      const uint4* sl = reinterpret_cast<const uint4*>(lo);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        hi[k] = Cvt<T16>::to(o[k]);
-        lo[k] = Cvt<T16>::to(o[k] - Cvt<T16>::from(hi[k]));
-      }
-      *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_hi) + dst) = *reinterpret_cast<uint2*>(hi);
-      if (p.out_lo != nullptr)
-        *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_lo) + dst) = *reinterpret_cast<uint2*>(lo);
+      for (int k = 0; k < 8; ++k) dl[k] = sl[k];
     }
   }
 }
@@ -245,9 +341,23 @@ int grid_for(long long total, int block) {
 
 using namespace dlb;
 
-extern "C" size_t dlb_norm_stats_workspace(int N, int HW, int C) {
-  const int slices = (HW + kSlicePixels - 1) / kSlicePixels;
-  return static_cast<size_t>(N) * slices * C * sizeof(float2);
+extern "C" size_t dlb_norm_stats_workspace(int N, int HW, int C) { return stats_layout(N, HW, C).total; }
+
+static int launch_finalize(void* workspace, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
+                           float eps, float* scale, float* shift, cudaStream_t stream) {
+  const StatsLayout L = stats_layout(N, HW, C);
+  const StatsPtrs ws = stats_ptrs(workspace, L);
+  dim3 grid(L.cchunks, N, L.G_cap);
+  stats_finalize_kernel<<<grid, 256, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_finalize_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_norm_finalize(void* workspace, size_t workspace_bytes, int N, int HW, int C, int pooled,
+                                 const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                                 dlb_stream_t stream) {
+  if (workspace_bytes < stats_layout(N, HW, C).total) return set_error("dlb_norm_finalize: workspace too small");
+  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
@@ -257,16 +367,13 @@ extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, 
   const int c4n = C / 4;
   if (c4n < 256 && 256 % c4n != 0) return set_error("dlb_norm_stats: C/4 must divide 256 (or be a multiple of 256)");
   if (c4n > 256 && c4n % 256 != 0) return set_error("dlb_norm_stats: C/4 must divide 256 (or be a multiple of 256)");
-  if (workspace_bytes < dlb_norm_stats_workspace(N, HW, C)) return set_error("dlb_norm_stats: workspace too small");
+  const StatsLayout L = stats_layout(N, HW, C);
+  if (workspace_bytes < L.total) return set_error("dlb_norm_stats: workspace too small");
   const int slices = (HW + kSlicePixels - 1) / kSlicePixels;
-  float2* partial = reinterpret_cast<float2*>(workspace);
-  stats_partial_kernel<<<dim3(slices, N), 256, 0, stream>>>(y, HW, C, slices, partial);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  stats_partial_kernel<<<dim3(slices, N), 256, 0, st>>>(y, HW, C, slices, stats_ptrs(workspace, L));
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_partial_kernel launch");
-  const int groups = pooled ? 1 : N;
-  stats_finalize_kernel<<<(groups * C + 127) / 128, 128, 0, stream>>>(partial, N, HW, C, slices, pooled, gamma, beta,
-                                                                    eps, scale, shift);
-  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_finalize_kernel launch");
-  return 0;
+  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, st);
 }
 
 extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
@@ -276,10 +383,13 @@ extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* s
   if (pad < 0 || (pad_mode == DLB_PAD_REFLECT && (pad >= H || pad >= W))) return set_error("dlb_norm_apply: bad pad");
   if (out_hi == nullptr && out_f32 == nullptr) return set_error("dlb_norm_apply: no output");
   ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode};
-  const long long total = static_cast<long long>(N) * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
-  const int grid = grid_for(total, 256);
-  if (fmt == DLB_FMT_BF16) norm_apply_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
-  else if (fmt == DLB_FMT_FP16) norm_apply_kernel<__half><<<grid, 256, 0, stream>>>(p);
+  const int row_quads = (W + 2 * pad) * (C / 4);
+  const int rows = N * (H + 2 * pad);
+  int gx = (row_quads + 255) / 256; if (gx > 64) gx = 64;
+  dim3 grid(gx, rows < 65535 ? rows : 65535);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (fmt == DLB_FMT_BF16) norm_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else if (fmt == DLB_FMT_FP16) norm_apply_kernel<__half><<<grid, 256, 0, st>>>(p);
   else return set_error("dlb_norm_apply: bad fmt");
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("norm_apply_kernel launch");
   return 0;
@@ -311,5 +421,23 @@ extern "C" int dlb_pack_weights_direct(const dlb_conv_desc* d, const float* w, f
   const long long total = static_cast<long long>(taps) * d->Cout * cin;
   pack_w_direct_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, d->Cout, cin, taps, d->transposed, w_packed);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("pack_w_direct_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_stem_window_pack(const float* x_nchw, int N, int C, int H, int W, int pad, int S, int pad_mode,
+                                    int fmt, void* out_hi, void* out_lo, dlb_stream_t stream) {
+  if (C < 1 || C > 8 || S < 1 || S > 8) return set_error("dlb_stem_window_pack: needs C <= 8 and S <= 8");
+  if (pad_mode == DLB_PAD_REFLECT && (pad >= H || pad >= W)) return set_error("dlb_stem_window_pack: bad pad");
+  const long long total = static_cast<long long>(N) * (H + 2 * pad) * W;
+  const int grid = grid_for(total, 256);
+  if (fmt == DLB_FMT_BF16)
+    stem_window_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x_nchw, N, C, H, W, pad, S, pad_mode,
+                                                              reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                              reinterpret_cast<__nv_bfloat16*>(out_lo));
+  else if (fmt == DLB_FMT_FP16)
+    stem_window_kernel<__half><<<grid, 256, 0, stream>>>(x_nchw, N, C, H, W, pad, S, pad_mode,
+                                                       reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo));
+  else return set_error("dlb_stem_window_pack: bad fmt");
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stem_window_kernel launch");
   return 0;
 }

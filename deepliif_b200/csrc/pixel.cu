@@ -73,6 +73,36 @@ __global__ void seg_finish_kernel(const SegParams p) {
   }
 }
 
+// Head finish: y[n, co, h, w] = act(bias[co] + sum_s z[n, h, w + s, s*4 + co]).
+// z is the output of the "horizontal taps as output channels" convolution (see dlb_head_finish in the header):
+// fp32 NHWC [N, H, W + S - 1, 32]; thread = one output pixel, S float4 loads.
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                                                          int N, int H, int W, int S, int CO, int act,
+                                                          float* __restrict__ y) {
+  const int WZ = W + S - 1;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(N) * plane;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % W);
+    const int h = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / plane);
+    const float* zr = z + ((static_cast<long long>(n) * H + h) * WZ + w) * 32;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(zr + s * 32 + s * 4));
+      a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+    }
+    const float acc[4] = {a0, a1, a2, a3};
+    for (int co = 0; co < CO; ++co) {
+      float v = acc[co] + (bias ? __ldg(bias + co) : 0.f);
+      if (act == DLB_ACT_TANH) v = tanhf(v);
+      else if (act == DLB_ACT_RELU) v = fmaxf(v, 0.f);
+      y[(static_cast<long long>(n) * CO + co) * plane + static_cast<long long>(h) * W + w] = v;
+    }
+  }
+}
+
 int grid1d(long long total) {
   long long g = (total + 255) / 256;
   return static_cast<int>(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8);
@@ -105,5 +135,13 @@ extern "C" int dlb_seg_finish(const float* const* segs, const float* weights, in
   p.seg_f32 = seg_f32_nchw; p.seg_u8 = seg_u8_nhwc; p.mask = mask;
   seg_finish_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("seg_finish_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_head_finish(const float* z, const float* bias, int N, int H, int W, int S, int CO, int act,
+                               float* y_nchw, dlb_stream_t stream) {
+  if (S < 1 || S > 8 || CO < 1 || CO > 4) return set_error("dlb_head_finish: needs S <= 8 and CO <= 4");
+  head_finish_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(z, bias, N, H, W, S, CO, act, y_nchw);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("head_finish_kernel launch");
   return 0;
 }

@@ -21,6 +21,23 @@ from . import ops
 from .ops import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16, PAD_REFLECT, PAD_ZERO)
 
 
+# bench.py sets this to a list to collect (start_event, end_event, tiles) around every ResNet-block conv launch
+# (roofline.achieved is measured live on the launching stream); None = no instrumentation.
+BLOCK_CONV_EVENTS = None
+
+
+def _block_conv(cv, acts, N, H, W, pad):
+    ev = BLOCK_CONV_EVENTS
+    if ev is None:
+        return cv.run_tc(acts, N, H, W, pad=pad)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = cv.run_tc(acts, N, H, W, pad=pad)
+    b.record()
+    ev.append((a, b, N))
+    return r
+
+
 @dataclass
 class Precision:
     """Operand format of the tensor-core convs.  split=True: hi/lo 16-bit planes, 3 MMAs per K step
@@ -78,11 +95,16 @@ class ConvLayer:
         return ops.conv_desc(N, H, W, self.cins, self.cout, self.R, self.S, self.stride,
                              self.pad if pad is None else pad, self.transposed, self.output_padding, pad_mode)
 
-    def run_tc(self, acts, N, H, W, pad=None):
-        """acts: list of Act (split planes).  H, W: extents of the (possibly border-padded) operand."""
+    def run_tc(self, acts, N, H, W, pad=None, fuse_stats=True):
+        """acts: list of Act (split planes).  H, W: extents of the (possibly border-padded) operand.
+        Returns (y, stats_ws | None): with fuse_stats the epilogue leaves partial statistics in stats_ws."""
         d = self.desc(N, H, W, pad)
-        return ops.conv_tc(d, [a.hi for a in acts], [a.lo for a in acts], self.w_hi, self.w_lo, self.bias,
-                           self.prec.fmt, self.prec.split, self.n_tile)
+        oh, ow = ops.conv_out_shape(d)
+        per_phase = (oh // self.stride) * (ow // self.stride) if self.transposed else oh * ow
+        ws = ops.stats_workspace(N, oh * ow, self.cout, acts[0].hi.device) if (fuse_stats and per_phase >= 128) else None
+        y = ops.conv_tc(d, [a.hi for a in acts], [a.lo for a in acts], self.w_hi, self.w_lo, self.bias,
+                        self.prec.fmt, self.prec.split, self.n_tile, stats_ws=ws)
+        return y, ws
 
     def run_direct(self, x, N, H, W, *, pad_mode=PAD_ZERO, in_nchw=False, in_scale=None, in_shift=None,
                    in_act=ACT_NONE, out_act=ACT_NONE, out_nchw=False):
@@ -104,11 +126,15 @@ class _EngineBase:
             raise NotImplementedError("normalization layer [%s] is not found" % norm)
         self.norm, self.norm_mode, self.prec, self.backend, self.device = norm, norm_mode, prec, backend, device
 
-    def _stats(self, y, np_):
-        """raw conv output -> (scale, shift) or (None, None) for norm='none'."""
+    def _stats(self, y, np_, ws=None):
+        """raw conv output -> (scale, shift) or (None, None) for norm='none'.  ws: partial statistics already
+        written by the conv epilogue (then y is not read again)."""
         if self.norm == "none" or np_ is None:
             return None, None
         pooled = self.norm == "batch" and self.norm_mode == "batch"
+        if ws is not None:
+            N, H, W, C = y.shape
+            return ops.norm_finalize(ws, N, H * W, C, np_.gamma, np_.beta, pooled)
         return ops.norm_stats(y, np_.gamma, np_.beta, pooled)
 
     def _apply(self, y, scale, shift, act, *, residual=None, want_f32=False, want_split=True, pad=0,
@@ -121,7 +147,7 @@ class _EngineBase:
         """Run a conv on an Act with whichever kernel the layer was packed for.  Zero padding only."""
         if layer.use_tc:
             return layer.run_tc([act], N, H, W)
-        return layer.run_direct(act.f32, N, H, W)
+        return layer.run_direct(act.f32, N, H, W), None
 
 
 class ResnetEngine(_EngineBase):
@@ -138,8 +164,19 @@ class ResnetEngine(_EngineBase):
         g = lambda k: sd[k].to(device) if k in sd else None
         mk = lambda k, **kw: ConvLayer(g(k + ".weight"), g(k + ".bias"), prec=prec, backend=backend, n_tile=n_tile, **kw)
         nrm = lambda k: _NormParams(sd, k, norm, device)
-        # stem / head always run on the fp32 direct kernel (Cin = 3 / Cout = 3)
-        self.stem = ConvLayer(g("model.1.weight"), g("model.1.bias"), pad=3, backend="direct")
+        # stem: on the tensor cores through the horizontal-window operand (K = 7 taps x 8 channel lanes = 64),
+        # else (validation backend / exotic channel counts) on the fp32 direct kernel.  head: direct kernel.
+        w1 = g("model.1.weight")
+        self.stem_tc = backend == "tc" and w1.shape[1] <= 8 and w1.shape[3] <= 8 and w1.shape[0] % 32 == 0
+        if self.stem_tc:
+            co, ci, R, S = w1.shape
+            wk = torch.zeros((co, 64, R, 1), dtype=torch.float32, device=device)
+            # wk[co, s*8 + c, r, 0] = w[co, c, r, s]
+            wk.view(co, 8, 8, R)[:, :S, :ci, :] = w1.to(torch.float32).permute(0, 3, 1, 2)
+            self.stem = ConvLayer(wk, g("model.1.bias"), pad=0, prec=prec, backend="tc", n_tile=n_tile)
+            self.stem_S = S
+        else:
+            self.stem = ConvLayer(w1, g("model.1.bias"), pad=3, backend="direct")
         self.stem_norm = nrm("model.2")
         idx = 4
         self.down, self.down_norm = [], []
@@ -159,7 +196,20 @@ class ResnetEngine(_EngineBase):
             self.up_norm.append(nrm(f"model.{idx + 1}"))
             idx += 3
         idx += 1
-        self.head = ConvLayer(g(f"model.{idx}.weight"), g(f"model.{idx}.bias"), pad=3, backend="direct")
+        # head: on the tensor cores with the horizontal taps moved into 32 virtual output channels (j = s*4 + co),
+        # followed by the shifted-sum finish; else the fp32 direct kernel.
+        wh, bh = g(f"model.{idx}.weight"), g(f"model.{idx}.bias")
+        self.head_tc = backend == "tc" and wh.shape[0] <= 4 and wh.shape[3] <= 8 and wh.shape[1] % 64 == 0
+        if self.head_tc:
+            co, ci, R, S = wh.shape
+            wv = torch.zeros((32, ci, R, 1), dtype=torch.float32, device=device)
+            # wv[s*4 + co, c, r, 0] = w[co, c, r, s]
+            wv.view(8, 4, ci, R)[:S, :co] = wh.to(torch.float32).permute(3, 0, 1, 2)
+            self.head = ConvLayer(wv, None, pad=0, prec=prec, backend="tc", n_tile=32)
+            self.head_bias = bh.detach().to(torch.float32).contiguous() if bh is not None else None
+            self.head_S, self.head_co = S, co
+        else:
+            self.head = ConvLayer(wh, bh, pad=3, backend="direct")
 
     @torch.no_grad()
     def forward(self, x, taps=None):
@@ -175,16 +225,20 @@ class ResnetEngine(_EngineBase):
                 taps[name] = a
 
         # stem: Pad3 + Conv7x7 (NCHW input read directly) -> norm -> ReLU
-        y = self.stem.run_direct(x, N, H, W, pad_mode=self.pad_mode, in_nchw=True)
+        if self.stem_tc:
+            xh, xl = ops.stem_window_pack(x, 3, self.stem_S, self.pad_mode, self.prec.fmt, self.prec.split)
+            y, ws = self.stem.run_tc([Act(None, xh, xl)], N, H + 6, W)
+        else:
+            y, ws = self.stem.run_direct(x, N, H, W, pad_mode=self.pad_mode, in_nchw=True), None
         tap("stem_conv", y)
-        sc, sh = self._stats(y, self.stem_norm)
+        sc, sh = self._stats(y, self.stem_norm, ws)
         a = self._apply(y, sc, sh, ACT_RELU, **want)
         h, w = H, W
         # two stride-2 down convs
         for i in range(2):
-            y = self._conv(self.down[i], a, N, h, w)
+            y, ws = self._conv(self.down[i], a, N, h, w)
             h, w = h // 2, w // 2
-            sc, sh = self._stats(y, self.down_norm[i])
+            sc, sh = self._stats(y, self.down_norm[i], ws)
             last = i == 1
             # the trunk keeps an fp32 residual stream next to the operand planes
             a = self._apply(y, sc, sh, ACT_RELU, want_f32=(not tc) or last, want_split=tc,
@@ -195,11 +249,11 @@ class ResnetEngine(_EngineBase):
             last = b == self.n_blocks - 1
             if tc:
                 p = 1 if refl else 0
-                y = cv1.run_tc([a], N, h + 2 * p, w + 2 * p, pad=0 if refl else 1)
-                sc, sh = self._stats(y, nm1)
+                y, ws = _block_conv(cv1, [a], N, h + 2 * p, w + 2 * p, 0 if refl else 1)
+                sc, sh = self._stats(y, nm1, ws)
                 t = self._apply(y, sc, sh, ACT_RELU, pad=p, pad_mode=self.pad_mode)
-                y = cv2.run_tc([t], N, h + 2 * p, w + 2 * p, pad=0 if refl else 1)
-                sc, sh = self._stats(y, nm2)
+                y, ws = _block_conv(cv2, [t], N, h + 2 * p, w + 2 * p, 0 if refl else 1)
+                sc, sh = self._stats(y, nm2, ws)
                 a = self._apply(y, sc, sh, ACT_NONE, residual=a.f32, want_f32=True,
                                 pad=0 if last else p, pad_mode=self.pad_mode)
             else:
@@ -211,15 +265,153 @@ class ResnetEngine(_EngineBase):
             tap(f"block{b}", a)
         # two ConvTranspose upsamplings
         for i in range(2):
-            y = self._conv(self.up[i], a, N, h, w)
+            y, ws = self._conv(self.up[i], a, N, h, w)
             h, w = h * 2, w * 2
-            sc, sh = self._stats(y, self.up_norm[i])
+            sc, sh = self._stats(y, self.up_norm[i], ws)
             if i == 0:
                 a = self._apply(y, sc, sh, ACT_RELU, **want)
                 tap("up0", a)
         # head: (norm + ReLU fused into the load) Pad3 + Conv7x7 + bias + Tanh, NCHW out
-        out = self.head.run_direct(y, N, h, w, pad_mode=self.pad_mode, in_scale=sc, in_shift=sh, in_act=ACT_RELU,
-                                   out_act=ACT_TANH, out_nchw=True)
-        return out
+        if self.head_tc:
+            a = self._apply(y, sc, sh, ACT_RELU, pad=3, pad_mode=self.pad_mode)
+            z, _ = self.head.run_tc([a], N, h + 6, w + 6, fuse_stats=False)
+            return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
+        return self.head.run_direct(y, N, h, w, pad_mode=self.pad_mode, in_scale=sc, in_shift=sh, in_act=ACT_RELU,
+                                    out_act=ACT_TANH, out_nchw=True)
+
+    __call__ = forward
+
+
+def _pad_cout32(w, transposed):
+    """Zero-pad the output-channel dim of a conv weight to 32 so a Cout <= 4 layer fits a tensor-core tile."""
+    if transposed:
+        ci, co, R, S = w.shape
+        out = torch.zeros((ci, 32, R, S), dtype=torch.float32, device=w.device)
+        out[:, :co] = w
+    else:
+        co, ci, R, S = w.shape
+        out = torch.zeros((32, ci, R, S), dtype=torch.float32, device=w.device)
+        out[:co] = w
+    return out, co
+
+
+class UnetEngine(_EngineBase):
+    """UnetGenerator forward (eval semantics).  Level k (0 = outermost) follows UnetSkipConnectionBlock
+    (networks.py:573-615): down = [LeakyReLU(0.2), Conv4x4 s2, Norm], up = [ReLU, ConvT4x4 s2, Norm], skip =
+    cat([x, model(x)], 1).  The skip concat is never materialised: every up-convolution reads its two sources
+    (skip, below) through two TMA tensor maps (dual-source K loop); relu(cat(a, u)) = cat(relu(a), relu(u)) and
+    relu(leaky_relu(x)) = relu(x), so the skip operand is relu(norm(d_{k-1}))."""
+
+    def __init__(self, sd, *, num_downs=9, norm="batch", norm_mode="sample", precision="bf16x3", backend="tc",
+                 device="cuda"):
+        prec = Precision.parse(precision) if isinstance(precision, str) else precision
+        super().__init__(norm, norm_mode, prec, backend, device)
+        if backend != "tc":
+            raise NotImplementedError("UnetEngine runs on the tensor-core backend only")
+        self.nd = num_downs
+        g = lambda k: sd[k].to(device) if k in sd else None
+        pre = ["model.model"]
+        for lvl in range(1, num_downs):
+            pre.append(f"{pre[-1]}.{1 if lvl == 1 else 3}.model")
+        self.down, self.down_norm, self.up, self.up_norm = [], [], [], []
+        for lvl in range(num_downs):
+            p = pre[lvl]
+            innermost = lvl == num_downs - 1
+            dk = f"{p}.0" if lvl == 0 else f"{p}.1"
+            uk = f"{p}.3" if (lvl == 0 or innermost) else f"{p}.5"
+            self.down.append(ConvLayer(g(dk + ".weight"), g(dk + ".bias"), stride=2, pad=1, prec=prec, backend=backend))
+            self.down_norm.append(_NormParams(sd, f"{p}.2", norm, device) if (0 < lvl < num_downs - 1) else None)
+            wu, bu = g(uk + ".weight").to(torch.float32), g(uk + ".bias")
+            cin_total, cout = wu.shape[0], wu.shape[1]
+            cins = [cin_total] if innermost else [cin_total // 2, cin_total // 2]
+            if lvl == 0:
+                if cout > 4:
+                    raise NotImplementedError("UnetEngine: output_nc <= 4 expected")
+                wu, self.out_nc = _pad_cout32(wu, True)
+                self.out_bias = bu.detach().to(torch.float32).contiguous()
+                self.up.append(ConvLayer(wu, None, transposed=True, stride=2, pad=1, cins=cins, prec=prec, backend="tc",
+                                         n_tile=32))
+            else:
+                self.up.append(ConvLayer(wu, bu, transposed=True, stride=2, pad=1, cins=cins, prec=prec, backend="tc"))
+            nk = None if lvl == 0 else (f"{p}.4" if innermost else f"{p}.6")
+            self.up_norm.append(_NormParams(sd, nk, norm, device) if nk else None)
+
+    @torch.no_grad()
+    def forward(self, x, taps=None):
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        nd = self.nd
+        # ---- down path: keep, per level, the raw conv output + its (scale, shift) ---------------------------------
+        raw, ss = [], []
+        h, w = H, W
+        y = self.down[0].run_direct(x, N, h, w, in_nchw=True)             # level 0: Conv(input_nc -> ngf), no norm
+        h, w = h // 2, w // 2
+        raw.append(y); ss.append((None, None))
+        dims = [(h, w)]
+        for lvl in range(1, nd):
+            sc, sh = ss[-1]
+            a = self._apply(raw[-1], sc, sh, ACT_LRELU02)                  # LeakyReLU(0.2)(norm(d_{lvl-1}))
+            y, ws = self.down[lvl].run_tc([a], N, h, w)
+            h, w = h // 2, w // 2
+            raw.append(y)
+            ss.append(self._stats(y, self.down_norm[lvl], ws) if self.down_norm[lvl] is not None else (None, None))
+            dims.append((h, w))
+        # ---- up path --------------------------------------------------------------------------------------------------
+        below = None
+        for lvl in range(nd - 1, -1, -1):
+            h, w = dims[lvl]
+            sc, sh = ss[lvl]
+            skip = self._apply(raw[lvl], sc, sh, ACT_RELU)                 # relu(norm(d_lvl)) (= relu of the skip half)
+            srcs = [skip] if lvl == nd - 1 else [skip, below]
+            if lvl == 0:
+                z, _ = self.up[0].run_tc(srcs, N, h, w, fuse_stats=False)
+                return ops.head_finish(z, self.out_bias, 2 * w, 1, self.out_nc, ACT_TANH)
+            y, ws = self.up[lvl].run_tc(srcs, N, h, w)
+            usc, ush = self._stats(y, self.up_norm[lvl], ws)
+            below = self._apply(y, usc, ush, ACT_RELU)                      # relu(norm(u_lvl)) for the level above
+            if taps is not None:
+                taps[f"up{lvl}"] = below
+
+    __call__ = forward
+
+
+class NLayerDEngine(_EngineBase):
+    """NLayerDiscriminator forward (networks.py:636-660): Conv4x4 s2 (+bias) LReLU; [Conv4x4 s2, Norm, LReLU] x (n-1);
+    Conv4x4 s1, Norm, LReLU; Conv4x4 s1 (-> 1, +bias).  Training-time module: norm_mode defaults to 'batch'."""
+
+    def __init__(self, sd, *, n_layers=3, norm="batch", norm_mode="batch", precision="bf16x3", backend="tc",
+                 device="cuda"):
+        prec = Precision.parse(precision) if isinstance(precision, str) else precision
+        super().__init__(norm, norm_mode, prec, backend, device)
+        g = lambda k: sd[k].to(device) if k in sd else None
+        self.first = ConvLayer(g("model.0.weight"), g("model.0.bias"), stride=2, pad=1, backend="direct")
+        self.mid = []
+        idx = 2
+        for n in range(1, n_layers + 1):
+            st = 2 if n < n_layers else 1
+            self.mid.append((ConvLayer(g(f"model.{idx}.weight"), g(f"model.{idx}.bias"), stride=st, pad=1, prec=prec,
+                                       backend=backend), _NormParams(sd, f"model.{idx + 1}", norm, device)))
+            idx += 3
+        wl, bl = g(f"model.{idx}.weight").to(torch.float32), g(f"model.{idx}.bias")
+        wl32, self.out_nc = _pad_cout32(wl, False)
+        self.last = ConvLayer(wl32, None, stride=1, pad=1, prec=prec, backend="tc", n_tile=32)
+        self.last_bias = bl.detach().to(torch.float32).contiguous()
+
+    @torch.no_grad()
+    def forward(self, x, taps=None):
+        """x: fp32 NCHW [N, 6, H, W] (cat of condition and image) -> fp32 NCHW [N, 1, h, w] logits."""
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        y = self.first.run_direct(x, N, H, W, in_nchw=True)
+        h, w = H // 2, W // 2
+        sc = sh = None
+        for cv, nm in self.mid:
+            a = self._apply(y, sc, sh, ACT_LRELU02)
+            y, ws = cv.run_tc([a], N, h, w)
+            h, w = y.shape[1], y.shape[2]
+            sc, sh = self._stats(y, nm, ws)
+        a = self._apply(y, sc, sh, ACT_LRELU02)
+        z, _ = self.last.run_tc([a], N, h, w, fuse_stats=False)
+        return ops.head_finish(z, self.last_bias, z.shape[2], 1, self.out_nc, ACT_NONE)
 
     __call__ = forward

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_apply", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -72,8 +72,23 @@ def pack_weights_direct(d, w):
     return out
 
 
-def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_tile=0, out=None):
-    """Tensor-core conv.  xs_hi/xs_lo: lists (one per source) of NHWC 16-bit planes.  Returns fp32 NHWC."""
+_WS_CACHE = {}
+
+
+def stats_workspace(N, HW, C, device):
+    """Zero-initialised statistics workspace (cached per shape/device; calls leave it clean)."""
+    key = (N, HW, C, str(device))
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        nbytes = _lib.load().dlb_norm_stats_workspace(N, HW, C)
+        ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_tile=0, out=None, stats_ws=None):
+    """Tensor-core conv.  xs_hi/xs_lo: lists (one per source) of NHWC 16-bit planes.  Returns fp32 NHWC.
+    stats_ws: workspace from stats_workspace(N, OH*OW, Cout) -> the epilogue also emits partial statistics."""
     xs_hi = list(xs_hi) if isinstance(xs_hi, (list, tuple)) else [xs_hi]
     xs_lo = (list(xs_lo) if isinstance(xs_lo, (list, tuple)) else [xs_lo]) if split else [None] * len(xs_hi)
     _need_cuda(*xs_hi, *xs_lo, w_hi, w_lo, bias)
@@ -83,7 +98,9 @@ def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_
     hi_arr = (C.c_void_p * 2)(*[x.data_ptr() for x in xs_hi] + [None] * (2 - len(xs_hi)))
     lo_arr = (C.c_void_p * 2)(*[(x.data_ptr() if x is not None else None) for x in xs_lo] + [None] * (2 - len(xs_lo)))
     check(_lib.load().dlb_conv_tc_fwd(C.byref(d), hi_arr, lo_arr, _p(w_hi), _p(w_lo) if split else None, _p(bias),
-                                      _p(out), fmt, int(split), n_tile, _stream()), "dlb_conv_tc_fwd")
+                                      _p(out), fmt, int(split), n_tile, _p(stats_ws),
+                                      stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
+          "dlb_conv_tc_fwd")
     LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
     return out
 
@@ -102,13 +119,23 @@ def conv_direct(d, x, w_packed, bias=None, in_nchw=False, in_scale=None, in_shif
     return out
 
 
+def norm_finalize(ws, N, HW, Cc, gamma=None, beta=None, pooled=False, eps=1e-5):
+    """Reduce the partial statistics a conv epilogue left in `ws` -> (scale, shift) fp32 [N,C]."""
+    scale = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
+    shift = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
+    check(_lib.load().dlb_norm_finalize(_p(ws), ws.numel() * 4, N, HW, Cc, int(pooled), _p(gamma), _p(beta),
+                                        float(eps), _p(scale), _p(shift), _stream()), "dlb_norm_finalize")
+    LAUNCHES["count"] += 1
+    return scale, shift
+
+
 def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5):
     """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift."""
     _need_cuda(y, gamma, beta)
     N, H, W, Cc = y.shape
     lib = _lib.load()
-    ws_bytes = lib.dlb_norm_stats_workspace(N, H * W, Cc)
-    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=y.device)
+    ws = stats_workspace(N, H * W, Cc, y.device)
+    ws_bytes = ws.numel() * 4
     scale = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
     shift = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
     check(lib.dlb_norm_stats(_p(y), N, H * W, Cc, int(pooled), _p(gamma), _p(beta), float(eps), _p(scale), _p(shift),
@@ -132,6 +159,30 @@ def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=
                                      N, H, W, Cc, pad, pad_mode, _stream()), "dlb_norm_apply")
     LAUNCHES["count"] += 1
     return f32, hi, lo
+
+
+def stem_window_pack(x_nchw, pad, S, pad_mode=PAD_ZERO, fmt=FMT_BF16, need_lo=True):
+    """x fp32 NCHW [N,C<=8,H,W] -> (hi, lo) planes [N, H+2pad, W, 64] with k = s*8 + c (see include)."""
+    _need_cuda(x_nchw)
+    N, Cc, H, W = x_nchw.shape
+    shp = (N, H + 2 * pad, W, 64)
+    hi = torch.empty(shp, dtype=_dtype(fmt), device=x_nchw.device)
+    lo = torch.empty(shp, dtype=_dtype(fmt), device=x_nchw.device) if need_lo else None
+    check(_lib.load().dlb_stem_window_pack(_p(x_nchw), N, Cc, H, W, pad, S, pad_mode, fmt, _p(hi), _p(lo), _stream()),
+          "dlb_stem_window_pack")
+    LAUNCHES["count"] += 1
+    return hi, lo
+
+
+def head_finish(z, bias, W, S, CO, act=ACT_TANH):
+    """z fp32 NHWC [N,H,W+S-1,32] -> fp32 NCHW [N,CO,H,W] (shifted tap sum + bias + activation)."""
+    _need_cuda(z, bias)
+    N, H, WZ, _ = z.shape
+    assert WZ == W + S - 1 and z.shape[3] == 32
+    out = torch.empty((N, CO, H, W), dtype=torch.float32, device=z.device)
+    check(_lib.load().dlb_head_finish(_p(z), _p(bias), N, H, W, S, CO, act, _p(out), _stream()), "dlb_head_finish")
+    LAUNCHES["count"] += 1
+    return out
 
 
 def u8_to_f32(img_nhwc):

@@ -1,0 +1,70 @@
+"""Tile-batched inference driver: uint8 tiles in (host) -> five uint8 outputs + posneg mask out (host).
+
+Replaces the reference's per-tile loop ``inference -> run_wrapper -> run_dask`` (deepliif/models/__init__.py:
+464-579, 258-361), which runs batch = 1 and converts PIL <-> tensor <-> PIL around every generator call, with a
+batched device pipeline: one H2D copy of the uint8 tiles, on-GPU ``transform`` (data/__init__.py:133-138), the
+generators in micro-batches sized for L2 residency, on-GPU ``tensor2im`` quantisation (util/util.py:130-135),
+seg aggregation + ``create_posneg_mask`` (models/__init__.py:338, postprocessing.py:163-190), one D2H copy of
+uint8 results.  Two graph shapes:
+
+  flat     : out_i = G_i(x), i = 1..5 (BASELINE.json configs 1-2: five ResNet-9 heads on the IHC tile; the
+             fifth is the Seg head)
+  cascade  : mods_i = G_i(x) (i = 1..4); seg = sum_k w_k * GS_k(x | mods_k)   (DeepLIIF_model.py:175-203)
+"""
+import torch
+
+from . import ops
+
+
+class TilePipeline:
+    def __init__(self, gens, segs=None, seg_weights=None, micro_batch=4, thresh=120):
+        """gens: list of callables fp32 NCHW -> fp32 NCHW (modalities).  segs: None (flat: last of `gens` is the
+        seg head) or list of len(gens)+1 seg generators (cascade)."""
+        self.gens, self.segs = list(gens), (list(segs) if segs is not None else None)
+        n_seg = len(self.segs) if self.segs is not None else 1
+        self.seg_weights = list(seg_weights) if seg_weights is not None else [1.0 / n_seg] * n_seg
+        self.micro_batch, self.thresh = micro_batch, thresh
+
+    @torch.no_grad()
+    def forward_device(self, x):
+        """x: fp32 NCHW on device.  Returns (list of modality fp32 NCHW, seg fp32 NCHW, seg_u8 NHWC, mask)."""
+        N = x.shape[0]
+        mb = self.micro_batch if self.micro_batch > 0 else N
+        mods_out, seg_out, segu8_out, mask_out = None, None, None, None
+        for s in range(0, N, mb):
+            xs = x[s:s + mb]
+            if self.segs is None:
+                outs = [g(xs) for g in self.gens]
+                mods, seg_in, w = outs[:-1], [outs[-1]], [1.0]
+            else:
+                mods = [g(xs) for g in self.gens]
+                seg_in = [self.segs[0](xs)] + [sg(m) for sg, m in zip(self.segs[1:], mods)]
+                w = self.seg_weights
+            seg, seg_u8, mask = ops.seg_finish(seg_in, w, self.thresh)
+            if mods_out is None:
+                mods_out = [torch.empty((N,) + tuple(m.shape[1:]), dtype=m.dtype, device=m.device) for m in mods]
+                seg_out = torch.empty((N,) + tuple(seg.shape[1:]), dtype=seg.dtype, device=seg.device)
+                segu8_out = torch.empty((N,) + tuple(seg_u8.shape[1:]), dtype=torch.uint8, device=seg.device)
+                mask_out = torch.empty((N,) + tuple(mask.shape[1:]), dtype=torch.uint8, device=seg.device)
+            for o, m in zip(mods_out, mods):
+                o[s:s + mb].copy_(m)
+            seg_out[s:s + mb].copy_(seg); segu8_out[s:s + mb].copy_(seg_u8); mask_out[s:s + mb].copy_(mask)
+        return mods_out, seg_out, segu8_out, mask_out
+
+    @torch.no_grad()
+    def infer_u8(self, tiles_u8_host, out_host=None):
+        """tiles_u8_host: pinned uint8 [N,H,W,3].  Returns dict of pinned uint8 host tensors:
+        'mods' [M,N,H,W,3], 'seg' [N,H,W,3], 'mask' [N,H,W].  Copies are part of the call (end-to-end path)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x_u8 = tiles_u8_host.to(dev, non_blocking=True)
+        x = ops.u8_to_f32(x_u8)
+        mods, seg, seg_u8, mask = self.forward_device(x)
+        mods_u8 = torch.stack([ops.f32_to_u8(m) for m in mods])
+        if out_host is None:
+            out_host = {"mods": torch.empty(mods_u8.shape, dtype=torch.uint8, pin_memory=True),
+                        "seg": torch.empty(seg_u8.shape, dtype=torch.uint8, pin_memory=True),
+                        "mask": torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)}
+        out_host["mods"].copy_(mods_u8, non_blocking=True)
+        out_host["seg"].copy_(seg_u8, non_blocking=True)
+        out_host["mask"].copy_(mask, non_blocking=True)
+        return out_host

@@ -69,10 +69,13 @@ int dlb_pack_weights_direct(const dlb_conv_desc* d, const float* w, float* w_pac
  * zero padding (reflect padding is produced by dlb_norm_apply into a padded operand buffer).
  * x_hi/x_lo: per source 16-bit NHWC planes; split != 0 selects the 3-MMA hi/lo scheme (fp32-grade
  * products), split == 0 a single pass on the hi planes.  y: fp32 NHWC [N, OH, OW, Cout].
- * n_tile: 0 = auto, or 64/128/256 (UMMA N). */
+ * n_tile: 0 = auto, or 64/128/256 (UMMA N).
+ * stats_ws (nullable): when given, the epilogue also writes per-slice partial statistics of y into the
+ * workspace (dlb_norm_stats_workspace(N, OH*OW, Cout) bytes, zero-initialised once at allocation), to be
+ * reduced by dlb_norm_finalize — this replaces the separate statistics read of y.  Needs OH*OW >= 128. */
 int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo, const void* w_hi,
                     const void* w_lo, const float* bias, float* y, int fmt, int split, int n_tile,
-                    dlb_stream_t stream);
+                    void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream);
 
 /* fp32 CUDA-core convolution for the layers tensor cores cannot tile (Cin = 3 stem, networks.py:386-397;
  * Cout = 3 head + Tanh, :438-444; PatchGAN first/last convs, :638, :659).  Fuses the producer's
@@ -88,17 +91,37 @@ int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, con
  * dlb_norm_stats: y fp32 NHWC [N, HW, C] -> per-(n,c) scale/shift such that norm(y) = y*scale + shift,
  *   scale = gamma * rstd, shift = beta - mean * scale (gamma/beta may be NULL = 1/0), biased variance.
  *   pooled != 0: statistics over N*HW (training-mode BatchNorm2d, N > 1), replicated for every n.
- *   Deterministic (fixed-order two-level reduction, no atomics).  workspace: dlb_norm_stats_workspace bytes.
+ *   Deterministic (fixed merge orders; the only atomic is a completion ticket).  workspace:
+ *   dlb_norm_stats_workspace bytes, zero-initialised once at allocation (calls leave it clean).
+ * dlb_norm_finalize: the reduction half of dlb_norm_stats, for partials written by dlb_conv_tc_fwd.
  * dlb_norm_apply: out = act(y*scale + shift) (+ residual), written as fp32 (out_f32) and/or as split
  *   16-bit planes (out_hi/out_lo) for the next tensor-core conv; `pad` > 0 writes the planes into a
  *   [N, H+2pad, W+2pad, C] buffer with a reflected (DLB_PAD_REFLECT) or zero border. */
 size_t dlb_norm_stats_workspace(int N, int HW, int C);
+int dlb_norm_finalize(void* workspace, size_t workspace_bytes, int N, int HW, int C, int pooled, const float* gamma,
+                      const float* beta, float eps, float* scale, float* shift, dlb_stream_t stream);
 int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
                    float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes,
                    dlb_stream_t stream);
 int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                    float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
                    int pad_mode, dlb_stream_t stream);
+
+/* Stem operand for the tensor cores.  The 7x7 Cin=3 stem conv (ReflectionPad2d/ZeroPad2d(3) + Conv2d(3, ngf, 7),
+ * networks.py:386-397) has K = 147, too ragged for 64-channel K chunks; this pass writes
+ *   Xw[n, hp, w, s*8 + c] = pad(x)[n, c, hp, w + s]   (s < S, c < C <= 8, zero elsewhere; [N, H+2pad, W, 64] planes)
+ * so that the stem becomes a vertical S=1, R=7, Cin=64 convolution for dlb_conv_tc_fwd with weights
+ * wk[co][s*8 + c][r] = w[co][c][r][s].  x: fp32 NCHW. */
+int dlb_stem_window_pack(const float* x_nchw, int N, int C, int H, int W, int pad, int S, int pad_mode, int fmt,
+                         void* out_hi, void* out_lo, dlb_stream_t stream);
+
+/* Head finish.  The 7x7 Cout=3 head (Pad(3) + Conv2d(ngf, 3, 7) + Tanh, networks.py:438-444) has N = 3, far too
+ * narrow for a tensor-core tile; it is run as a vertical R=7, S=1 convolution with the S horizontal taps moved
+ * into 32 virtual output channels j = s*4 + co (weights wv[j][c][r] = w[co][c][r][s]) over the operand padded
+ * by 3 (dlb_norm_apply pad=3), z = [N, H, W+S-1, 32]; this pass then forms
+ *   y[n, co, h, w] = act(bias[co] + sum_s z[n, h, w + s, s*4 + co])     (fp32 NCHW out). */
+int dlb_head_finish(const float* z, const float* bias, int N, int H, int W, int S, int CO, int act, float* y_nchw,
+                    dlb_stream_t stream);
 
 /* ---- pixel ends ------------------------------------------------------------------------------------
  * dlb_u8_to_f32: deepliif.data.transform (data/__init__.py:133-138): uint8 HWC -> fp32 NCHW in [-1,1].

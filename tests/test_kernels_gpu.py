@@ -138,6 +138,7 @@ def test_conv_direct(ops, case):
 # tensor-core conv (tcgen05)
 # ------------------------------------------------------------------------------------------------
 TC_CASES = [
+    ("k7x1_64_32_head", 1, 22, 70, [64], 32, (7, 1), 1, 0, False, 0, 32),
     # name, N, H, W, cins, Cout, R, stride, pad, transposed, outpad, n_tile
     ("k3s1_64_64_w16", 1, 8, 16, [64], 64, 3, 1, 1, False, 0, 0),
     ("k1s1_64_64", 2, 8, 16, [64], 64, 1, 1, 0, False, 0, 0),
@@ -165,14 +166,15 @@ def _tc_ref(x, w, b, st, pad, tr, op):
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv_tc(ops, case, prec):
     name, N, H, W, cins, Cout, R, st, pad, tr, op, n_tile = case
+    R, S = (R if isinstance(R, tuple) else (R, R))
     fmt = ops.FMT_FP16 if prec.startswith("fp16") else ops.FMT_BF16
     dt = torch.float16 if prec.startswith("fp16") else torch.bfloat16
     split = prec.endswith("x3")
     Cin = sum(cins)
     x = _rand((N, Cin, H, W), 21)
-    w = _rand((Cin, Cout, R, R) if tr else (Cout, Cin, R, R), 22, 0.05)
+    w = _rand((Cin, Cout, R, S) if tr else (Cout, Cin, R, S), 22, 0.05)
     b = _rand((Cout,), 23, 0.1)
-    d = ops.conv_desc(N, H, W, cins, Cout, R, R, st, pad, tr, op)
+    d = ops.conv_desc(N, H, W, cins, Cout, R, S, st, pad, tr, op)
     w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), fmt, split)
     xs = torch.split(x, cins, dim=1)
     planes = [split16(nhwc(xi), dt) for xi in xs]
@@ -194,3 +196,27 @@ def test_conv_tc(ops, case, prec):
         xr = torch.cat([p[0].float() for p in planes], dim=3)
         ref1 = _tc_ref(nchw(xr).double(), w.to(dt).double(), b.double(), st, pad, tr, op).float()
         assert (got - ref1).abs().max().item() < 2e-5 * scale
+
+
+@pytest.mark.parametrize("case", [("s1", 2, 16, 16, 64, 64, 3, 1, 1, False, 0), ("s2", 2, 32, 48, 64, 128, 3, 2, 1, False, 0),
+                                  ("ct", 2, 16, 16, 128, 64, 3, 2, 1, True, 1), ("ragged", 1, 21, 37, 64, 128, 3, 1, 1, False, 0),
+                                  ("big", 1, 128, 128, 64, 256, 3, 1, 1, False, 0)], ids=lambda c: c[0])
+@pytest.mark.parametrize("pooled", [False, True])
+def test_conv_tc_fused_stats(ops, case, pooled):
+    """Partial statistics from the conv epilogue + dlb_norm_finalize == statistics of the stored output."""
+    name, N, H, W, Cin, Cout, R, st, pad, tr, op = case
+    x = _rand((N, Cin, H, W), 31)
+    w = _rand((Cin, Cout, R, R) if tr else (Cout, Cin, R, R), 32, 0.05)
+    b = _rand((Cout,), 33, 0.5)
+    gamma = (1 + 0.1 * _rand((Cout,), 34)).cuda(); beta = (0.1 * _rand((Cout,), 35)).cuda()
+    d = ops.conv_desc(N, H, W, [Cin], Cout, R, R, st, pad, tr, op)
+    w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), ops.FMT_BF16, True)
+    hi, lo = split16(nhwc(x), torch.bfloat16)
+    oh, ow = ops.conv_out_shape(d)
+    ws = ops.stats_workspace(N, oh * ow, Cout, "cuda")
+    for rep in range(2):      # second round checks the workspace was left clean
+        y = ops.conv_tc(d, [hi.cuda()], [lo.cuda()], w_hi, w_lo, b.cuda(), ops.FMT_BF16, True, 0, stats_ws=ws)
+        sc, sh = ops.norm_finalize(ws, N, oh * ow, Cout, gamma, beta, pooled)
+        sc2, sh2 = ops.norm_stats(y, gamma, beta, pooled)
+        assert (sc - sc2).abs().max().item() <= 2e-6 * sc2.abs().max().item()
+        assert (sh - sh2).abs().max().item() <= 5e-6 * max(1.0, sh2.abs().max().item())
