@@ -86,80 +86,60 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
   }
 }
 
-// ---- finalize: merge slices -> scale/shift.  grid (C/32, N, G_cap), block 256 (8 warps, lane = channel). ---
-// Level 1: each block merges one group of 64 slices (8 per warp, then the 8 warps in order).  Level 2: the
-// last block to finish for a (n, channel-chunk) merges the groups in index order.  Every merge order is
-// fixed, so the result is deterministic although the identity of the last block is not.
-struct Moments { double n, mean, m2; };
-__device__ __forceinline__ void chan_merge(Moments& a, double nb, double mb, double Mb) {
-  if (nb <= 0.0) return;
-  const double nt = a.n + nb;
-  const double d = mb - a.mean;
-  a.mean += d * (nb / nt);
-  a.m2 += Mb + d * d * (a.n * nb / nt);
-  a.n = nt;
-}
-
-__global__ void __launch_bounds__(256) stats_finalize_kernel(StatsPtrs ws, int N, int C, int pooled,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float eps,
-                                                             float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ double sm[8][32][3];
+// ---- finalize: merge slices -> scale/shift.  grid (C/32, groups), block 1024 (32 warps, lane = channel). -------
+// Two independent-load passes over the slice partials instead of a serial Chan chain:
+//   pass 1: n = sum n_i, mean = sum(sum_i) / n;   pass 2: M2 = sum(M2_i + n_i * (mean_i - mean)^2).
+// Every thread accumulates its slices in index order (fp32), the 32 warps are combined in warp order (fp64):
+// fixed orders -> deterministic.  groups = N (per-sample statistics) or 1 (pooled over the batch).
+__global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int N, int C, int pooled,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double sm[32][33];
+  __shared__ double sm2[32][33];
   const int S = *ws.S;
-  const int G = (S + kSlicesPerGroup - 1) / kSlicesPerGroup;
-  const int g = blockIdx.z;
-  if (g >= G) return;
-  const int cchunk = blockIdx.x, n = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = cchunk * 32 + lane;
+  const int c = blockIdx.x * 32 + lane;
   const bool cok = c < C;
-  Moments m{0.0, 0.0, 0.0};
-  if (cok) {
-#pragma unroll
-    for (int i = 0; i < kSlicesPerGroup / 8; ++i) {
-      const int s = g * kSlicesPerGroup + w + 8 * i;
-      if (s < S) {
-        const float nb = ws.cnt[n * ws.S_cap + s];
-        if (nb > 0.f) {
-          const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
-          chan_merge(m, nb, static_cast<double>(pr.x) / nb, pr.y);
-        }
-      }
-    }
-  }
-  sm[w][lane][0] = m.n; sm[w][lane][1] = m.mean; sm[w][lane][2] = m.m2;
-  __syncthreads();
-  if (w != 0) return;
-  Moments t{0.0, 0.0, 0.0};
-#pragma unroll
-  for (int k = 0; k < 8; ++k) chan_merge(t, sm[k][lane][0], sm[k][lane][1], sm[k][lane][2]);
+  const int n_lo = pooled ? 0 : blockIdx.y, n_hi = pooled ? N : blockIdx.y + 1;
+  // pass 1
+  float cnt = 0.f, sum = 0.f;
   if (cok)
-    ws.group[(static_cast<long long>(n) * ws.G_cap + g) * C + c] =
-        make_float4(static_cast<float>(t.n), static_cast<float>(t.mean), static_cast<float>(t.m2), 0.f);
-  __threadfence();
-  int ticket = 0;
-  int* counter = ws.counters + (pooled ? N * ws.cchunks + cchunk : n * ws.cchunks + cchunk);
-  if (lane == 0) ticket = atomicAdd(counter, 1);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  const int expected = pooled ? N * G : G;
-  if (ticket != expected - 1) return;
-  __threadfence();
-  if (lane == 0) *counter = 0;                        // leave the workspace clean for the next call
-  if (!cok) return;
-  Moments f{0.0, 0.0, 0.0};
-  const int n_lo = pooled ? 0 : n, n_hi = pooled ? N : n + 1;
-  for (int nn = n_lo; nn < n_hi; ++nn)
-    for (int gg = 0; gg < G; ++gg) {
-      const float4 v = __ldcg(&ws.group[(static_cast<long long>(nn) * ws.G_cap + gg) * C + c]);
-      chan_merge(f, v.x, v.y, v.z);
-    }
-  const double var = f.m2 / f.n;                      // biased variance (PyTorch norm layers)
+    for (int n = n_lo; n < n_hi; ++n)
+      for (int s = w; s < S; s += 32) {
+        const float nb = ws.cnt[n * ws.S_cap + s];
+        const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
+        cnt += nb; sum += pr.x;
+      }
+  sm[w][lane] = cnt; sm2[w][lane] = sum;
+  __syncthreads();
+  double tn = 0.0, ts = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) { tn += sm[k][lane]; ts += sm2[k][lane]; }
+  const float mean = static_cast<float>(ts / tn);
+  __syncthreads();
+  // pass 2
+  float m2 = 0.f;
+  if (cok)
+    for (int n = n_lo; n < n_hi; ++n)
+      for (int s = w; s < S; s += 32) {
+        const float nb = ws.cnt[n * ws.S_cap + s];
+        const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
+        if (nb > 0.f) { const float d = pr.x / nb - mean; m2 += pr.y + nb * d * d; }
+      }
+  sm[w][lane] = m2;
+  __syncthreads();
+  if (w != 0 || !cok) return;
+  double tm = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) tm += sm[k][lane];
+  const double var = tm / tn;                         // biased variance (PyTorch norm layers)
   const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float ga = gamma ? gamma[c] : 1.f;
   const float be = beta ? beta[c] : 0.f;
   const float sc = ga * rstd;
-  const float sh = be - static_cast<float>(f.mean) * sc;
-  for (int nn = n_lo; nn < n_hi; ++nn) { scale[nn * C + c] = sc; shift[nn * C + c] = sh; }
+  const float sh = be - mean * sc;
+  for (int n = n_lo; n < n_hi; ++n) { scale[n * C + c] = sc; shift[n * C + c] = sh; }
 }
 
 // ---- apply: act(y*scale+shift) (+residual) -> fp32 and/or split 16-bit planes ---------------------
@@ -203,45 +183,61 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
     const float* __restrict__ rrow = p.residual ? p.residual + (static_cast<long long>(n) * p.H + h) * p.W * p.C : nullptr;
     float* __restrict__ frow = p.out_f32 ? p.out_f32 + (static_cast<long long>(n) * p.H + h) * p.W * p.C : nullptr;
     const long long drow = (static_cast<long long>(n) * HP + hp) * WP * p.C;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < row_quads; q += gridDim.x * blockDim.x) {
-      const int wp = q / c4n, cq = q - wp * c4n;
-      int w = wp - p.pad;
-      bool border = hborder || (w < 0) || (w >= p.W);
-      bool zero = false;
-      if (border) {
-        if (p.pad_mode == DLB_PAD_REFLECT) { if (w < 0) w = -w; if (w >= p.W) w = 2 * p.W - 2 - w; }
-        else zero = true;
-      }
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!zero) {
-        const int src = w * p.C + cq * 4;
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(yrow + src));
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-        if (p.scale != nullptr) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n * p.C + cq * 4));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n * p.C + cq * 4));
-          o[0] = fmaf(o[0], sc.x, sh.x); o[1] = fmaf(o[1], sc.y, sh.y);
-          o[2] = fmaf(o[2], sc.z, sh.z); o[3] = fmaf(o[3], sc.w, sh.w);
-        }
+    constexpr int U = 4;                                 // quads per thread: all loads are issued before any use
+    for (int q0 = blockIdx.x * blockDim.x * U + threadIdx.x; q0 < row_quads; q0 += gridDim.x * blockDim.x * U) {
+      float4 v[U], rv[U];
+      int srcs[U];
+      bool zero[U], border[U], live[U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = act1(o[k], p.act);
-        if (rrow != nullptr) {
-          const float4 rv = __ldcs(reinterpret_cast<const float4*>(rrow + src));
-          o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * blockDim.x;
+        live[u] = q < row_quads;
+        const int wp = q / c4n, cq = q - wp * c4n;
+        int w = wp - p.pad;
+        border[u] = hborder || (w < 0) || (w >= p.W);
+        zero[u] = false;
+        if (border[u]) {
+          if (p.pad_mode == DLB_PAD_REFLECT) { if (w < 0) w = -w; if (w >= p.W) w = 2 * p.W - 2 - w; }
+          else zero[u] = true;
         }
-        if (frow != nullptr && !border) *reinterpret_cast<float4*>(frow + src) = make_float4(o[0], o[1], o[2], o[3]);
+        srcs[u] = w * p.C + cq * 4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = v[u];
+        if (live[u] && !zero[u]) {
+          v[u] = __ldcs(reinterpret_cast<const float4*>(yrow + srcs[u]));
+          if (rrow != nullptr) rv[u] = __ldcs(reinterpret_cast<const float4*>(rrow + srcs[u]));
+        }
       }
-      if (p.out_hi != nullptr) {
-        const long long dst = drow + static_cast<long long>(q) * 4;
-        T16 hi[4], lo[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          hi[k] = Cvt<T16>::to(o[k]);
-          lo[k] = Cvt<T16>::to(o[k] - Cvt<T16>::from(hi[k]));
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+        const int q = q0 + u * blockDim.x;
+        const int cq = q % c4n;
+        float o[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        if (!zero[u]) {
+          if (p.scale != nullptr) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n * p.C + cq * 4));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n * p.C + cq * 4));
+            o[0] = fmaf(o[0], sc.x, sh.x); o[1] = fmaf(o[1], sc.y, sh.y);
+            o[2] = fmaf(o[2], sc.z, sh.z); o[3] = fmaf(o[3], sc.w, sh.w);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = act1(o[k], p.act);
+          o[0] += rv[u].x; o[1] += rv[u].y; o[2] += rv[u].z; o[3] += rv[u].w;
+          if (frow != nullptr && !border[u])
+            *reinterpret_cast<float4*>(frow + srcs[u]) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_hi) + dst) = *reinterpret_cast<uint2*>(hi);
-        if (p.out_lo != nullptr)
-          *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_lo) + dst) = *reinterpret_cast<uint2*>(lo);
+        if (p.out_hi != nullptr) {
+          const long long dst = drow + static_cast<long long>(q) * 4;
+          T16 hi[4], lo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            hi[k] = Cvt<T16>::to(o[k]);
+            lo[k] = Cvt<T16>::to(o[k] - Cvt<T16>::from(hi[k]));
+          }
+          *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_hi) + dst) = *reinterpret_cast<uint2*>(hi);
+          if (p.out_lo != nullptr)
+            *reinterpret_cast<uint2*>(reinterpret_cast<T16*>(p.out_lo) + dst) = *reinterpret_cast<uint2*>(lo);
+        }
       }
     }
   }
@@ -347,8 +343,8 @@ static int launch_finalize(void* workspace, int N, int HW, int C, int pooled, co
                            float eps, float* scale, float* shift, cudaStream_t stream) {
   const StatsLayout L = stats_layout(N, HW, C);
   const StatsPtrs ws = stats_ptrs(workspace, L);
-  dim3 grid(L.cchunks, N, L.G_cap);
-  stats_finalize_kernel<<<grid, 256, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift);
+  dim3 grid(L.cchunks, pooled ? 1 : N);
+  stats_finalize_kernel<<<grid, 1024, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_finalize_kernel launch");
   return 0;
 }
@@ -385,7 +381,7 @@ extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* s
   ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode};
   const int row_quads = (W + 2 * pad) * (C / 4);
   const int rows = N * (H + 2 * pad);
-  int gx = (row_quads + 255) / 256; if (gx > 64) gx = 64;
+  int gx = (row_quads + 1023) / 1024; if (gx > 64) gx = 64;
   dim3 grid(gx, rows < 65535 ? rows : 65535);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (fmt == DLB_FMT_BF16) norm_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);

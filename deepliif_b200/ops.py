@@ -77,7 +77,7 @@ _WS_CACHE = {}
 
 def stats_workspace(N, HW, C, device):
     """Zero-initialised statistics workspace (cached per shape/device; calls leave it clean)."""
-    key = (N, HW, C, str(device))
+    key = (N, HW, C, str(device), torch.cuda.current_stream().cuda_stream)   # one workspace per stream
     ws = _WS_CACHE.get(key)
     if ws is None:
         nbytes = _lib.load().dlb_norm_stats_workspace(N, HW, C)

@@ -17,39 +17,80 @@ from . import ops
 
 
 class TilePipeline:
-    def __init__(self, gens, segs=None, seg_weights=None, micro_batch=4, thresh=120):
+    def __init__(self, gens, segs=None, seg_weights=None, micro_batch=4, thresh=120, n_streams=1):
         """gens: list of callables fp32 NCHW -> fp32 NCHW (modalities).  segs: None (flat: last of `gens` is the
         seg head) or list of len(gens)+1 seg generators (cascade)."""
         self.gens, self.segs = list(gens), (list(segs) if segs is not None else None)
         n_seg = len(self.segs) if self.segs is not None else 1
         self.seg_weights = list(seg_weights) if seg_weights is not None else [1.0 / n_seg] * n_seg
         self.micro_batch, self.thresh = micro_batch, thresh
+        self.n_streams, self._stream_cache = n_streams, {}
 
     @torch.no_grad()
     def forward_device(self, x):
-        """x: fp32 NCHW on device.  Returns (list of modality fp32 NCHW, seg fp32 NCHW, seg_u8 NHWC, mask)."""
-        N = x.shape[0]
+        """x: fp32 NCHW on device.  Returns (list of modality fp32 NCHW, seg fp32 NCHW, seg_u8 NHWC, mask).
+
+        Independent (micro-batch, generator) chains are issued round-robin on `n_streams` CUDA streams: the
+        memory-bound passes of one chain (normalise/split, statistics) then overlap the tensor-core-bound
+        convolutions of another, and wave-quantisation tails are filled."""
+        N, _, H, W = x.shape
+        dev = x.device
         mb = self.micro_batch if self.micro_batch > 0 else N
-        mods_out, seg_out, segu8_out, mask_out = None, None, None, None
+        n_mod = len(self.gens) - (1 if self.segs is None else 0)
+        mods_out = [torch.empty((N, 3, H, W), dtype=torch.float32, device=dev) for _ in range(n_mod)]
+        seg_out = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+        segu8_out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev)
+        mask_out = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        main = torch.cuda.current_stream()
+        streams = self._streams(dev)
+        for st in streams:
+            st.wait_stream(main)
+        k = 0
         for s in range(0, N, mb):
             xs = x[s:s + mb]
             if self.segs is None:
-                outs = [g(xs) for g in self.gens]
-                mods, seg_in, w = outs[:-1], [outs[-1]], [1.0]
+                for i, g in enumerate(self.gens):
+                    st = streams[k % len(streams)]; k += 1
+                    with torch.cuda.stream(st):
+                        o = g(xs)
+                        if i < n_mod:
+                            mods_out[i][s:s + mb].copy_(o)
+                        else:
+                            seg, seg_u8, mask = ops.seg_finish([o], [1.0], self.thresh)
+                            seg_out[s:s + mb].copy_(seg); segu8_out[s:s + mb].copy_(seg_u8); mask_out[s:s + mb].copy_(mask)
             else:
-                mods = [g(xs) for g in self.gens]
-                seg_in = [self.segs[0](xs)] + [sg(m) for sg, m in zip(self.segs[1:], mods)]
-                w = self.seg_weights
-            seg, seg_u8, mask = ops.seg_finish(seg_in, w, self.thresh)
-            if mods_out is None:
-                mods_out = [torch.empty((N,) + tuple(m.shape[1:]), dtype=m.dtype, device=m.device) for m in mods]
-                seg_out = torch.empty((N,) + tuple(seg.shape[1:]), dtype=seg.dtype, device=seg.device)
-                segu8_out = torch.empty((N,) + tuple(seg_u8.shape[1:]), dtype=torch.uint8, device=seg.device)
-                mask_out = torch.empty((N,) + tuple(mask.shape[1:]), dtype=torch.uint8, device=seg.device)
-            for o, m in zip(mods_out, mods):
-                o[s:s + mb].copy_(m)
-            seg_out[s:s + mb].copy_(seg); segu8_out[s:s + mb].copy_(seg_u8); mask_out[s:s + mb].copy_(mask)
+                # cascade: modality chain i feeds seg generator i+1; the base seg generator reads the tile itself
+                parts = [None] * len(self.segs)
+                used = []
+                for i in range(len(self.segs)):
+                    st = streams[k % len(streams)]; k += 1
+                    used.append(st)
+                    with torch.cuda.stream(st):
+                        if i == 0:
+                            parts[0] = self.segs[0](xs)
+                        else:
+                            m = self.gens[i - 1](xs)
+                            mods_out[i - 1][s:s + mb].copy_(m)
+                            parts[i] = self.segs[i](m)
+                fin = used[0]
+                for st in used[1:]:
+                    fin.wait_stream(st)
+                with torch.cuda.stream(fin):
+                    seg, seg_u8, mask = ops.seg_finish(parts, self.seg_weights, self.thresh)
+                    seg_out[s:s + mb].copy_(seg); segu8_out[s:s + mb].copy_(seg_u8); mask_out[s:s + mb].copy_(mask)
+                for st in used[1:]:
+                    st.wait_stream(fin)      # parts stay alive until seg_finish has consumed them
+        for st in streams:
+            main.wait_stream(st)
         return mods_out, seg_out, segu8_out, mask_out
+
+    def _streams(self, dev):
+        if self.n_streams <= 1:
+            return [torch.cuda.current_stream()]
+        key = str(dev)
+        if key not in self._stream_cache:
+            self._stream_cache[key] = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
+        return self._stream_cache[key]
 
     @torch.no_grad()
     def infer_u8(self, tiles_u8_host, out_host=None):
