@@ -1,0 +1,149 @@
+"""`deepliif` console entry point: the `test` / `train` / `trainlaunch` commands of the reference CLI
+(/root/reference/cli.py:72-193, 573-758, 833-919) for the DeepLIIF model on the sm_100a path.
+
+  deepliif test --input-dir D --output-dir O --tile-size 512 --model-dir M [--gpu-ids 0] [--seg-intermediate]
+                [--seg-only] [--mod-only]         writes <stem>_<name>.png and <stem>.json per input image
+  deepliif train --dataroot D --name N ...        one process per GPU (see trainlaunch for several GPUs)
+  deepliif trainlaunch --use-torchrun "<torchrun args>" ...   spawns torchrun deepliif_b200/scripts_train.py
+
+There is no CPU fallback: `--gpu-ids -1` is rejected with a clear error (the reference would fall back to CPU).
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import click
+import torch
+from PIL import Image
+
+from .models import infer_modalities
+from .options import Options, print_options
+
+IMG_EXT = (".png", ".jpg", ".jpeg", ".tif", ".tiff", ".bmp")
+
+
+@click.group()
+def cli():
+    """Commonly used DeepLIIF batch operations (B200-native build)."""
+
+
+@cli.command()
+@click.option("--input-dir", default="./Sample_Large_Tissues/", help="reads images from here")
+@click.option("--output-dir", help="saves results here.")
+@click.option("--tile-size", type=click.IntRange(min=1), required=True, help="tile size")
+@click.option("--model-dir", default="./model-server/DeepLIIF_Latest_Model/", help="load models from here.")
+@click.option("--filename-pattern", default="*", help="run inference on files of which the name matches the pattern.")
+@click.option("--gpu-ids", type=int, multiple=True, help="gpu-ids 0 (one process drives one GPU)")
+@click.option("--eager-mode", is_flag=True, help="accepted for compatibility: models are always loaded from .pth files")
+@click.option("--epoch", default="latest", help="which epoch to load")
+@click.option("--seg-intermediate", is_flag=True, help="also save intermediate segmentation images")
+@click.option("--seg-only", is_flag=True, help="save only the final segmentation image; overwrites --seg-intermediate")
+@click.option("--mod-only", is_flag=True, help="save only the translated modality images")
+@click.option("--color-dapi", is_flag=True)
+@click.option("--color-marker", is_flag=True)
+def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids, eager_mode, epoch, seg_intermediate,
+         seg_only, mod_only, color_dapi, color_marker):
+    """Test trained models"""
+    output_dir = output_dir or input_dir
+    os.makedirs(output_dir, exist_ok=True)
+    if mod_only:
+        seg_only = seg_intermediate = False
+    elif seg_only:
+        seg_intermediate = False
+    if filename_pattern == "*":
+        image_files = sorted(fn for fn in os.listdir(input_dir) if fn.lower().endswith(IMG_EXT))
+    else:
+        image_files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(input_dir, filename_pattern)))
+    print(len(image_files), "image files")
+    assert "train_opt.txt" in os.listdir(model_dir), f"file train_opt.txt is missing from model directory {model_dir}"
+    if gpu_ids and gpu_ids[0] == -1:
+        raise click.UsageError("deepliif_b200 has no CPU path: --gpu-ids -1 is not available")
+    if not torch.cuda.is_available():
+        raise click.UsageError("deepliif_b200 needs a CUDA (sm_100a) device")
+    torch.cuda.set_device(gpu_ids[0] if gpu_ids else 0)
+    opt = Options(path_file=os.path.join(model_dir, "train_opt.txt"), mode="test")
+    opt.epoch = epoch
+    opt.gpu_ids = list(gpu_ids) if gpu_ids else [torch.cuda.current_device()]
+    seg_weights = getattr(opt, "seg_weights", None)
+    print_options(opt)
+    with click.progressbar(image_files, label=f"Processing {len(image_files)} images", item_show_func=lambda fn: fn) as bar:
+        for filename in bar:
+            img = Image.open(os.path.join(input_dir, filename)).convert("RGB")
+            images, scoring = infer_modalities(img, tile_size, model_dir, True, color_dapi, color_marker, opt,
+                                               return_seg_intermediate=seg_intermediate, seg_only=seg_only,
+                                               mod_only=mod_only, seg_weights=seg_weights)
+            stem = filename[: filename.rfind(".")]
+            for name, im in images.items():
+                im.save(os.path.join(output_dir, f"{stem}_{name}.png"))
+            if scoring is not None:
+                with open(os.path.join(output_dir, f"{stem}.json"), "w") as f:
+                    json.dump(scoring, f, indent=2)
+
+
+TRAIN_DEFAULTS = dict(
+    dataroot=None, name="experiment_name", checkpoints_dir="./checkpoints", gpu_ids=(), model="DeepLIIF", seg_weights=None,
+    loss_weights_g=None, loss_weights_d=None, input_nc=3, output_nc=3, ngf=64, ndf=64, net_d="n_layers", net_g="resnet_9blocks",
+    net_gs="unet_512", n_layers_d=4, norm="batch", init_type="normal", init_gain=0.02, no_dropout=False, padding="zero",
+    upsample="convtranspose", direction="AtoB", serial_batches=False, num_threads=4, batch_size=1, load_size=512,
+    crop_size=512, max_dataset_size=None, preprocess="resize_and_crop", no_flip=False, display_winsize=512, epoch="latest",
+    load_iter=0, verbose=False, lambda_l1=100.0, is_train=True, save_latest_freq=500, save_epoch_freq=100,
+    save_by_iter=False, continue_train=False, epoch_count=1, phase="train", lr_policy="linear", n_epochs=100,
+    n_epochs_decay=100, optimizer="adam", beta1=0.5, lr_g=0.0002, lr_d=0.0002, lr_decay_iters=50, gan_mode="vanilla",
+    gan_mode_s="lsgan", pool_size=50, seed=None, modalities_no=4, seg_gen=True, print_freq=100, dataset_mode="aligned",
+    input_no=1, scale_size=512, with_val=False, precision="bf16x3")
+
+
+@cli.command()
+@click.option("--dataroot", required=True, help="path to images (should have subfolders train, val)")
+@click.option("--name", default="experiment_name")
+@click.option("--checkpoints-dir", default="./checkpoints")
+@click.option("--gpu-ids", type=int, multiple=True)
+@click.option("--batch-size", default=1)
+@click.option("--modalities-no", default=4, type=int)
+@click.option("--seg-gen", type=bool, default=True)
+@click.option("--net-g", default="resnet_9blocks")
+@click.option("--net-gs", default="unet_512")
+@click.option("--net-d", default="n_layers")
+@click.option("--norm", default="batch")
+@click.option("--no-dropout", is_flag=True)
+@click.option("--padding", default="zero")
+@click.option("--n-epochs", default=100)
+@click.option("--n-epochs-decay", default=100)
+@click.option("--lr-g", default=0.0002)
+@click.option("--lr-d", default=0.0002)
+@click.option("--optimizer", default="adam")
+@click.option("--gan-mode", default="vanilla")
+@click.option("--gan-mode-s", default="lsgan")
+@click.option("--seed", type=int, default=None)
+@click.option("--save-epoch-freq", default=100)
+@click.option("--print-freq", default=100)
+@click.option("--continue-train", is_flag=True)
+@click.option("--epoch", default="latest")
+@click.option("--num-threads", default=4)
+@click.option("--max-dataset-size", type=int, default=None)
+def train(**kw):
+    """General-purpose training script for the DeepLIIF multi-task image-to-image translation model."""
+    from . import training
+    params = dict(TRAIN_DEFAULTS)
+    params.update({k: v for k, v in kw.items() if v is not None})
+    training.run_training(params)
+
+
+@cli.command(context_settings=dict(ignore_unknown_options=True, allow_extra_args=True))
+@click.option("--use-torchrun", type=str, default=None, help='torchrun options, e.g. "--nproc_per_node 8"')
+@click.pass_context
+def trainlaunch(ctx, use_torchrun):
+    """Launch `train` under torchrun: one process per GPU, gradients all-reduced over NCCL (reference cli.py:697-758)."""
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts_train.py")
+    if use_torchrun:
+        cmd = [sys.executable, "-m", "torch.distributed.run", *use_torchrun.split(), script, *ctx.args]
+    else:
+        cmd = [sys.executable, script, *ctx.args]
+    print("launching:", " ".join(cmd))
+    sys.exit(subprocess.run(cmd).returncode)
+
+
+if __name__ == "__main__":
+    cli()

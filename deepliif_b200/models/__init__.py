@@ -1,0 +1,214 @@
+"""Model factory and inference helpers with the reference's public names and argument meaning
+(deepliif/models/__init__.py:101-660): create_model, init_nets, run_dask, run_wrapper, inference, infer_modalities.
+
+What changes underneath: the reference runs one tile at a time (batch 1, PIL <-> tensor around every net, Dask
+threads across nets, nets spread over GPUs).  Here all tiles of an image form one uint8 batch that goes through
+``TilePipeline`` (H2D once, on-GPU transform, all generators on the sm_100a kernels in micro-batches, on-GPU
+quantisation, D2H of uint8 results); several GPUs shard tiles, not networks (deepliif_b200/sharding.py).
+Out of scope: TorchScript (.pt) loading, TorchServe, Dask, WSI readers, numba cell post-processing —
+``infer_modalities`` returns the on-device posneg mask statistics instead of the cell-level scoring dict."""
+import importlib
+import os
+from functools import lru_cache
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .base_model import BaseModel
+from ..options import Options, print_options
+from ..pipeline import TilePipeline
+from ..util import TileGrid, disable_batchnorm_tracking_stats, image_variance_gray
+from ..util.util import tensor_to_pil
+
+Image.MAX_IMAGE_PIXELS = None
+EMPTY_TILE_VARIANCE = 9          # is_empty(): tiles with gray-level variance below this skip the networks
+
+
+def find_model_using_name(model_name):
+    """deepliif_b200.models.<model_name>_model.<ModelName>Model (case-insensitive), a BaseModel subclass."""
+    try:
+        modellib = importlib.import_module(f"deepliif_b200.models.{model_name}_model")
+    except ImportError:
+        raise NotImplementedError(f"model [{model_name}] is outside the B200 hot-path scope (DeepLIIF only)")
+    target = model_name.replace("_", "") + "model"
+    for name, cls in vars(modellib).items():
+        if name.lower() == target.lower() and isinstance(cls, type) and issubclass(cls, BaseModel):
+            return cls
+    raise NotImplementedError(f"In {model_name}_model.py, there should be a subclass of BaseModel named {target}")
+
+
+def create_model(opt):
+    instance = find_model_using_name(opt.model)(opt)
+    print("model [%s] was created" % type(instance).__name__)
+    return instance
+
+
+def load_eager_models(opt, devices=None):
+    model = create_model(opt)
+    model.setup(opt)
+    nets = {}
+    for name in (devices.keys() if devices else model.model_names):
+        net = getattr(model, "net" + name)
+        if opt.phase != "train":
+            net = disable_batchnorm_tracking_stats(net.eval())
+        nets[name] = net.module if hasattr(net, "module") and not hasattr(net, "engine") else net
+        if devices:
+            nets[name].to(devices[name])
+    return nets
+
+
+@lru_cache
+def get_opt(model_dir, mode="test"):
+    return Options(path_file=os.path.join(model_dir, "train_opt.txt"), mode=mode)
+
+
+@lru_cache
+def init_nets(model_dir, eager_mode=True, opt=None, phase="test"):
+    """dict[name -> callable net] for a model directory (train_opt.txt + latest_net_*.pth), built once.
+    Only the eager path exists here: serialized TorchScript (.pt) models are cuDNN graphs, out of scope."""
+    if opt is None:
+        opt = get_opt(model_dir, mode=phase)
+    if opt.model != "DeepLIIF":
+        raise Exception(f"init_nets() not implemented for model {opt.model}")
+    opt.phase = phase
+    if not hasattr(opt, "epoch"):
+        opt.epoch = "latest"
+    return load_eager_models(opt)
+
+
+def _names(opt):
+    S, base = opt.mod_id_seg, int(opt.input_id)
+    gens = [f"G{i + 1}" for i in range(opt.modalities_no)]
+    segs = [f"G{S}{i + base}" for i in range(opt.modalities_no + 1)] if opt.seg_gen else []
+    return gens, segs
+
+
+def _seg_weights(opt, seg_weights):
+    if seg_weights is not None:
+        return list(seg_weights)
+    return [1 / (opt.modalities_no + 1)] * (opt.modalities_no + 1)
+
+
+def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=4, n_streams=2):
+    """uint8 tiles [T,ts,ts,3] (numpy) -> dict[name -> uint8 [T,ts,ts,3]] with the reference's result keys
+    (G1.., G{S}, and per-modality seg G{S}k), skipping empty tiles exactly like run_wrapper (:399-443)."""
+    gens, segs = _names(opt)
+    T, ts = tiles_u8.shape[0], tiles_u8.shape[1]
+    S = opt.mod_id_seg
+    keys = list(gens) + ([f"G{S}"] + segs if (segs and not mod_only) else [])
+    out = {k: np.zeros((T, ts, ts, 3), np.uint8) for k in keys}
+    live = [i for i in range(T) if image_variance_gray(tiles_u8[i]) >= EMPTY_TILE_VARIANCE]
+    for i in set(range(T)) - set(live):
+        for j, k in enumerate(gens):
+            out[k][i] = np.array(opt.background_colors[j], np.uint8)
+    if live:
+        batch = torch.from_numpy(np.ascontiguousarray(tiles_u8[live])).pin_memory()
+        w = _seg_weights(opt, seg_weights)
+        pipe = TilePipeline([nets[k] for k in gens], [nets[k] for k in segs] if (segs and not mod_only) else None,
+                            w, micro_batch=micro_batch, n_streams=n_streams)
+        if segs and not mod_only:
+            res = pipe.infer_u8(batch, want_parts=True)
+            torch.cuda.synchronize()
+            out[f"G{S}"][live] = res["seg"].numpy()
+            for j, k in enumerate(segs):
+                out[k][live] = res["parts"][j].numpy()
+        else:
+            res = pipe.infer_mods_u8(batch)
+            torch.cuda.synchronize()
+        for j, k in enumerate(gens):
+            out[k][live] = res["mods"][j].numpy()
+    return out
+
+
+def run_dask(img, model_path=None, nets=None, eager_mode=True, opt=None, seg_only=False, mod_only=False,
+             seg_weights=None, use_dask=False, output_tensor=False):
+    """Single-tile entry kept for API compatibility (name from the reference; nothing here uses Dask)."""
+    assert model_path is not None or nets is not None, "Provide either the model path or the networks object."
+    if nets is None:
+        nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
+    tile = np.asarray(img.resize((opt.scale_size, opt.scale_size)).convert("RGB"))[None]
+    res = run_batch(tile, nets, opt, seg_weights, mod_only)
+    out = {k: Image.fromarray(v[0]) for k, v in res.items()}
+    if seg_only:
+        keep = [f"G{opt.mod_id_seg}", f"G{opt.modalities_no}"]
+        out = {k: v for k, v in out.items() if k in keep}
+    return out
+
+
+def run_wrapper(tile, run_fn, model_path=None, nets=None, eager_mode=True, opt=None, seg_only=False, mod_only=False,
+                seg_weights=None, use_dask=False, output_tensor=False):
+    return run_fn(tile, model_path, nets, eager_mode, opt, seg_only, mod_only, seg_weights)
+
+
+def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, eager_mode=True, color_dapi=False,
+              color_marker=False, opt=None, return_seg_intermediate=False, seg_only=False, mod_only=False,
+              seg_weights=None, opt_args={}):
+    """PIL image -> dict[name -> PIL image] with the reference's output names (mod{i}-{Name}, Seg, {mod}_s)."""
+    if use_torchserve:
+        raise NotImplementedError("TorchServe is outside the B200 hot-path scope")
+    if opt is None:
+        opt = get_opt(model_path)
+    for k, v in opt_args.items():
+        setattr(opt, k, v)
+    if seg_weights is None and hasattr(opt, "seg_weights"):
+        seg_weights = opt.seg_weights
+    nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
+    grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
+    tiles = grid.tiles()
+    if tile_size != opt.scale_size:
+        tiles = np.stack([np.asarray(Image.fromarray(t).resize((opt.scale_size, opt.scale_size))) for t in tiles])
+    res = run_batch(tiles, nets, opt, seg_weights, mod_only)
+    results = {}
+    for k, v in res.items():
+        if tile_size != opt.scale_size:
+            v = np.stack([np.asarray(Image.fromarray(t).resize((tile_size, tile_size))) for t in v])
+        results[k] = Image.fromarray(grid.stitch(v))
+    # ---- the reference's naming (models/__init__.py:502-565) -----------------------------------------------
+    n, S = opt.modalities_no, opt.mod_id_seg
+    names = opt.modalities_names
+    mod_names = [f"mod{i + 1}" for i in range(n)]
+    if mod_names != names[opt.input_no:]:
+        mod_names = [f"mod{i + 1}-{nm}" for i, nm in enumerate(names[opt.input_no:])]
+    name2id = {nm: f"G{i + 1}" for i, nm in enumerate(mod_names)}
+    if not mod_only and opt.seg_gen:
+        name2id["Seg"] = f"G{S}"
+    if seg_only:
+        images = {"Seg": results[name2id["Seg"]]}
+        marker = [k for k in name2id if k.endswith("Marker")]
+        if marker:
+            images[marker[0]] = results[name2id[marker[0]]]
+        return images
+    images = {nm: results[mid] for nm, mid in name2id.items()}
+    if opt.seg_gen and return_seg_intermediate and not mod_only:
+        seg_names = [f"mod{i}" for i in range(n + 1)]
+        if seg_names != names:
+            seg_names = [f"mod{i}-{nm}" for i, nm in enumerate(names)]
+        base = 0 if f"G{S}0" in results else 1
+        images.update({f"{nm}_s": results[f"G{S}{i + base}"] for i, nm in enumerate(seg_names)})
+    return images
+
+
+def posneg_summary(seg_img, thresh=120):
+    """Pixel-level summary of create_posneg_mask on the stitched Seg image (the cell-level numba post-processing
+    of the reference, postprocessing.py:1223-1304, is out of scope)."""
+    a = np.asarray(seg_img).astype(np.int64)
+    hit = (a[..., 0] + a[..., 2] > thresh) & (a[..., 1] <= 80)
+    pos = int((hit & (a[..., 0] >= a[..., 2])).sum())
+    neg = int((hit & (a[..., 0] < a[..., 2])).sum())
+    return {"num_pos_pixels": pos, "num_neg_pixels": neg,
+            "percent_pos_pixels": round(100.0 * pos / (pos + neg), 1) if pos + neg else 0.0}
+
+
+def infer_modalities(img, tile_size, model_dir, eager_mode=True, color_dapi=False, color_marker=False, opt=None,
+                     return_seg_intermediate=False, seg_only=False, mod_only=False, seg_weights=None):
+    if opt is None:
+        opt = get_opt(model_dir)
+    if not tile_size:
+        tile_size = opt.scale_size
+    images = inference(img, tile_size=tile_size, overlap_size=tile_size // 16, model_path=model_dir,
+                       eager_mode=True, color_dapi=color_dapi, color_marker=color_marker, opt=opt,
+                       return_seg_intermediate=return_seg_intermediate, seg_only=seg_only, mod_only=mod_only,
+                       seg_weights=seg_weights)
+    scoring = posneg_summary(images["Seg"]) if "Seg" in images else None
+    return images, scoring

@@ -124,11 +124,6 @@ class _EngineBacked(nn.Module):
         return self.engine().forward(input.float())
 
 
-def _norm_mods(norm_layer, c):
-    m = norm_layer(c)
-    return [m]
-
-
 class ResnetBlock(nn.Module):
     """x + conv_block(x); conv_block indices follow networks.py:479-506 (pad modules, optional dropout)."""
 
@@ -183,14 +178,162 @@ class ResnetGenerator(_EngineBacked):
                                     **self.cfg)
 
 
-def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02,
-             gpu_ids=[], padding_type="reflect", upsample="convtranspose"):
-    """Create a generator (reference signature, networks.py:142-144)."""
+# ------------------------------------------------------------------------------------------------------------
+# UnetGenerator / NLayerDiscriminator containers (state_dict layout of networks.py:516-664)
+# ------------------------------------------------------------------------------------------------------------
+class UnetSkipConnectionBlock(nn.Module):
+    """Parameter container for one U-Net level; module order inside ``self.model`` fixes the state_dict keys:
+    outermost [conv, sub, relu, convT, tanh]; innermost [lrelu, conv, relu, convT, norm];
+    middle [lrelu, conv, norm, sub, relu, convT, norm, (dropout)]."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super().__init__()
+        self.outermost = outermost
+        bias = _norm_name(norm_layer) == "instance"
+        cin = outer_nc if input_nc is None else input_nc
+        down = nn.Conv2d(cin, inner_nc, kernel_size=4, stride=2, padding=1, bias=bias)
+        if outermost:
+            seq = [down, submodule, nn.ReLU(True),
+                   nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1), nn.Tanh()]
+        elif innermost:
+            seq = [nn.LeakyReLU(0.2, True), down, nn.ReLU(True),
+                   nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=bias),
+                   norm_layer(outer_nc)]
+        else:
+            seq = [nn.LeakyReLU(0.2, True), down, norm_layer(inner_nc), submodule, nn.ReLU(True),
+                   nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=bias),
+                   norm_layer(outer_nc)]
+            if use_dropout:
+                seq.append(nn.Dropout(0.5))
+        self.model = nn.Sequential(*seq)
+
+
+class UnetGenerator(_EngineBacked):
+    def __init__(self, input_nc, output_nc, num_downs, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super().__init__()
+        self.cfg = dict(num_downs=num_downs, norm=_norm_name(norm_layer))
+        blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, norm_layer=norm_layer, innermost=True)
+        for _ in range(num_downs - 5):
+            blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, submodule=blk, norm_layer=norm_layer, use_dropout=use_dropout)
+        for mult in (4, 2, 1):
+            blk = UnetSkipConnectionBlock(ngf * mult, ngf * mult * 2, submodule=blk, norm_layer=norm_layer)
+        self.model = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=blk, outermost=True,
+                                             norm_layer=norm_layer)
+
+    def _build_engine(self, device):
+        return _engine.UnetEngine(self.state_dict(), device=device, precision=self.precision,
+                                  norm_mode="batch" if (self.training and self.cfg["norm"] == "batch") else "sample",
+                                  **self.cfg)
+
+
+class NLayerDiscriminator(_EngineBacked):
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_spectral_norm=False):
+        super().__init__()
+        if use_spectral_norm:
+            raise NotImplementedError("spectral norm is outside the B200 hot-path scope")
+        self.cfg = dict(n_layers=n_layers, norm=_norm_name(norm_layer))
+        bias = self.cfg["norm"] == "instance"
+        seq = [nn.Conv2d(input_nc, ndf, kernel_size=4, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        mult = 1
+        for n in range(1, n_layers + 1):
+            prev, mult = mult, min(2 ** n, 8)
+            seq += [nn.Conv2d(ndf * prev, ndf * mult, kernel_size=4, stride=2 if n < n_layers else 1, padding=1, bias=bias),
+                    norm_layer(ndf * mult), nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(ndf * mult, 1, kernel_size=4, stride=1, padding=1)]
+        self.model = nn.Sequential(*seq)
+
+    def _build_engine(self, device):
+        # the discriminator only exists in training: BatchNorm2d uses pooled batch statistics
+        return _engine.NLayerDEngine(self.state_dict(), device=device, precision=self.precision,
+                                     norm_mode="batch" if self.cfg["norm"] == "batch" else "sample", **self.cfg)
+
+
+_UNET_DOWNS = {"unet_32": 5, "unet_64": 6, "unet_128": 7, "unet_256": 8, "unet_512": 9}
+
+
+def _define_G_impl(input_nc, output_nc, ngf, netG, norm, use_dropout, padding_type, upsample):
     norm_layer = get_norm_layer(norm_type=norm)
     if netG.startswith("resnet_"):
         n_blocks = int(netG.split("_")[1].replace("blocks", ""))
-        net = ResnetGenerator(input_nc, output_nc, ngf, norm_layer=norm_layer, use_dropout=use_dropout,
-                              n_blocks=n_blocks, padding_type=padding_type, upsample=upsample)
-    else:
-        raise NotImplementedError("Generator model name [%s] is not recognized" % netG)
+        return ResnetGenerator(input_nc, output_nc, ngf, norm_layer=norm_layer, use_dropout=use_dropout,
+                               n_blocks=n_blocks, padding_type=padding_type, upsample=upsample)
+    if netG in _UNET_DOWNS:
+        return UnetGenerator(input_nc, output_nc, _UNET_DOWNS[netG], ngf, norm_layer=norm_layer, use_dropout=use_dropout)
+    if netG == "unet_512_attention":
+        raise NotImplementedError("Generator model name [unet_512_attention] is outside the B200 hot-path scope")
+    raise NotImplementedError("Generator model name [%s] is not recognized" % netG)
+
+
+def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02,
+             gpu_ids=[], padding_type="reflect", upsample="convtranspose"):
+    """Create a generator (reference signature, networks.py:142-144): resnet_{n}blocks | unet_{32..512}."""
+    net = _define_G_impl(input_nc, output_nc, ngf, netG, norm, use_dropout, padding_type, upsample)
     return init_net(net, init_type, init_gain, gpu_ids)
+
+
+def define_D(input_nc, ndf, netD, n_layers_D=3, norm="batch", init_type="normal", init_gain=0.02, gpu_ids=[]):
+    """Create a discriminator (networks.py:196): basic (70x70 PatchGAN) | n_layers."""
+    norm_layer = get_norm_layer(norm_type=norm)
+    if netD == "basic":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers=3, norm_layer=norm_layer)
+    elif netD == "n_layers":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers_D, norm_layer=norm_layer)
+    elif netD == "pixel":
+        raise NotImplementedError("Discriminator model name [pixel] is outside the B200 hot-path scope")
+    else:
+        raise NotImplementedError("Discriminator model name [%s] is not recognized" % netD)
+    return init_net(net, init_type, init_gain, gpu_ids)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# losses / schedulers (tiny tensors: plain torch, as the reference; networks.py:46-81, 244-317)
+# ------------------------------------------------------------------------------------------------------------
+OPTIMIZER_MAPPING = {n.lower(): n for n in dir(torch.optim) if n[0].isupper()}
+
+
+def get_optimizer(optimizer_name):
+    name = optimizer_name if hasattr(torch.optim, optimizer_name) else OPTIMIZER_MAPPING.get(optimizer_name)
+    if name is None:
+        raise NotImplementedError("optimizer [%s] is not found" % optimizer_name)
+    return getattr(torch.optim, name)
+
+
+def get_scheduler(optimizer, opt):
+    from torch.optim import lr_scheduler
+    if opt.lr_policy == "linear":
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda epoch: 1.0 - max(0, epoch + opt.epoch_count - opt.n_epochs)
+                                     / float(opt.n_epochs_decay + 1))
+    if opt.lr_policy == "step":
+        return lr_scheduler.StepLR(optimizer, step_size=opt.lr_decay_iters, gamma=0.1)
+    if opt.lr_policy == "plateau":
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=0.2, threshold=0.01, patience=5)
+    if opt.lr_policy == "cosine":
+        return lr_scheduler.CosineAnnealingLR(optimizer, T_max=opt.n_epochs, eta_min=0)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
+class GANLoss(nn.Module):
+    """vanilla -> BCEWithLogits, lsgan -> MSE against a constant label map (networks.py:244-317)."""
+
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0):
+        super().__init__()
+        self.register_buffer("real_label", torch.tensor(target_real_label))
+        self.register_buffer("fake_label", torch.tensor(target_fake_label))
+        self.gan_mode = gan_mode
+        if gan_mode == "lsgan":
+            self.loss = nn.MSELoss()
+        elif gan_mode == "vanilla":
+            self.loss = nn.BCEWithLogitsLoss()
+        elif gan_mode == "wgangp":
+            self.loss = None
+        else:
+            raise NotImplementedError("gan mode %s not implemented" % gan_mode)
+
+    def get_target_tensor(self, prediction, target_is_real):
+        return (self.real_label if target_is_real else self.fake_label).expand_as(prediction)
+
+    def __call__(self, prediction, target_is_real):
+        if self.gan_mode in ("lsgan", "vanilla"):
+            return self.loss(prediction, self.get_target_tensor(prediction, target_is_real))
+        return -prediction.mean() if target_is_real else prediction.mean()

@@ -41,6 +41,9 @@ class TilePipeline:
         seg_out = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
         segu8_out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev)
         mask_out = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        keep_parts = getattr(self, "_keep_parts", None) is not None and self.segs is not None
+        self._parts_out = ([torch.empty((N, 3, H, W), dtype=torch.float32, device=dev) for _ in self.segs]
+                           if keep_parts else None)
         main = torch.cuda.current_stream()
         streams = self._streams(dev)
         for st in streams:
@@ -72,6 +75,8 @@ class TilePipeline:
                             m = self.gens[i - 1](xs)
                             mods_out[i - 1][s:s + mb].copy_(m)
                             parts[i] = self.segs[i](m)
+                        if keep_parts:
+                            self._parts_out[i][s:s + mb].copy_(parts[i])
                 fin = used[0]
                 for st in used[1:]:
                     fin.wait_stream(st)
@@ -93,14 +98,18 @@ class TilePipeline:
         return self._stream_cache[key]
 
     @torch.no_grad()
-    def infer_u8(self, tiles_u8_host, out_host=None):
+    def infer_u8(self, tiles_u8_host, out_host=None, want_parts=False):
         """tiles_u8_host: pinned uint8 [N,H,W,3].  Returns dict of pinned uint8 host tensors:
-        'mods' [M,N,H,W,3], 'seg' [N,H,W,3], 'mask' [N,H,W].  Copies are part of the call (end-to-end path)."""
+        'mods' [M,N,H,W,3], 'seg' [N,H,W,3], 'mask' [N,H,W] (+ 'parts' [K,N,H,W,3], the per-modality seg outputs,
+        when want_parts).  Copies are part of the call (end-to-end path); the D2H copies are asynchronous on the
+        current stream — synchronise before reading."""
         dev = torch.device("cuda", torch.cuda.current_device())
         x_u8 = tiles_u8_host.to(dev, non_blocking=True)
         x = ops.u8_to_f32(x_u8)
+        self._keep_parts = [] if want_parts else None
         mods, seg, seg_u8, mask = self.forward_device(x)
-        mods_u8 = torch.stack([ops.f32_to_u8(m) for m in mods])
+        mods_u8 = torch.stack([ops.f32_to_u8(m) for m in mods]) if mods else torch.empty((0,) + tuple(seg_u8.shape),
+                                                                                          dtype=torch.uint8, device=dev)
         if out_host is None:
             out_host = {"mods": torch.empty(mods_u8.shape, dtype=torch.uint8, pin_memory=True),
                         "seg": torch.empty(seg_u8.shape, dtype=torch.uint8, pin_memory=True),
@@ -108,4 +117,20 @@ class TilePipeline:
         out_host["mods"].copy_(mods_u8, non_blocking=True)
         out_host["seg"].copy_(seg_u8, non_blocking=True)
         out_host["mask"].copy_(mask, non_blocking=True)
+        if want_parts:
+            parts_u8 = torch.stack([ops.f32_to_u8(p) for p in self._parts_out])
+            out_host["parts"] = torch.empty(parts_u8.shape, dtype=torch.uint8, pin_memory=True)
+            out_host["parts"].copy_(parts_u8, non_blocking=True)
         return out_host
+
+    @torch.no_grad()
+    def infer_mods_u8(self, tiles_u8_host):
+        """Modalities only (mod_only / seg_gen=False): no seg generators are run."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = ops.u8_to_f32(tiles_u8_host.to(dev, non_blocking=True))
+        mb = self.micro_batch if self.micro_batch > 0 else x.shape[0]
+        outs = [torch.cat([g(x[s:s + mb]) for s in range(0, x.shape[0], mb)]) for g in self.gens]
+        mods_u8 = torch.stack([ops.f32_to_u8(m) for m in outs])
+        host = torch.empty(mods_u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(mods_u8, non_blocking=True)
+        return {"mods": host}

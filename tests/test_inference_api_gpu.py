@@ -1,0 +1,101 @@
+"""End-to-end boundary test: a reference-format model directory (train_opt.txt + latest_net_*.pth) goes through
+create_model / init_nets / infer_modalities / `deepliif test`, and the stitched uint8 outputs are compared with the
+oracle's cascade (DeepLIIF_model.py:175-203 + tensor2im) on the same weights."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import nets, pixel
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_model_dir(root, net_g="resnet_9blocks", net_gs="unet_512", n_blocks=9):
+    from deepliif_b200.options import Options, print_options
+    d = dict(model="DeepLIIF", name="m", checkpoints_dir=str(root), gpu_ids=(0,), input_nc=3, output_nc=3, ngf=64, ndf=64,
+             net_g=net_g, net_gs=net_gs, net_d="n_layers", norm="batch", no_dropout=False, padding="zero", init_type="normal",
+             init_gain=0.02, modalities_no=4, seg_gen=True, input_no=1, scale_size=512, phase="train",
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25],
+             loss_G_weights=[0.2] * 5, loss_D_weights=[0.2] * 5, mod_id_seg="S")
+    opt = Options(d_params=d, mode="train")
+    print_options(opt, save=True)
+    mdir = os.path.join(str(root), "m")
+    sds = {}
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, n_blocks, "batch", True, "zero")
+    s_shapes = nets.unet_param_shapes(9, 64, 3, 3, "batch") if net_gs == "unet_512" else \
+        nets.resnet_param_shapes(3, 3, 64, n_blocks, "batch", True, "reflect")
+    for i in range(1, 5):
+        sds[f"G{i}"] = nets.make_state_dict(g_shapes, 50 + i, "stress")
+    for i in range(5):
+        sds[f"GS{i}"] = nets.make_state_dict(s_shapes, 60 + i, "stress")
+    for k, sd in sds.items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    return mdir, sds
+
+
+def _oracle_cascade(x, sds, net_gs):
+    torch.set_num_threads(os.cpu_count())
+    cfg = dict(n_blocks=9, norm="batch", use_dropout=True, padding_type="zero", norm_mode="sample")
+    with torch.no_grad():
+        run_g = lambda t, sd: nets.resnet_forward(t, sd, **cfg)
+        if net_gs == "unet_512":
+            run_s = lambda t, sd: nets.unet_forward(t, sd, num_downs=9, norm="batch", norm_mode="sample")
+        else:
+            run_s = lambda t, sd: nets.resnet_forward(t, sd, **{**cfg, "padding_type": "reflect"})
+        return nets.deepliif_forward(x, [sds[f"G{i}"] for i in range(1, 5)], [sds[f"GS{i}"] for i in range(5)],
+                                     [0.25, 0.15, 0.25, 0.1, 0.25], run_g, run_s)
+
+
+def test_infer_modalities_matches_oracle_cascade(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200.models import infer_modalities
+    mdir, sds = _write_model_dir(tmp_path)
+    rng = np.random.default_rng(11)
+    # smooth-ish synthetic IHC tile (variance >> empty-tile threshold)
+    img = (rng.random((512, 512, 3)) * 255).astype(np.uint8)
+    images, scoring = infer_modalities(Image.fromarray(img), 512, mdir, return_seg_intermediate=True)
+    assert set(images) == {"mod1-Hema", "mod2-DAPI", "mod3-Lap2", "mod4-Marker", "Seg", "mod0-IHC_s", "mod1-Hema_s",
+                           "mod2-DAPI_s", "mod3-Lap2_s", "mod4-Marker_s"}
+    x = torch.from_numpy(pixel.transform(img))
+    mods, parts, seg = _oracle_cascade(x, sds, "unet_512")
+    worst = 0
+    for name, ref in [("mod1-Hema", mods[0]), ("mod2-DAPI", mods[1]), ("mod3-Lap2", mods[2]), ("mod4-Marker", mods[3]),
+                      ("Seg", seg), ("mod0-IHC_s", parts[0]), ("mod4-Marker_s", parts[4])]:
+        got = np.asarray(images[name]).astype(np.int32)
+        want = pixel.tensor2im(ref.numpy()).astype(np.int32)
+        diff = np.abs(got - want)
+        frac = float((diff > 0).mean())
+        print(f"{name}: uint8 mismatches {frac * 100:.3f}% (max |d| {diff.max()})")
+        # fp32 outputs agree to ~1e-4, so a uint8 can differ by at most 1 LSB where (x+1)/2*255 straddles an integer
+        assert diff.max() <= 1 and frac < 0.02
+        worst = max(worst, frac)
+    mask_ref = pixel.create_posneg_mask(pixel.tensor2im(seg.numpy()))
+    mask_got = pixel.create_posneg_mask(np.asarray(images["Seg"]))
+    mism = int((mask_ref != mask_got).sum())
+    print(f"posneg mask pixel mismatches vs oracle-from-fp32: {mism} of {mask_ref.size}")
+    assert mism <= 0.005 * mask_ref.size
+    assert set(scoring) == {"num_pos_pixels", "num_neg_pixels", "percent_pos_pixels"}
+
+
+def test_cli_test_command_writes_outputs(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from click.testing import CliRunner
+    from deepliif_b200.cli import cli
+    mdir, _ = _write_model_dir(tmp_path)
+    inp, out = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    rng = np.random.default_rng(12)
+    Image.fromarray((rng.random((600, 700, 3)) * 255).astype(np.uint8)).save(inp / "roi.png")
+    r = CliRunner().invoke(cli, ["test", "--input-dir", str(inp), "--output-dir", str(out), "--tile-size", "512",
+                                 "--model-dir", mdir, "--gpu-ids", "0"])
+    assert r.exit_code == 0, r.output
+    files = sorted(os.listdir(out))
+    assert "roi_Seg.png" in files and "roi_mod4-Marker.png" in files and "roi.json" in files
+    assert Image.open(out / "roi_Seg.png").size == (700, 600)
+    assert "num_pos_pixels" in json.load(open(out / "roi.json"))
