@@ -31,8 +31,13 @@ SIGNATURES = {
     "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_direct_fwd": (_i, [_cd, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
-    "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
-    "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
+    "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dlb_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                          _i, _vp, _sz, _vp]),
+    "dlb_conv_wgrad_workspace": (_sz, [_cd]),
+    "dlb_conv_wgrad": (_i, [_cd, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dlb_head_bwd_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dlb_stem_window_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dlb_head_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -1,0 +1,355 @@
+// Weight gradient of Conv2d / ConvTranspose2d on the tcgen05 tensor cores (training path; autograd of the layers
+// conv_tc.cu runs forward — reference: loss.backward() through networks.py:399-404, 425-430, 490, 505, 638-659).
+//
+// Per filter tap t the gradient is a GEMM whose reduction runs over pixels:
+//     G_t[m][n] = sum_px P[px][m] * Q[px*st + tap_t][n]
+// P = "anchor" tensor (dy for Conv2d, x for ConvTranspose2d), Q = the other one, both NHWC 16-bit planes (hi [, lo]).
+// Both operands are therefore *MN-major* for the MMA (channels contiguous, pixels = K strided): a TMA box of
+// [64 channels x 64 pixels] lands as 64 K-rows of 128 B, which is exactly the canonical SW128 MN-major layout
+// (8-row atoms 1024 B apart = SBO; the next 64-channel block 8192 B further = LBO).  No transposes are materialised.
+// Q is read through the same shifted / stride-2 5-D views as the forward A operand (zero padding = TMA OOB fill).
+//
+// Work decomposition: one CTA = (tap, 128-row M tile, N tile, K split); K = all anchor pixels in 64-pixel boxes.
+// Split-K partial tiles are stored in fp32 to a workspace and reduced in fixed order by wgrad_reduce_kernel, which
+// also writes the PyTorch weight layout (deterministic, no atomics).  x3 precision as in the forward kernel.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace dlb {
+namespace {
+
+constexpr int kMaxTaps = 64;
+constexpr int kPx = 64;                 // pixels (K) per pipeline stage
+constexpr int kBlkBytes = kPx * 128;    // one [64 ch x 64 px] block of one plane: 8 KB
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;
+
+struct alignas(64) WgParams {
+  CUtensorMap p_hi, p_lo, q_hi, q_lo;
+  int ntaps, planes, n_tile, nb;        // nb = n_tile / 64 Q blocks
+  int q_dim_sel[5];                     // Q-map dim i takes: 0 channel block, 1 w0, 2 h0, 3 n0, 4 nothing
+  int tap_off[kMaxTaps][5];
+  int tile_w, tile_h, tile_n;           // anchor pixel box (tile_w*tile_h*tile_n = 64)
+  int tiles_w, tiles_h, tiles_n;
+  int m_tiles, n_tiles, splits;
+  int CP, CQ;                           // channels of P (GEMM M) and Q (GEMM N)
+  float* ws;                            // [splits][ntaps][CP][CQ]
+  uint32_t idesc;
+  int stages;
+};
+
+// MN-major SW128 descriptor: LBO = 8192 B (next 64-channel block), SBO = 1024 B (next 8 K-rows)
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(kBlkBytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item
+  int item = blockIdx.x;
+  const int split = item % p.splits; item /= p.splits;
+  const int nt = item % p.n_tiles; item /= p.n_tiles;
+  const int mt = item % p.m_tiles; item /= p.m_tiles;
+  const int tap = item;
+  const int total_pt = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int per = (total_pt + p.splits - 1) / p.splits;
+  const int pt0 = split * per, pt1 = min(pt0 + per, total_pt);
+  const int p_bytes = 2 * kBlkBytes;                 // M = 128 = two 64-channel blocks
+  const int q_bytes = p.nb * kBlkBytes;
+  const int stage_bytes = p.planes * (p_bytes + q_bytes);
+  uint32_t tmem_cols = 32; while (tmem_cols < static_cast<uint32_t>(p.n_tile)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&p.p_hi); prefetch_tensormap(&p.q_hi);
+    if (p.planes == 2) { prefetch_tensormap(&p.p_lo); prefetch_tensormap(&p.q_lo); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0; uint32_t ph = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        int t = pt;
+        const int w0 = (t % p.tiles_w) * p.tile_w; t /= p.tiles_w;
+        const int h0 = (t % p.tiles_h) * p.tile_h; t /= p.tiles_h;
+        const int n0 = t * p.tile_n;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+        // P: anchor tensor, dims (c, w, h, n, 1), two 64-channel blocks of the M tile
+        for (int pl = 0; pl < p.planes; ++pl) {
+          const CUtensorMap* pm = pl == 0 ? &p.p_hi : &p.p_lo;
+          for (int b = 0; b < 2; ++b)
+            tma_load_5d(st + pl * p_bytes + b * kBlkBytes, pm, &full_bar[s], mt * 128 + b * 64, w0, h0, n0, 0);
+        }
+        // Q: shifted / strided view, nb 64-channel blocks of the N tile
+        uint8_t* sq = st + p.planes * p_bytes;
+        for (int pl = 0; pl < p.planes; ++pl) {
+          const CUtensorMap* qm = pl == 0 ? &p.q_hi : &p.q_lo;
+          for (int b = 0; b < p.nb; ++b) {
+            int c[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const int sel = p.q_dim_sel[i];
+              c[i] = p.tap_off[tap][i] + (sel == 0 ? nt * p.n_tile + b * 64 : sel == 1 ? w0 : sel == 2 ? h0 : sel == 3 ? n0 : 0);
+            }
+            tma_load_5d(sq + pl * q_bytes + b * kBlkBytes, qm, &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+          }
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int s = 0; uint32_t ph = 0;
+      uint32_t accumulate = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t ph_ = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t pl_ = ph_ + p_bytes;
+        const uint32_t qh_ = ph_ + p.planes * p_bytes;
+        const uint32_t ql_ = qh_ + q_bytes;
+#pragma unroll
+        for (int k = 0; k < kPx / 16; ++k) {               // 16 pixels (K) per MMA = two 8-row atoms = 2048 B
+          const uint64_t da_hi = make_sw128_mnmajor_desc(ph_ + k * 2048);
+          const uint64_t db_hi = make_sw128_mnmajor_desc(qh_ + k * 2048);
+          if (p.planes == 2) {
+            const uint64_t da_lo = make_sw128_mnmajor_desc(pl_ + k * 2048);
+            const uint64_t db_lo = make_sw128_mnmajor_desc(ql_ + k * 2048);
+            umma_f16(tmem_base, da_lo, db_hi, p.idesc, accumulate);
+            umma_f16(tmem_base, da_hi, db_lo, p.idesc, 1);
+            umma_f16(tmem_base, da_hi, db_hi, p.idesc, 1);
+          } else {
+            umma_f16(tmem_base, da_hi, db_hi, p.idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> fp32 partial tile =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // row of the M tile = P channel
+    const int mrow = mt * 128 + m;
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    float* out = p.ws + ((static_cast<long long>(split) * p.ntaps + tap) * p.CP + mrow) * p.CQ + nt * p.n_tile;
+    const bool any = pt1 > pt0;
+    for (int c = 0; c < p.n_tile; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (mrow < p.CP && (nt * p.n_tile + c) < p.CQ) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = any ? __uint_as_float(v[j + 0]) : 0.f; o.y = any ? __uint_as_float(v[j + 1]) : 0.f;
+          o.z = any ? __uint_as_float(v[j + 2]) : 0.f; o.w = any ? __uint_as_float(v[j + 3]) : 0.f;
+          *reinterpret_cast<float4*>(out + c + j) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// dW (PyTorch layout [CP][CQ][taps]) (+)= sum_splits ws[split][tap][m][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int CP, int CQ,
+                                    float* __restrict__ dw, int accumulate) {
+  const long long total = static_cast<long long>(taps) * CP * CQ;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx % CQ);
+    const int m = static_cast<int>((idx / CQ) % CP);
+    const int t = static_cast<int>(idx / (static_cast<long long>(CQ) * CP));
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[static_cast<long long>(s) * total + idx];
+    const long long dst = (static_cast<long long>(m) * CQ + n) * taps + t;
+    dw[dst] = accumulate ? dw[dst] + acc : acc;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode5(CUtensorMap* map, const void* base, int is_bf16, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  cuuint64_t gd[5], gs[4]; cuuint32_t bx[5], es[5];
+  for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < 4; ++i) gs[i] = strides[i];
+  const CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
+                        const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof(b), "wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); set_error(b); return false; }
+  return true;
+}
+
+int pow2c(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct WgGeom {
+  int PN, PH, PW, CP;      // anchor tensor
+  int QH, QW, CQ;          // other tensor
+  int stride, taps, R, S, pad;
+  int n_tile, nb, m_tiles, n_tiles, splits, tile_w, tile_h, tile_n, tiles_w, tiles_h, tiles_n;
+};
+
+int wg_geometry(const dlb_conv_desc* d, WgGeom* g) {
+  int OH, OW;
+  if (d->transposed) { OH = (d->H - 1) * d->stride - 2 * d->pad + d->R + d->output_padding; OW = (d->W - 1) * d->stride - 2 * d->pad + d->S + d->output_padding; }
+  else { OH = (d->H + 2 * d->pad - d->R) / d->stride + 1; OW = (d->W + 2 * d->pad - d->S) / d->stride + 1; }
+  g->stride = d->stride; g->R = d->R; g->S = d->S; g->pad = d->pad; g->taps = d->R * d->S; g->PN = d->N;
+  if (!d->transposed) { g->PH = OH; g->PW = OW; g->CP = d->Cout; g->QH = d->H; g->QW = d->W; g->CQ = d->Cin[0]; }
+  else { g->PH = d->H; g->PW = d->W; g->CP = d->Cin[0]; g->QH = OH; g->QW = OW; g->CQ = d->Cout; }
+  if (g->taps > kMaxTaps) return set_error("wgrad: more than 64 taps");
+  if (g->CP % 64 != 0 || g->CQ % 64 != 0) return set_error("wgrad: channel counts must be multiples of 64 (pad small sides)");
+  if (g->stride == 2 && ((g->QH & 1) || (g->QW & 1))) return set_error("wgrad: stride-2 needs even extents");
+  g->n_tile = g->CQ >= 256 ? 256 : g->CQ;
+  if (g->n_tile != 64 && g->n_tile != 128 && g->n_tile != 256) { g->n_tile = 64; }
+  g->nb = g->n_tile / 64;
+  g->m_tiles = (g->CP + 127) / 128;
+  g->n_tiles = (g->CQ + g->n_tile - 1) / g->n_tile;
+  g->tile_w = g->PW >= kPx ? kPx : pow2c(g->PW);
+  g->tile_h = kPx / g->tile_w; { const int hp = pow2c(g->PH); if (g->tile_h > hp) g->tile_h = hp; }
+  g->tile_n = kPx / (g->tile_w * g->tile_h);
+  g->tiles_w = (g->PW + g->tile_w - 1) / g->tile_w;
+  g->tiles_h = (g->PH + g->tile_h - 1) / g->tile_h;
+  g->tiles_n = (g->PN + g->tile_n - 1) / g->tile_n;
+  const int items = g->taps * g->m_tiles * g->n_tiles;
+  const int total_pt = g->tiles_w * g->tiles_h * g->tiles_n;
+  int splits = (2 * 148 + items - 1) / items;
+  if (splits > total_pt) splits = total_pt;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  g->splits = splits;
+  return 0;
+}
+
+}  // namespace
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" size_t dlb_conv_wgrad_workspace(const dlb_conv_desc* d) {
+  WgGeom g;
+  if (wg_geometry(d, &g) != 0) return 0;
+  return static_cast<size_t>(g.splits) * g.taps * g.CP * g.CQ * sizeof(float);
+}
+
+extern "C" int dlb_conv_wgrad(const dlb_conv_desc* d, const void* x_hi, const void* x_lo, const void* dy_hi,
+                              const void* dy_lo, float* dw, int accumulate, int fmt, int split, void* workspace,
+                              size_t workspace_bytes, dlb_stream_t stream) {
+  if (d->nsrc != 1) return set_error("dlb_conv_wgrad: single source only");
+  if (fmt != DLB_FMT_BF16 && fmt != DLB_FMT_FP16) return set_error("dlb_conv_wgrad: bad fmt");
+  WgGeom g;
+  if (wg_geometry(d, &g) != 0) return DLB_ERR_INVALID;
+  const size_t need = static_cast<size_t>(g.splits) * g.taps * g.CP * g.CQ * sizeof(float);
+  if (workspace_bytes < need) return set_error("dlb_conv_wgrad: workspace too small");
+  const int is_bf16 = fmt == DLB_FMT_BF16;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.planes = split ? 2 : 1; p.ntaps = g.taps; p.n_tile = g.n_tile; p.nb = g.nb;
+  p.tile_w = g.tile_w; p.tile_h = g.tile_h; p.tile_n = g.tile_n;
+  p.tiles_w = g.tiles_w; p.tiles_h = g.tiles_h; p.tiles_n = g.tiles_n;
+  p.m_tiles = g.m_tiles; p.n_tiles = g.n_tiles; p.splits = g.splits; p.CP = g.CP; p.CQ = g.CQ;
+  p.ws = reinterpret_cast<float*>(workspace);
+  // instruction descriptor: both operands MN-major (bits 15, 16)
+  p.idesc = make_idesc_f16(128, g.n_tile, is_bf16) | (1u << 15) | (1u << 16);
+  const void* P_hi = d->transposed ? x_hi : dy_hi; const void* P_lo = d->transposed ? x_lo : dy_lo;
+  const void* Q_hi = d->transposed ? dy_hi : x_hi; const void* Q_lo = d->transposed ? dy_lo : x_lo;
+  {  // anchor map: (c, w, h, n, 1)
+    const uint64_t C = g.CP, W = g.PW, H = g.PH, N = g.PN;
+    uint64_t dims[5] = {C, W, H, N, 1};
+    uint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, N * H * W * C * 2};
+    uint32_t box[5] = {64, (uint32_t)g.tile_w, (uint32_t)g.tile_h, (uint32_t)g.tile_n, 1};
+    if (!encode5(&p.p_hi, P_hi, is_bf16, dims, str, box)) return DLB_ERR_INVALID;
+    if (split && !encode5(&p.p_lo, P_lo, is_bf16, dims, str, box)) return DLB_ERR_INVALID;
+  }
+  {  // Q map: stride 1 -> (c, w, h, n, 1); stride 2 -> (wp*C + c, ww, hp, hh, n)
+    const uint64_t C = g.CQ, W = g.QW, H = g.QH, N = g.PN;
+    uint64_t dims[5], str[4]; uint32_t box[5];
+    if (g.stride == 1) {
+      dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 1;
+      str[0] = C * 2; str[1] = W * C * 2; str[2] = H * W * C * 2; str[3] = N * H * W * C * 2;
+      box[0] = 64; box[1] = g.tile_w; box[2] = g.tile_h; box[3] = g.tile_n; box[4] = 1;
+      p.q_dim_sel[0] = 0; p.q_dim_sel[1] = 1; p.q_dim_sel[2] = 2; p.q_dim_sel[3] = 3; p.q_dim_sel[4] = 4;
+    } else {
+      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+      str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+      box[0] = 64; box[1] = g.tile_w; box[2] = 1; box[3] = g.tile_h; box[4] = g.tile_n;
+      p.q_dim_sel[0] = 0; p.q_dim_sel[1] = 1; p.q_dim_sel[2] = 4; p.q_dim_sel[3] = 2; p.q_dim_sel[4] = 3;
+    }
+    if (!encode5(&p.q_hi, Q_hi, is_bf16, dims, str, box)) return DLB_ERR_INVALID;
+    if (split && !encode5(&p.q_lo, Q_lo, is_bf16, dims, str, box)) return DLB_ERR_INVALID;
+    for (int r = 0; r < g.R; ++r)
+      for (int s = 0; s < g.S; ++s) {
+        const int t = r * g.S + s;
+        const int dh = r - g.pad, dw = s - g.pad;      // Q index = anchor*stride + (r - pad)
+        if (g.stride == 1) {
+          p.tap_off[t][0] = 0; p.tap_off[t][1] = dw; p.tap_off[t][2] = dh; p.tap_off[t][3] = 0; p.tap_off[t][4] = 0;
+        } else {
+          const int hp = ((dh % 2) + 2) % 2, wp = ((dw % 2) + 2) % 2;
+          p.tap_off[t][0] = wp * static_cast<int>(C); p.tap_off[t][1] = (dw - wp) / 2; p.tap_off[t][2] = hp;
+          p.tap_off[t][3] = (dh - hp) / 2; p.tap_off[t][4] = 0;
+        }
+      }
+  }
+  const int stage_bytes = p.planes * (2 * kBlkBytes + g.nb * kBlkBytes);
+  int stages = (kSmemLimit - 2048 - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error("dlb_conv_wgrad: not enough shared memory");
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 2048) != cudaSuccess)
+      return set_cuda_error("cudaFuncSetAttribute(conv_wgrad_kernel)");
+    attr_set = true;
+  }
+  const int grid = g.taps * g.m_tiles * g.n_tiles * g.splits;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  conv_wgrad_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("conv_wgrad_kernel launch");
+  const long long total = static_cast<long long>(g.taps) * g.CP * g.CQ;
+  long long rg = (total + 255) / 256; if (rg > 148 * 8) rg = 148 * 8;
+  wgrad_reduce_kernel<<<static_cast<int>(rg), 256, 0, st>>>(p.ws, g.splits, g.taps, g.CP, g.CQ, dw, accumulate);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("wgrad_reduce_kernel launch");
+  return 0;
+}

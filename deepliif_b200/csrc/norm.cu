@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
 __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int N, int C, int pooled,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps,
-                                                              float* __restrict__ scale, float* __restrict__ shift) {
+                                                              float* __restrict__ scale, float* __restrict__ shift,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   __shared__ double sm[32][33];
   __shared__ double sm2[32][33];
   const int S = *ws.S;
@@ -139,7 +140,10 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int 
   const float be = beta ? beta[c] : 0.f;
   const float sc = ga * rstd;
   const float sh = be - mean * sc;
-  for (int n = n_lo; n < n_hi; ++n) { scale[n * C + c] = sc; shift[n * C + c] = sh; }
+  for (int n = n_lo; n < n_hi; ++n) {
+    scale[n * C + c] = sc; shift[n * C + c] = sh;
+    if (mean_out != nullptr) { mean_out[n * C + c] = mean; rstd_out[n * C + c] = rstd; }
+  }
 }
 
 // ---- apply: act(y*scale+shift) (+residual) -> fp32 and/or split 16-bit planes ---------------------
@@ -340,25 +344,26 @@ using namespace dlb;
 extern "C" size_t dlb_norm_stats_workspace(int N, int HW, int C) { return stats_layout(N, HW, C).total; }
 
 static int launch_finalize(void* workspace, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
-                           float eps, float* scale, float* shift, cudaStream_t stream) {
+                           float eps, float* scale, float* shift, float* mean, float* rstd, cudaStream_t stream) {
   const StatsLayout L = stats_layout(N, HW, C);
   const StatsPtrs ws = stats_ptrs(workspace, L);
   dim3 grid(L.cchunks, pooled ? 1 : N);
-  stats_finalize_kernel<<<grid, 1024, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift);
+  stats_finalize_kernel<<<grid, 1024, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift, mean, rstd);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_finalize_kernel launch");
   return 0;
 }
 
 extern "C" int dlb_norm_finalize(void* workspace, size_t workspace_bytes, int N, int HW, int C, int pooled,
                                  const float* gamma, const float* beta, float eps, float* scale, float* shift,
-                                 dlb_stream_t stream) {
+                                 float* mean, float* rstd, dlb_stream_t stream) {
   if (workspace_bytes < stats_layout(N, HW, C).total) return set_error("dlb_norm_finalize: workspace too small");
-  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, reinterpret_cast<cudaStream_t>(stream));
+  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, mean, rstd,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
-                              float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes,
-                              dlb_stream_t stream) {
+                              float eps, float* scale, float* shift, float* mean, float* rstd, void* workspace,
+                              size_t workspace_bytes, dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_stats: C % 4 != 0");
   const int c4n = C / 4;
   if (c4n < 256 && 256 % c4n != 0) return set_error("dlb_norm_stats: C/4 must divide 256 (or be a multiple of 256)");
@@ -369,7 +374,7 @@ extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   stats_partial_kernel<<<dim3(slices, N), 256, 0, st>>>(y, HW, C, slices, stats_ptrs(workspace, L));
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_partial_kernel launch");
-  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, st);
+  return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, mean, rstd, st);
 }
 
 extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,

@@ -4,6 +4,9 @@
 //   dlb_seg_finish  run_dask aggregation (models/__init__.py:338) + tensor2im + create_posneg_mask
 //                   (postprocessing.py:163-190, labels :87-95)
 // Pure HBM streams; bit-exact against oracle/pixel.py (same fp32 operation order, no FMA contraction).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "internal.h"
 
 namespace dlb {
@@ -103,6 +106,47 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
   }
 }
 
+// Backward of head_finish: dz[n, h, u, s*4 + co] = dzz[n, co, h, u - s] (0 <= u - s < W), other lanes 0; written as
+// 64-channel hi/lo planes [N, H, W+S-1, 64] = the operand of the head's dgrad / wgrad GEMMs.  S = 1, CO = 1 is the
+// PatchGAN last conv, S = 1, CO = 3 the UNet outermost ConvTranspose.  thread = one (n, h, u) pixel.
+template <typename T16>
+__global__ void __launch_bounds__(256) head_bwd_pack_kernel(const float* __restrict__ dzz, int N, int H, int W, int S,
+                                                            int CO, T16* __restrict__ out_hi, T16* __restrict__ out_lo) {
+  const int WZ = W + S - 1;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(N) * H * WZ;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % WZ);
+    const int h = static_cast<int>((idx / WZ) % H);
+    const int n = static_cast<int>(idx / (static_cast<long long>(WZ) * H));
+    __align__(16) T16 hi[64];
+    __align__(16) T16 lo[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) { hi[k] = T16(0.f); lo[k] = T16(0.f); }
+    for (int s = 0; s < S; ++s) {
+      const int w = u - s;
+      if (w < 0 || w >= W) continue;
+      for (int co = 0; co < CO; ++co) {
+        const float v = __ldg(dzz + (static_cast<long long>(n) * CO + co) * plane + static_cast<long long>(h) * W + w);
+        const T16 hh = T16(v);
+        hi[s * 4 + co] = hh;
+        lo[s * 4 + co] = T16(v - static_cast<float>(hh));
+      }
+    }
+    uint4* dh = reinterpret_cast<uint4*>(out_hi + idx * 64);
+    const uint4* sh = reinterpret_cast<const uint4*>(hi);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dh[k] = sh[k];
+    if (out_lo != nullptr) {
+      uint4* dl = reinterpret_cast<uint4*>(out_lo + idx * 64);
+      const uint4* sl = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dl[k] = sl[k];
+    }
+  }
+}
+
 int grid1d(long long total) {
   long long g = (total + 255) / 256;
   return static_cast<int>(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8);
@@ -143,5 +187,20 @@ extern "C" int dlb_head_finish(const float* z, const float* bias, int N, int H, 
   if (S < 1 || S > 8 || CO < 1 || CO > 4) return set_error("dlb_head_finish: needs S <= 8 and CO <= 4");
   head_finish_kernel<<<grid1d(static_cast<long long>(N) * H * W), 256, 0, stream>>>(z, bias, N, H, W, S, CO, act, y_nchw);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("head_finish_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_head_bwd_pack(const float* dzz_nchw, int N, int H, int W, int S, int CO, int fmt, void* out_hi,
+                                 void* out_lo, dlb_stream_t stream) {
+  if (S < 1 || S > 8 || CO < 1 || CO > 4) return set_error("dlb_head_bwd_pack: needs S <= 8 and CO <= 4");
+  const int g = grid1d(static_cast<long long>(N) * H * (W + S - 1));
+  if (fmt == DLB_FMT_BF16)
+    head_bwd_pack_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(dzz_nchw, N, H, W, S, CO, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                             reinterpret_cast<__nv_bfloat16*>(out_lo));
+  else if (fmt == DLB_FMT_FP16)
+    head_bwd_pack_kernel<__half><<<g, 256, 0, stream>>>(dzz_nchw, N, H, W, S, CO, reinterpret_cast<__half*>(out_hi),
+                                                      reinterpret_cast<__half*>(out_lo));
+  else return set_error("dlb_head_bwd_pack: bad fmt");
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("head_bwd_pack_kernel launch");
   return 0;
 }

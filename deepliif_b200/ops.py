@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -119,18 +119,21 @@ def conv_direct(d, x, w_packed, bias=None, in_nchw=False, in_scale=None, in_shif
     return out
 
 
-def norm_finalize(ws, N, HW, Cc, gamma=None, beta=None, pooled=False, eps=1e-5):
-    """Reduce the partial statistics a conv epilogue left in `ws` -> (scale, shift) fp32 [N,C]."""
+def norm_finalize(ws, N, HW, Cc, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False):
+    """Reduce the partial statistics a conv epilogue left in `ws` -> (scale, shift) fp32 [N,C]
+    (+ (mean, rstd) with want_stats, kept for the backward pass)."""
     scale = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
     shift = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
+    mean = torch.empty((N, Cc), dtype=torch.float32, device=ws.device) if want_stats else None
+    rstd = torch.empty((N, Cc), dtype=torch.float32, device=ws.device) if want_stats else None
     check(_lib.load().dlb_norm_finalize(_p(ws), ws.numel() * 4, N, HW, Cc, int(pooled), _p(gamma), _p(beta),
-                                        float(eps), _p(scale), _p(shift), _stream()), "dlb_norm_finalize")
+                                        float(eps), _p(scale), _p(shift), _p(mean), _p(rstd), _stream()), "dlb_norm_finalize")
     LAUNCHES["count"] += 1
-    return scale, shift
+    return (scale, shift, mean, rstd) if want_stats else (scale, shift)
 
 
-def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5):
-    """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift."""
+def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False):
+    """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift (+ mean, rstd)."""
     _need_cuda(y, gamma, beta)
     N, H, W, Cc = y.shape
     lib = _lib.load()
@@ -138,10 +141,69 @@ def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5):
     ws_bytes = ws.numel() * 4
     scale = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
     shift = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
+    mean = torch.empty((N, Cc), dtype=torch.float32, device=y.device) if want_stats else None
+    rstd = torch.empty((N, Cc), dtype=torch.float32, device=y.device) if want_stats else None
     check(lib.dlb_norm_stats(_p(y), N, H * W, Cc, int(pooled), _p(gamma), _p(beta), float(eps), _p(scale), _p(shift),
-                             _p(ws), ws_bytes, _stream()), "dlb_norm_stats")
+                             _p(mean), _p(rstd), _p(ws), ws_bytes, _stream()), "dlb_norm_stats")
     LAUNCHES["count"] += 2
-    return scale, shift
+    return (scale, shift, mean, rstd) if want_stats else (scale, shift)
+
+
+def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE, dout2=None, pooled=False,
+             dgamma=None, dbeta=None, accumulate=False, want_f32=False, want_split=True, fmt=FMT_BF16, need_lo=True):
+    """Backward of norm(+affine)+activation: returns (dy_f32 | None, dy_hi | None, dy_lo | None); writes the
+    parameter gradients into dgamma/dbeta (fp32 [C]) when given.  scale=None: layer without norm."""
+    _need_cuda(dout, dout2, y, scale, shift, mean, rstd, dgamma, dbeta)
+    N, H, W, Cc = y.shape
+    dev = y.device
+    c1 = torch.empty((N, Cc), dtype=torch.float32, device=dev) if scale is not None else None
+    c2 = torch.empty((N, Cc), dtype=torch.float32, device=dev) if scale is not None else None
+    f32 = torch.empty_like(y) if want_f32 else None
+    hi = torch.empty(y.shape, dtype=_dtype(fmt), device=dev) if want_split else None
+    lo = torch.empty(y.shape, dtype=_dtype(fmt), device=dev) if (want_split and need_lo) else None
+    ws = stats_workspace(N, H * W, Cc, dev)
+    check(_lib.load().dlb_norm_bwd(_p(dout), _p(dout2), _p(y), _p(scale), _p(shift), _p(mean), _p(rstd), act, N, H * W, Cc,
+                                   int(pooled), _p(c1), _p(c2), _p(dgamma), _p(dbeta), int(accumulate), _p(f32), _p(hi),
+                                   _p(lo), fmt, _p(ws), ws.numel() * 4, _stream()), "dlb_norm_bwd")
+    LAUNCHES["count"] += 3 if scale is not None else 1
+    return f32, hi, lo
+
+
+_WG_CACHE = {}
+
+
+def conv_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw=None, accumulate=False, fmt=FMT_BF16, split=True):
+    """Weight gradient (fp32, PyTorch weight layout) of the forward layer `d` from hi/lo NHWC planes."""
+    _need_cuda(x_hi, x_lo, dy_hi, dy_lo, dw)
+    lib = _lib.load()
+    nbytes = lib.dlb_conv_wgrad_workspace(C.byref(d))
+    if nbytes == 0:
+        check(-1, "dlb_conv_wgrad_workspace")
+    key = (nbytes, str(x_hi.device), torch.cuda.current_stream().cuda_stream)
+    ws = _WG_CACHE.get(key)
+    if ws is None:
+        ws = _WG_CACHE[key] = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=x_hi.device)
+    if dw is None:
+        cin = _cin_total(d)
+        shape = (cin, d.Cout, d.R, d.S) if d.transposed else (d.Cout, cin, d.R, d.S)
+        dw = torch.empty(shape, dtype=torch.float32, device=x_hi.device)
+        accumulate = False
+    check(lib.dlb_conv_wgrad(C.byref(d), _p(x_hi), _p(x_lo) if split else None, _p(dy_hi), _p(dy_lo) if split else None,
+                             _p(dw), int(accumulate), fmt, int(split), _p(ws), ws.numel() * 4, _stream()), "dlb_conv_wgrad")
+    LAUNCHES["count"] += 2
+    return dw
+
+
+def head_bwd_pack(dzz_nchw, S, fmt=FMT_BF16, need_lo=True):
+    """dzz fp32 NCHW [N,CO<=4,H,W] -> (hi, lo) planes [N, H, W+S-1, 64] with lane j = s*4 + co."""
+    _need_cuda(dzz_nchw)
+    N, CO, H, W = dzz_nchw.shape
+    shp = (N, H, W + S - 1, 64)
+    hi = torch.empty(shp, dtype=_dtype(fmt), device=dzz_nchw.device)
+    lo = torch.empty(shp, dtype=_dtype(fmt), device=dzz_nchw.device) if need_lo else None
+    check(_lib.load().dlb_head_bwd_pack(_p(dzz_nchw), N, H, W, S, CO, fmt, _p(hi), _p(lo), _stream()), "dlb_head_bwd_pack")
+    LAUNCHES["count"] += 1
+    return hi, lo
 
 
 def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=False, want_split=True,

@@ -94,18 +94,45 @@ int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, con
  *   Deterministic (fixed merge orders; the only atomic is a completion ticket).  workspace:
  *   dlb_norm_stats_workspace bytes, zero-initialised once at allocation (calls leave it clean).
  * dlb_norm_finalize: the reduction half of dlb_norm_stats, for partials written by dlb_conv_tc_fwd.
+ *   mean/rstd (nullable, fp32 [N,C]): the statistics themselves, kept for the backward pass.
  * dlb_norm_apply: out = act(y*scale + shift) (+ residual), written as fp32 (out_f32) and/or as split
  *   16-bit planes (out_hi/out_lo) for the next tensor-core conv; `pad` > 0 writes the planes into a
  *   [N, H+2pad, W+2pad, C] buffer with a reflected (DLB_PAD_REFLECT) or zero border. */
 size_t dlb_norm_stats_workspace(int N, int HW, int C);
 int dlb_norm_finalize(void* workspace, size_t workspace_bytes, int N, int HW, int C, int pooled, const float* gamma,
-                      const float* beta, float eps, float* scale, float* shift, dlb_stream_t stream);
+                      const float* beta, float eps, float* scale, float* shift, float* mean, float* rstd,
+                      dlb_stream_t stream);
 int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
-                   float eps, float* scale, float* shift, void* workspace, size_t workspace_bytes,
-                   dlb_stream_t stream);
+                   float eps, float* scale, float* shift, float* mean, float* rstd, void* workspace,
+                   size_t workspace_bytes, dlb_stream_t stream);
 int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                    float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
                    int pad_mode, dlb_stream_t stream);
+
+/* ---- training: backward of norm + activation -------------------------------------------------------------------
+ * Autograd of BatchNorm2d (batch statistics) / InstanceNorm2d + ReLU / LeakyReLU(0.2) (networks.py:25-44, 391-404,
+ * 490-513, 640-656).  With n = y*scale + shift, yhat = (y-mean)*rstd, dn = (dout [+ dout2]) * act'(n):
+ *   dbeta = sum dn, dgamma = sum dn*yhat (nullable; += when accumulate_param_grads),
+ *   dy = scale * (dn - mean_g(dn) - yhat * mean_g(dn*yhat)),  g = (n,c) plane, or the batch when pooled.
+ * scale == NULL: layer without norm, dy = dn with n = y.  c1/c2: fp32 [N,C] scratch.  dy is written as fp32 and/or
+ * as hi/lo planes (operands of the dgrad / wgrad GEMMs).  workspace: dlb_norm_stats_workspace(N, HW, C) bytes. */
+int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const float* scale, const float* shift,
+                 const float* mean, const float* rstd, int act, int N, int HW, int C, int pooled, float* c1, float* c2,
+                 float* dgamma, float* dbeta, int accumulate_param_grads, float* dy_f32, void* dy_hi, void* dy_lo,
+                 int fmt, void* workspace, size_t workspace_bytes, dlb_stream_t stream);
+
+/* Weight gradient of a convolution on the tensor cores (autograd of nn.Conv2d / nn.ConvTranspose2d wrt weight):
+ *   Conv2d:          dW[co][ci][r][s] = sum_{n,oh,ow} dy[n,oh,ow,co] * x[n, oh*st + r - pad, ow*st + s - pad, ci]
+ *   ConvTranspose2d: dW[ci][co][r][s] = sum_{n,ih,iw} x[n,ih,iw,ci] * dy[n, ih*st + r - pad, iw*st + s - pad, co]
+ * i.e. per tap a [P-channels x Q-channels] GEMM whose K dimension runs over the pixels of the low-resolution
+ * ("anchor") tensor P (dy for Conv2d, x for ConvTranspose2d); Q is read through the same shifted / stride-2 TMA views
+ * as the forward operand.  d describes the FORWARD layer (nsrc == 1).  x/dy: hi/lo NHWC planes.  dw: fp32 in the
+ * PyTorch weight layout; accumulate != 0 adds to it.  Split-K partials go to `workspace`
+ * (dlb_conv_wgrad_workspace bytes) and are reduced in a fixed order (deterministic). */
+size_t dlb_conv_wgrad_workspace(const dlb_conv_desc* d);
+int dlb_conv_wgrad(const dlb_conv_desc* d, const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo,
+                   float* dw, int accumulate, int fmt, int split, void* workspace, size_t workspace_bytes,
+                   dlb_stream_t stream);
 
 /* Stem operand for the tensor cores.  The 7x7 Cin=3 stem conv (ReflectionPad2d/ZeroPad2d(3) + Conv2d(3, ngf, 7),
  * networks.py:386-397) has K = 147, too ragged for 64-channel K chunks; this pass writes
@@ -122,6 +149,11 @@ int dlb_stem_window_pack(const float* x_nchw, int N, int C, int H, int W, int pa
  *   y[n, co, h, w] = act(bias[co] + sum_s z[n, h, w + s, s*4 + co])     (fp32 NCHW out). */
 int dlb_head_finish(const float* z, const float* bias, int N, int H, int W, int S, int CO, int act, float* y_nchw,
                     dlb_stream_t stream);
+
+/* Backward of dlb_head_finish: scatters dzz = dL/d(pre-activation) (fp32 NCHW [N,CO,H,W]) into the 64-lane virtual
+ * channel planes dz[n, h, u, s*4+co] = dzz[n, co, h, u-s], [N, H, W+S-1, 64] hi/lo (operand of the head's dgrad/wgrad). */
+int dlb_head_bwd_pack(const float* dzz_nchw, int N, int H, int W, int S, int CO, int fmt, void* out_hi, void* out_lo,
+                      dlb_stream_t stream);
 
 /* ---- pixel ends ------------------------------------------------------------------------------------
  * dlb_u8_to_f32: deepliif.data.transform (data/__init__.py:133-138): uint8 HWC -> fp32 NCHW in [-1,1].
