@@ -195,10 +195,46 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const BwdParams p, 
   }
 }
 
+// ---- per-channel sum over (n, pixel): bias gradient of a convolution ------------------------------------------------
+// grid (slices), block 256: slice partials [slices][C]; then one block per 32 channels sums the slices in order.
+__global__ void __launch_bounds__(256) chsum_partial_kernel(const float* __restrict__ x, long long rows, int C, int rows_per,
+                                                            float* __restrict__ part) {
+  const int sl = blockIdx.x, tid = threadIdx.x;
+  const long long r0 = static_cast<long long>(sl) * rows_per, r1 = min(r0 + rows_per, rows);
+  for (int c = tid; c < C; c += 256) {
+    float a = 0.f;
+    for (long long r = r0; r < r1; ++r) a += x[r * C + c];
+    part[static_cast<long long>(sl) * C + c] = a;
+  }
+}
+__global__ void chsum_final_kernel(const float* __restrict__ part, int slices, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0;
+  for (int s = 0; s < slices; ++s) a += part[static_cast<long long>(s) * C + c];
+  out[c] = accumulate ? out[c] + static_cast<float>(a) : static_cast<float>(a);
+}
+
 }  // namespace
 }  // namespace dlb
 
 using namespace dlb;
+
+// out[c] (+)= sum over rows of x[rows][C]  (bias gradient: rows = N*OH*OW of dy).  workspace: >= 1024*C floats.
+extern "C" int dlb_channel_sum(const float* x, long long rows, int C, float* out, int accumulate, void* workspace,
+                               size_t workspace_bytes, dlb_stream_t stream) {
+  int slices = static_cast<int>((rows + 255) / 256);
+  if (slices > 1024) slices = 1024;
+  if (slices < 1) slices = 1;
+  const int rows_per = static_cast<int>((rows + slices - 1) / slices);
+  if (workspace_bytes < static_cast<size_t>(slices) * C * sizeof(float)) return set_error("dlb_channel_sum: workspace too small");
+  float* part = reinterpret_cast<float*>(workspace);
+  chsum_partial_kernel<<<slices, 256, 0, stream>>>(x, rows, C, rows_per, part);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("chsum_partial_kernel launch");
+  chsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, slices, C, out, accumulate);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("chsum_final_kernel launch");
+  return 0;
+}
 
 // dout2 (nullable): second addend of the incoming gradient.  scale == NULL: the layer has no norm (then only `apply`
 // is meaningful: dy = dOut * act'(y)).  c1/c2: fp32 [N,C] scratch produced by reduce+finalize, consumed by apply.

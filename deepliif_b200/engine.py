@@ -84,6 +84,7 @@ class ConvLayer:
         self.prec = prec
         self.n_tile = n_tile
         self.use_tc = backend == "tc" and _tc_ok(self.cins, self.cout)
+        self.w_f32 = w          # kept for the data-gradient packing (training)
         d = ops.conv_desc(1, 8, 8, self.cins, self.cout, self.R, self.S, stride, pad, transposed, output_padding)
         if self.use_tc:
             self.w_hi, self.w_lo = ops.pack_weights_tc(d, w, prec.fmt, prec.split)
@@ -106,6 +107,28 @@ class ConvLayer:
                         self.prec.fmt, self.prec.split, self.n_tile, stats_ws=ws)
         return y, ws
 
+    # ---- training ------------------------------------------------------------------------------------------------
+    def wgrad(self, x_act, dy_hi, dy_lo, N, H, W, pad=None):
+        """dL/dW in the PyTorch weight layout from the forward operand planes and the output-gradient planes."""
+        d = self.desc(N, H, W, pad)
+        return ops.conv_wgrad(d, x_act.hi, x_act.lo, dy_hi, dy_lo, fmt=self.prec.fmt, split=self.prec.split)
+
+    def dgrad(self, dy_hi, dy_lo, N, H, W, pad=None):
+        """dL/dx (fp32 NHWC [N,H,W,Cin]) of the forward layer applied to an [N,H,W,Cin] input: the same weight
+        tensor in the opposite role (Conv2d <-> ConvTranspose2d), so it runs on conv_tc."""
+        assert len(self.cins) == 1
+        pad = self.pad if pad is None else pad
+        fd = self.desc(N, H, W, pad)
+        oh, ow = ops.conv_out_shape(fd)
+        if self.transposed:
+            dd = ops.conv_desc(N, oh, ow, [self.cout], self.cins[0], self.R, self.S, self.stride, pad, False, 0)
+        else:
+            op = H - ((oh - 1) * self.stride - 2 * pad + self.R)
+            dd = ops.conv_desc(N, oh, ow, [self.cout], self.cins[0], self.R, self.S, self.stride, pad, True, op)
+        if getattr(self, "_wT", None) is None:
+            self._wT = ops.pack_weights_tc(dd, self.w_f32, self.prec.fmt, self.prec.split)
+        return ops.conv_tc(dd, [dy_hi], [dy_lo], self._wT[0], self._wT[1], None, self.prec.fmt, self.prec.split)
+
     def run_direct(self, x, N, H, W, *, pad_mode=PAD_ZERO, in_nchw=False, in_scale=None, in_shift=None,
                    in_act=ACT_NONE, out_act=ACT_NONE, out_nchw=False):
         d = self.desc(N, H, W, None, pad_mode)
@@ -126,16 +149,18 @@ class _EngineBase:
             raise NotImplementedError("normalization layer [%s] is not found" % norm)
         self.norm, self.norm_mode, self.prec, self.backend, self.device = norm, norm_mode, prec, backend, device
 
-    def _stats(self, y, np_, ws=None):
-        """raw conv output -> (scale, shift) or (None, None) for norm='none'.  ws: partial statistics already
+    def _pooled(self):
+        return self.norm == "batch" and self.norm_mode == "batch"
+
+    def _stats(self, y, np_, ws=None, want_stats=False):
+        """raw conv output -> (scale, shift[, mean, rstd]) or Nones for norm='none'.  ws: partial statistics already
         written by the conv epilogue (then y is not read again)."""
         if self.norm == "none" or np_ is None:
-            return None, None
-        pooled = self.norm == "batch" and self.norm_mode == "batch"
+            return (None, None, None, None) if want_stats else (None, None)
         if ws is not None:
             N, H, W, C = y.shape
-            return ops.norm_finalize(ws, N, H * W, C, np_.gamma, np_.beta, pooled)
-        return ops.norm_stats(y, np_.gamma, np_.beta, pooled)
+            return ops.norm_finalize(ws, N, H * W, C, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats)
+        return ops.norm_stats(y, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats)
 
     def _apply(self, y, scale, shift, act, *, residual=None, want_f32=False, want_split=True, pad=0,
                pad_mode=PAD_ZERO):
@@ -174,7 +199,7 @@ class ResnetEngine(_EngineBase):
             # wk[co, s*8 + c, r, 0] = w[co, c, r, s]
             wk.view(co, 8, 8, R)[:, :S, :ci, :] = w1.to(torch.float32).permute(0, 3, 1, 2)
             self.stem = ConvLayer(wk, g("model.1.bias"), pad=0, prec=prec, backend="tc", n_tile=n_tile)
-            self.stem_S = S
+            self.stem_S, self.stem_in_nc = S, ci
         else:
             self.stem = ConvLayer(w1, g("model.1.bias"), pad=3, backend="direct")
         self.stem_norm = nrm("model.2")
@@ -384,7 +409,11 @@ class NLayerDEngine(_EngineBase):
         prec = Precision.parse(precision) if isinstance(precision, str) else precision
         super().__init__(norm, norm_mode, prec, backend, device)
         g = lambda k: sd[k].to(device) if k in sd else None
-        self.first = ConvLayer(g("model.0.weight"), g("model.0.bias"), stride=2, pad=1, backend="direct")
+        # first conv: Cin = 6 padded to 64 zero lanes so it runs (forward, wgrad, dgrad) on the tensor cores
+        w0 = g("model.0.weight").to(torch.float32)
+        w0p = torch.zeros((w0.shape[0], 64, w0.shape[2], w0.shape[3]), dtype=torch.float32, device=device)
+        w0p[:, : w0.shape[1]] = w0
+        self.first = ConvLayer(w0p, g("model.0.bias"), stride=2, pad=1, prec=prec, backend="tc")
         self.mid = []
         idx = 2
         for n in range(1, n_layers + 1):
@@ -402,7 +431,8 @@ class NLayerDEngine(_EngineBase):
         """x: fp32 NCHW [N, 6, H, W] (cat of condition and image) -> fp32 NCHW [N, 1, h, w] logits."""
         x = x.contiguous()
         N, _, H, W = x.shape
-        y = self.first.run_direct(x, N, H, W, in_nchw=True)
+        xh, xl = ops.stem_window_pack(x, 0, 1, PAD_ZERO, self.prec.fmt, self.prec.split)
+        y, _ = self.first.run_tc([Act(None, xh, xl)], N, H, W, fuse_stats=False)
         h, w = H // 2, W // 2
         sc = sh = None
         for cv, nm in self.mid:

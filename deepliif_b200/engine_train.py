@@ -1,0 +1,228 @@
+"""Training-mode executors: forward that records a tape + backward that walks it (autograd of the reference's
+generators / discriminators, i.e. what ``loss.backward()`` does in DeepLIIF_model.py:332 and :429, on the sm_100a
+kernels).  Per recorded layer  y = conv(x);  a = act(norm(y)) [+ residual]:
+
+    backward:  dn-path   ops.norm_bwd      (norm + activation backward, param grads dgamma/dbeta)
+               dW        ConvLayer.wgrad   (tcgen05, K over pixels)   [+ bias grad = ops.channel_sum]
+               dx        ConvLayer.dgrad   (conv_tc with the weight in the opposite role)
+
+Scope of round 1: ResnetGenerator with zero padding and no dropout (BASELINE config 4: `--norm instance|batch
+--no-dropout --padding zero`) and NLayerDiscriminator.  Gradients are returned keyed by the reference's state_dict
+names so the nn.Module containers can store them in ``param.grad``."""
+import torch
+
+from . import ops
+from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_ZERO, Act, ConvLayer, NLayerDEngine, ResnetEngine,
+                     _pad_cout32)
+
+
+class _Rec:
+    """One conv -> norm -> activation step of the tape."""
+    __slots__ = ("layer", "x", "dims", "pad", "y", "sc", "sh", "mean", "rstd", "act", "np", "wkey", "nkey", "extra")
+
+    def __init__(self, **kw):
+        self.extra = None
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def _pad_lanes64(w, transposed=False):
+    """Zero-pad the output-channel dim of a conv weight to 64 lanes (GEMM M/N tiles are multiples of 64)."""
+    if transposed:
+        ci, co, R, S = w.shape
+        out = torch.zeros((ci, 64, R, S), dtype=torch.float32, device=w.device); out[:, :co] = w
+    else:
+        co, ci, R, S = w.shape
+        out = torch.zeros((64, ci, R, S), dtype=torch.float32, device=w.device); out[:co] = w
+    return out
+
+
+class _TrainOps:
+    """Shared tape helpers (mixed into the engines below)."""
+
+    def _fwd(self, tape, layer, np_, srcs, N, H, W, pad, act, wkey, nkey, *, residual=None, want_f32=False,
+             want_split=True, out_pad=0):
+        y, ws = layer.run_tc(srcs, N, H, W, pad)
+        sc, sh, mean, rstd = self._stats(y, np_, ws, want_stats=True)
+        a = self._apply(y, sc, sh, act, residual=residual, want_f32=want_f32, want_split=want_split, pad=out_pad)
+        tape.append(_Rec(layer=layer, x=srcs[0], dims=(N, H, W), pad=pad, y=y, sc=sc, sh=sh, mean=mean, rstd=rstd, act=act,
+                         np=np_, wkey=wkey, nkey=nkey))
+        return a, y
+
+    def _bwd(self, rec, grads, dout, dout2=None, need_dx=True):
+        """dout: fp32 NHWC gradient wrt the activation output of `rec`.  Returns dx (fp32 NHWC) or None."""
+        layer, (N, H, W) = rec.layer, rec.dims
+        dg = db = None
+        if rec.np is not None and rec.np.gamma is not None:
+            dg = torch.empty_like(rec.np.gamma); db = torch.empty_like(rec.np.gamma)
+        need_f32 = layer.bias is not None
+        f32, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, dout2=dout2,
+                                   pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=need_f32, want_split=True,
+                                   fmt=self.prec.fmt, need_lo=self.prec.split)
+        if dg is not None:
+            grads[rec.nkey + ".weight"], grads[rec.nkey + ".bias"] = dg, db
+        grads[rec.wkey + ".weight"] = layer.wgrad(rec.x, hi, lo, N, H, W, rec.pad)
+        if layer.bias is not None:
+            grads[rec.wkey + ".bias"] = ops.channel_sum(f32)
+        return layer.dgrad(hi, lo, N, H, W, rec.pad) if need_dx else None
+
+
+class ResnetTrainEngine(ResnetEngine, _TrainOps):
+    def __init__(self, sd, **kw):
+        if kw.get("padding_type", "zero") != "zero":
+            raise NotImplementedError("training path: zero padding only (reflect-pad backward is not built yet)")
+        if kw.get("use_dropout", False):
+            raise NotImplementedError("training path: --no-dropout only (Philox dropout is not built yet)")
+        kw.setdefault("backend", "tc")
+        super().__init__(sd, **kw)
+        if not (self.stem_tc and self.head_tc):
+            raise NotImplementedError("training path needs the tensor-core stem/head (input_nc, output_nc <= 4)")
+        dev = self.device
+        # 64-lane copy of the head's virtual-channel weight for its wgrad / dgrad GEMMs
+        wv32 = self.head.w_f32
+        wv64 = torch.zeros((64,) + tuple(wv32.shape[1:]), dtype=torch.float32, device=wv32.device)
+        wv64[:32] = wv32
+        self.head64 = ConvLayer(wv64, None, pad=0, prec=self.prec, backend="tc")
+        self.keys = self._layer_keys(sd)
+
+    def _layer_keys(self, sd):
+        idx = 4
+        down = []
+        for _ in range(2):
+            down.append((f"model.{idx}", f"model.{idx + 1}")); idx += 3
+        blocks = []
+        c1, n1, c2, n2 = 0, 1, 3, 4      # zero padding, no dropout (networks.py:479-506)
+        for _ in range(self.n_blocks):
+            pre = f"model.{idx}.conv_block"
+            blocks.append(((f"{pre}.{c1}", f"{pre}.{n1}"), (f"{pre}.{c2}", f"{pre}.{n2}"))); idx += 1
+        up = []
+        for _ in range(2):
+            up.append((f"model.{idx}", f"model.{idx + 1}")); idx += 3
+        idx += 1
+        return dict(stem=("model.1", "model.2"), down=down, blocks=blocks, up=up, head=f"model.{idx}")
+
+    def forward_train(self, x):
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        tape = []
+        K = self.keys
+        xh, xl = ops.stem_window_pack(x, 3, self.stem_S, PAD_ZERO, self.prec.fmt, self.prec.split)
+        a, _ = self._fwd(tape, self.stem, self.stem_norm, [Act(None, xh, xl)], N, H + 6, W, 0, ACT_RELU, *K["stem"])
+        h, w = H, W
+        for i in range(2):
+            a, _ = self._fwd(tape, self.down[i], self.down_norm[i], [a], N, h, w, None, ACT_RELU, *K["down"][i],
+                             want_f32=(i == 1))
+            h, w = h // 2, w // 2
+        for b, (cv1, nm1, cv2, nm2) in enumerate(self.blocks):
+            (k1, kn1), (k2, kn2) = K["blocks"][b]
+            t, _ = self._fwd(tape, cv1, nm1, [a], N, h, w, None, ACT_RELU, k1, kn1)
+            a, _ = self._fwd(tape, cv2, nm2, [t], N, h, w, None, ACT_NONE, k2, kn2, residual=a.f32, want_f32=True)
+        for i in range(2):
+            last = i == 1
+            a, _ = self._fwd(tape, self.up[i], self.up_norm[i], [a], N, h, w, None, ACT_RELU, *K["up"][i],
+                             out_pad=3 if last else 0)
+            h, w = h * 2, w * 2
+        z, _ = self.head.run_tc([a], N, h + 6, w + 6, fuse_stats=False)
+        out = ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
+        return out, dict(tape=tape, a_pad=a, out=out, N=N, H=H, W=W)
+
+    def backward(self, ctx, dY):
+        """dY: fp32 NCHW gradient wrt the tanh output.  Returns {state_dict key: gradient}."""
+        tape, N, H, W = ctx["tape"], ctx["N"], ctx["H"], ctx["W"]
+        grads = {}
+        Y = ctx["out"]
+        dzz = (dY * (1.0 - Y * Y)).contiguous()                     # tanh'  (3-channel image: glue)
+        hk = self.keys["head"]
+        grads[hk + ".bias"] = dzz.sum(dim=(0, 2, 3))
+        S, co = self.head_S, self.head_co
+        dzh, dzl = ops.head_bwd_pack(dzz, S, self.prec.fmt, self.prec.split)
+        a_pad = ctx["a_pad"]
+        G = self.head64.wgrad(a_pad, dzh, dzl, N, H + 6, W + 6, 0)                 # [64 j][ngf][R][1]
+        ngf, R = G.shape[1], G.shape[2]
+        grads[hk + ".weight"] = G[:, :, :, 0].reshape(16, 4, ngf, R)[:S, :co].permute(1, 2, 3, 0).contiguous()
+        # data gradient wrt the un-padded head input: ConvTranspose(dz, wv64) cropped by 3 on every side
+        dd = ops.conv_desc(N, H, W + 6, [64], ngf, R, 1, 1, 3, True, 0)
+        if getattr(self, "_head_wT", None) is None:
+            self._head_wT = ops.pack_weights_tc(dd, self.head64.w_f32, self.prec.fmt, self.prec.split)
+        dout = ops.conv_tc(dd, [dzh], [dzl], self._head_wT[0], self._head_wT[1], None, self.prec.fmt, self.prec.split)
+        # ---- up convs ------------------------------------------------------------------------------------------------
+        n_rec = len(tape)
+        i = n_rec - 1
+        for _ in range(2):
+            dout = self._bwd(tape[i], grads, dout); i -= 1
+        # ---- ResNet blocks: x_{k+1} = x_k + n2(c2(relu(n1(c1(x_k))))) ---------------------------------------------------
+        for _ in range(self.n_blocks):
+            dt = self._bwd(tape[i], grads, dout); i -= 1            # through norm2 + conv2 -> d(relu(n1(.)))
+            dxb = self._bwd(tape[i], grads, dt); i -= 1             # through relu + norm1 + conv1 -> branch part of dx_k
+            dout, _, _ = ops.norm_apply(dxb, None, None, ACT_NONE, dout, want_f32=True, want_split=False)   # + skip part
+        # ---- down convs + stem ----------------------------------------------------------------------------------------
+        dout = self._bwd(tape[i], grads, dout); i -= 1
+        dout = self._bwd(tape[i], grads, dout); i -= 1
+        rec = tape[i]
+        self._bwd(rec, grads, dout, need_dx=False)
+        # stem weight: G[co][s*8 + c][r][0] -> w[co][c][r][s]
+        G = grads[rec.wkey + ".weight"]
+        cin = self.stem_in_nc
+        grads[rec.wkey + ".weight"] = G[:, :, :, 0].reshape(G.shape[0], 8, 8, G.shape[2])[:, :self.stem_S, :cin] \
+            .permute(0, 2, 3, 1).contiguous()
+        return grads
+
+
+class NLayerDTrainEngine(NLayerDEngine, _TrainOps):
+    """PatchGAN forward/backward with gradient wrt the input (backward_G flows through the frozen D into G)."""
+
+    def __init__(self, sd, **kw):
+        super().__init__(sd, **kw)
+        dev = self.device
+        self.keys = [f"model.{2 + 3 * i}" for i in range(len(self.mid))]
+        self.last_key = f"model.{2 + 3 * len(self.mid)}"
+        wl64 = torch.zeros((64,) + tuple(self.last.w_f32.shape[1:]), dtype=torch.float32, device=dev)
+        wl64[:32] = self.last.w_f32
+        self.last64 = ConvLayer(wl64, None, stride=1, pad=1, prec=self.prec, backend="tc")
+
+    def forward_train(self, x):
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        tape = []
+        xh, xl = ops.stem_window_pack(x, 0, 1, PAD_ZERO, self.prec.fmt, self.prec.split)
+        # first conv (+bias), LeakyReLU: no norm
+        a, _ = self._fwd(tape, self.first, None, [Act(None, xh, xl)], N, H, W, None, ACT_LRELU02, "model.0", None)
+        h, w = H // 2, W // 2
+        for (cv, nm), key in zip(self.mid, self.keys):
+            a, y = self._fwd(tape, cv, nm, [a], N, h, w, None, ACT_LRELU02, key, f"model.{int(key.split('.')[1]) + 1}")
+            h, w = y.shape[1], y.shape[2]
+        z, _ = self.last.run_tc([a], N, h, w, fuse_stats=False)
+        out = ops.head_finish(z, self.last_bias, z.shape[2], 1, self.out_nc, ACT_NONE)
+        return out, dict(tape=tape, a_last=a, hw=(h, w), N=N, C=C, H=H, W=W)
+
+    def backward(self, ctx, dY, need_dx=True, param_grads=True):
+        """dY: fp32 NCHW [N,1,h',w'] gradient wrt the logits.  Returns (grads, dx NCHW | None)."""
+        tape, N, (h, w) = ctx["tape"], ctx["N"], ctx["hw"]
+        grads = {}
+        dY = dY.contiguous()
+        dzh, dzl = ops.head_bwd_pack(dY, 1, self.prec.fmt, self.prec.split)        # lane 0 = dY
+        if param_grads:
+            grads[self.last_key + ".bias"] = dY.sum(dim=(0, 2, 3))
+            G = self.last64.wgrad(ctx["a_last"], dzh, dzl, N, h, w, 1)             # [64][Cin][4][4]
+            grads[self.last_key + ".weight"] = G[: self.out_nc].contiguous()
+        dout = self.last64.dgrad(dzh, dzl, N, h, w, 1)
+        for i in range(len(tape) - 1, -1, -1):
+            first = i == 0
+            if param_grads:
+                dout = self._bwd(tape[i], grads, dout, need_dx=(not first) or need_dx)
+            else:
+                dout = self._bwd_data_only(tape[i], dout)
+        if param_grads:
+            G = grads["model.0.weight"]                                            # [ndf][64 padded lanes][4][4]
+            grads["model.0.weight"] = G[:, : ctx["C"]].contiguous()
+        dx = None
+        if need_dx:
+            dx = dout[..., : ctx["C"]].permute(0, 3, 1, 2).contiguous()            # padded lanes dropped, NHWC -> NCHW
+        return grads, dx
+
+    def _bwd_data_only(self, rec, dout):
+        """Frozen discriminator (set_requires_grad(False) in optimize_parameters): only dx is needed."""
+        N, H, W = rec.dims
+        _, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, pooled=self._pooled(),
+                                 want_f32=False, want_split=True, fmt=self.prec.fmt, need_lo=self.prec.split)
+        return rec.layer.dgrad(hi, lo, N, H, W, rec.pad)

@@ -48,6 +48,9 @@ class DeepLIIFModel(BaseModel):
         for i, name in enumerate(self.model_names_gs):       # seg generators use define_G's default padding (reflect)
             setattr(self, "net" + name, networks.define_G(in_nc, opt.output_nc, opt.ngf, opt.net_gs[i], opt.norm,
                                                           not opt.no_dropout, opt.init_type, opt.init_gain, self.gpu_ids))
+        if self.is_train:
+            from .. import training
+            training.install()
         for name in self.model_names_d + self.model_names_ds:
             setattr(self, "net" + name, networks.define_D(in_nc + opt.output_nc, opt.ndf, opt.netD, opt.n_layers_D,
                                                           opt.norm, opt.init_type, opt.init_gain, self.gpu_ids))

@@ -94,6 +94,7 @@ class _EngineBacked(nn.Module):
     """Common forward: (re)build the engine from the current parameters, run it."""
     precision = "bf16x3"       # parity default (SURVEY.md §8d); "bf16" = single pass
     backend = "tc"
+    GLOBAL_VERSION = 0         # bumped by optimizers that update parameter storage behind autograd's back
 
     def __init__(self):
         super().__init__()
@@ -102,7 +103,7 @@ class _EngineBacked(nn.Module):
 
     def _param_key(self):
         dev = next(self.parameters()).device
-        return (str(dev), self.precision, self.backend, self.training,
+        return (str(dev), self.precision, self.backend, self.training, _EngineBacked.GLOBAL_VERSION,
                 tuple((id(p), p._version) for p in self.parameters()))
 
     def _build_engine(self, device):

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -170,6 +170,32 @@ def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE
 
 
 _WG_CACHE = {}
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place fused Adam on flat fp32 buffers."""
+    _need_cuda(p, g, m, v)
+    check(_lib.load().dlb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                    int(step), float(grad_scale), _stream()), "dlb_adam_step")
+    LAUNCHES["count"] += 1
+
+
+def channel_sum(x, out=None, accumulate=False):
+    """Sum over all leading dims of fp32 [..., C] -> [C] (bias gradient)."""
+    _need_cuda(x, out)
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    key = ("chsum", Cc, str(x.device), torch.cuda.current_stream().cuda_stream)
+    ws = _WG_CACHE.get(key)
+    if ws is None:
+        ws = _WG_CACHE[key] = torch.empty(1024 * Cc, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        accumulate = False
+    check(_lib.load().dlb_channel_sum(_p(x), rows, Cc, _p(out), int(accumulate), _p(ws), ws.numel() * 4, _stream()),
+          "dlb_channel_sum")
+    LAUNCHES["count"] += 2
+    return out
 
 
 def conv_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw=None, accumulate=False, fmt=FMT_BF16, split=True):

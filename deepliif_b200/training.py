@@ -1,0 +1,336 @@
+"""Training step and loop: ``DeepLIIFModel.optimize_parameters`` and ``deepliif train`` on the sm_100a kernels.
+
+Reference semantics kept (deepliif/models/DeepLIIF_model.py:205-467, cli.py:194-570):
+  forward -> D step (GAN loss on detached fakes + reals, x0.5, weighted) -> G step (GAN + SmoothL1*lambda_L1, weighted)
+  Adam(lr, betas=(beta1, 0.999)), linear-decay LambdaLR stepped per epoch, checkpoints ``{epoch}_net_{name}.pth``.
+What is different underneath:
+  * every network forward/backward runs through ``engine_train`` (tcgen05 forward, dgrad, wgrad; norm backward);
+    PyTorch autograd only glues the tiny loss expressions (cat / BCE / MSE / SmoothL1 on 3-channel images and logits);
+  * parameters and gradients of all generators (resp. all discriminators) live in ONE flat fp32 bucket each:
+    the optimizer is a single fused-Adam launch per bucket and data parallelism is one NCCL all-reduce per bucket
+    (the reference wraps each of its 18 nets in its own DistributedDataParallel reducer, networks.py:134);
+  * rank 0's initial weights are broadcast (the reference re-initialises after the DDP wrap with per-rank seeds, so
+    its replicas start from different weights — SURVEY.md §5; not reproduced);
+  * the VGG perceptual term needs downloaded VGG19 weights and is outside the scope (north_star: L1 + GAN).
+Round-1 limits: ResNet generators with `--padding zero --no-dropout`, `--seg-gen False` (the seg cascade needs
+generator input gradients and the UNet backward, planned next)."""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import engine_train, ops
+from .models import networks
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# autograd bridge
+# -------------------------------------------------------------------------------------------------------------------
+class _NetFn(torch.autograd.Function):
+    """y = net(x) with the forward tape kept by the training engine; backward returns dL/dx and dL/dparams."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module.train_engine()
+        out, tape = eng.forward_train(x.detach())
+        ctx.module, ctx.eng, ctx.tape = module, eng, tape
+        ctx.names = [n for n, _ in module.named_parameters()]
+        ctx.x_needs = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        need_params = any(ctx.needs_input_grad[2:])
+        eng = ctx.eng
+        if isinstance(eng, engine_train.NLayerDTrainEngine):
+            grads, dx = eng.backward(ctx.tape, dy, need_dx=ctx.x_needs, param_grads=need_params)
+        else:
+            if ctx.x_needs:
+                raise NotImplementedError("generator input gradients (seg cascade) are not built yet")
+            grads, dx = eng.backward(ctx.tape, dy), None
+        out = [None, dx]
+        for name, need in zip(ctx.names, ctx.needs_input_grad[2:]):
+            out.append(grads.get(name) if (need and need_params) else None)
+        return tuple(out)
+
+
+def _train_engine(self):
+    key = ("train",) + self._param_key()
+    if getattr(self, "_tengine_key", None) != key:
+        dev = next(self.parameters()).device
+        sd = self.state_dict()
+        if isinstance(self, networks.ResnetGenerator):
+            self._tengine = engine_train.ResnetTrainEngine(sd, device=dev, precision=self.precision,
+                                                          norm_mode="batch" if self.cfg["norm"] == "batch" else "sample",
+                                                          **self.cfg)
+        elif isinstance(self, networks.NLayerDiscriminator):
+            self._tengine = engine_train.NLayerDTrainEngine(sd, device=dev, precision=self.precision,
+                                                           norm_mode="batch" if self.cfg["norm"] == "batch" else "sample",
+                                                           **self.cfg)
+        else:
+            raise NotImplementedError(f"training path for {type(self).__name__} is not built yet")
+        self._tengine_key = key
+    return self._tengine
+
+
+def _forward_with_grad(self, input):
+    if self.training and torch.is_grad_enabled():
+        return _NetFn.apply(self, input.float(), *self.parameters())
+    return networks._EngineBacked._inference_forward(self, input)
+
+
+def install():
+    """Give the engine-backed modules their training-mode forward (idempotent)."""
+    if getattr(networks._EngineBacked, "_train_installed", False):
+        return
+    networks._EngineBacked._inference_forward = networks._EngineBacked.forward
+    networks._EngineBacked.forward = _forward_with_grad
+    networks._EngineBacked.train_engine = _train_engine
+    networks._EngineBacked._train_installed = True
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# flat buckets + fused Adam
+# -------------------------------------------------------------------------------------------------------------------
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics on one flat fp32 bucket (parameters and gradients are views into it)."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        al = lambda k: (k + 63) // 64 * 64          # every tensor starts 256-byte aligned (kernels use 128-bit loads)
+        n = sum(al(p.numel()) for p in params)
+        dev = params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += al(k)
+        self.t = 0
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+
+    def broadcast_from_rank0(self):
+        if self.world > 1:
+            dist.broadcast(self.flat, src=0)
+
+    def all_reduce_grads(self):
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self.t += 1
+        g = self.param_groups[0]
+        ops.adam_step(self.flat, self.grad, self.m, self.v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.t,
+                      1.0 / self.world)
+        networks._EngineBacked.GLOBAL_VERSION += 1        # packed weights of every engine are now stale
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# the step (DeepLIIF_model.py:205-467)
+# -------------------------------------------------------------------------------------------------------------------
+def _d_inputs(model, i, which):
+    """Conditional-GAN discriminator input for seg head i: cat(condition, image) (DeepLIIF_model.py:252-262)."""
+    S = model.mod_id_seg
+    cond = model.real_A if i == 0 else getattr(model, f"real_B_{i}")
+    return torch.cat((cond, getattr(model, f"{which}_B_{S}")), 1)
+
+
+def _loss_D(model):
+    opt, n, S = model.opt, model.opt.modalities_no, model.mod_id_seg
+    total = torch.zeros((), device=model.device)
+    for i, name in enumerate(model.model_names_d):
+        D = model._net(name)
+        fake = torch.cat((model.real_A, getattr(model, f"fake_B_{i + 1}").detach()), 1)
+        real = torch.cat((model.real_A, getattr(model, f"real_B_{i + 1}")), 1)
+        lf = model.criterionGAN_mod(D(fake), False)
+        lr = model.criterionGAN_mod(D(real), True)
+        setattr(model, f"loss_D_fake_{i + 1}", lf); setattr(model, f"loss_D_real_{i + 1}", lr)
+        total = total + (lf + lr) * 0.5 * model.loss_D_weights[i]
+    if model.seg_gen:
+        pf = sum(model._net(nm)(_d_inputs(model, i, "fake").detach()) * model.seg_weights[i]
+                 for i, nm in enumerate(model.model_names_ds))
+        pr = sum(model._net(nm)(_d_inputs(model, i, "real")) * model.seg_weights[i]
+                 for i, nm in enumerate(model.model_names_ds))
+        lf, lr = model.criterionGAN_seg(pf, False), model.criterionGAN_seg(pr, True)
+        setattr(model, f"loss_D_fake_{S}", lf); setattr(model, f"loss_D_real_{S}", lr)
+        total = total + (lf + lr) * 0.5 * model.loss_D_weights[n]
+    model.loss_D = total
+    return total
+
+
+def _loss_G(model):
+    opt, n, S = model.opt, model.opt.modalities_no, model.mod_id_seg
+    total = torch.zeros((), device=model.device)
+    for i, name in enumerate(model.model_names_d):
+        fake_B = getattr(model, f"fake_B_{i + 1}")
+        lg = model.criterionGAN_mod(model._net(name)(torch.cat((model.real_A, fake_B), 1)), True)
+        l1 = model.criterionSmoothL1(fake_B, getattr(model, f"real_B_{i + 1}")) * opt.lambda_L1
+        setattr(model, f"loss_G_GAN_{i + 1}", lg); setattr(model, f"loss_G_L1_{i + 1}", l1)
+        total = total + (lg + l1) * model.loss_G_weights[i]
+    if model.seg_gen:
+        pf = sum(model._net(nm)(_d_inputs(model, i, "fake")) * model.seg_weights[i] for i, nm in enumerate(model.model_names_ds))
+        lg = model.criterionGAN_seg(pf, True)
+        l1 = model.criterionSmoothL1(getattr(model, f"fake_B_{S}"), getattr(model, f"real_B_{S}")) * opt.lambda_L1
+        setattr(model, f"loss_G_GAN_{S}", lg); setattr(model, f"loss_G_L1_{S}", l1)
+        # the reference weights the seg term with loss_G_weights[i] of the stale loop index (= last modality)
+        total = total + (lg + l1) * model.loss_G_weights[n - 1]
+    model.loss_G = total
+    return total
+
+
+def deepliif_step(model):
+    install()
+    model.forward()
+    d_nets = [model._net(nm) for nm in model.model_names_d + model.model_names_ds]
+    model.set_requires_grad(d_nets, True)
+    model.optimizer_D.zero_grad()
+    _loss_D(model).backward()
+    _sync_and_step(model.optimizer_D)
+    model.set_requires_grad(d_nets, False)
+    model.optimizer_G.zero_grad()
+    _loss_G(model).backward()
+    _sync_and_step(model.optimizer_G)
+
+
+def _sync_and_step(optimizer):
+    if isinstance(optimizer, FlatAdam):
+        optimizer.all_reduce_grads()
+    optimizer.step()
+    if not isinstance(optimizer, FlatAdam):
+        networks._EngineBacked.GLOBAL_VERSION += 1
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# data: AlignedDataset semantics (row of equally sized tiles: A | B_1 | ... ) — deepliif/data/aligned_dataset.py:36-113
+# -------------------------------------------------------------------------------------------------------------------
+class AlignedTiles(torch.utils.data.Dataset):
+    EXT = (".png", ".jpg", ".jpeg", ".tif", ".tiff", ".bmp")
+
+    def __init__(self, root, phase, n_targets, no_flip=True, max_dataset_size=None, seed=0):
+        d = os.path.join(root, phase)
+        self.paths = sorted(os.path.join(d, f) for f in os.listdir(d) if f.lower().endswith(self.EXT))
+        if max_dataset_size:
+            self.paths = self.paths[:max_dataset_size]
+        self.n_targets, self.no_flip = n_targets, no_flip
+        self.rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return len(self.paths)
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        from .data import transform_array
+        img = np.asarray(Image.open(self.paths[idx]).convert("RGB"))
+        k = self.n_targets + 1
+        w = img.shape[1] // k
+        flip = (not self.no_flip) and self.rng.random() < 0.5
+        tiles = []
+        for j in range(k):
+            t = img[:, j * w:(j + 1) * w]
+            if flip:
+                t = t[:, ::-1]
+            tiles.append(torch.from_numpy(transform_array(np.ascontiguousarray(t))[0]))
+        return {"A": tiles[0], "B": tiles[1:], "A_paths": self.paths[idx]}
+
+
+def _collate(items):
+    return {"A": torch.stack([it["A"] for it in items]),
+            "B": [torch.stack([it["B"][j] for it in items]) for j in range(len(items[0]["B"]))],
+            "A_paths": [it["A_paths"] for it in items]}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# `deepliif train`
+# -------------------------------------------------------------------------------------------------------------------
+def build_options(params):
+    from .options import Options
+    p = dict(params)
+    n = p["modalities_no"]
+    targets = n + (1 if p["seg_gen"] else 0)
+    p.setdefault("seg_no", 1 if p["seg_gen"] else 0)
+    p["seg_weights"] = p.get("seg_weights") or [1 / (n + 1)] * (n + 1)
+    p["loss_G_weights"] = p.pop("loss_weights_g", None) or [1 / targets] * targets
+    p["loss_D_weights"] = p.pop("loss_weights_d", None) or [1 / targets] * targets
+    p.setdefault("modalities_names", [f"mod{i}" for i in range(n + 1)])
+    opt = Options(d_params=p, mode="train")
+    opt.gpu_ids = list(p.get("gpu_ids") or [int(os.environ.get("LOCAL_RANK", "0"))])
+    opt.netD = p.get("net_d", "n_layers")
+    if opt.netD == "n_layers":
+        opt.n_layers_D = 4
+    return opt
+
+
+def make_optimizers(model):
+    """Replace the model's optimizers by flat-bucket fused Adam when --optimizer adam (the default)."""
+    opt = model.opt
+    if str(opt.optimizer).lower() != "adam":
+        return
+    g = [p for nm in model.model_names_g + model.model_names_gs for p in model._net(nm).parameters()]
+    d = [p for nm in model.model_names_d + model.model_names_ds for p in model._net(nm).parameters()]
+    model.optimizer_G = FlatAdam(g, lr=opt.lr_g, betas=(opt.beta1, 0.999))
+    model.optimizer_D = FlatAdam(d, lr=opt.lr_d, betas=(opt.beta1, 0.999))
+    model.optimizers = [model.optimizer_G, model.optimizer_D]
+    model.optimizer_G.broadcast_from_rank0(); model.optimizer_D.broadcast_from_rank0()
+
+
+def run_training(params):
+    from .models import create_model
+    from .options import print_options
+    install()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("deepliif train needs a CUDA (sm_100a) device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if params.get("seed") is not None:
+        torch.manual_seed(params["seed"]); np.random.seed(params["seed"])
+    opt = build_options(params)
+    if rank == 0:
+        print_options(opt, save=True)
+    n_targets = opt.modalities_no + (1 if opt.seg_gen else 0)
+    ds = AlignedTiles(opt.dataroot, "train", n_targets, no_flip=opt.no_flip, max_dataset_size=opt.max_dataset_size,
+                      seed=(params.get("seed") or 0) + rank)
+    sampler = torch.utils.data.distributed.DistributedSampler(ds, world, rank, shuffle=True) if world > 1 else None
+    dl = torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=sampler is None, sampler=sampler,
+                                     num_workers=opt.num_threads, collate_fn=_collate, pin_memory=True, drop_last=False)
+    model = create_model(opt)
+    model.setup(opt)
+    make_optimizers(model)
+    from .models import networks as nw
+    model.schedulers = [nw.get_scheduler(o, opt) for o in model.optimizers]
+    model.train()
+    total_iters = 0
+    for epoch in range(opt.epoch_count, opt.n_epochs + opt.n_epochs_decay + 1):
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        t0 = time.time()
+        for data in dl:
+            total_iters += opt.batch_size
+            model.set_input(data)
+            model.optimize_parameters()
+            if rank == 0 and total_iters % opt.print_freq < opt.batch_size:
+                losses = model.get_current_losses()
+                print("(epoch: %d, iters: %d) " % (epoch, total_iters) + " ".join("%s: %.3f" % kv for kv in losses.items()),
+                      flush=True)
+        if rank == 0 and (epoch % opt.save_epoch_freq == 0 or epoch == opt.n_epochs + opt.n_epochs_decay):
+            model.save_networks("latest"); model.save_networks(epoch)
+        if rank == 0:
+            print("End of epoch %d / %d \t Time Taken: %d sec" % (epoch, opt.n_epochs + opt.n_epochs_decay, time.time() - t0))
+        model.update_learning_rate()
+    if world > 1:
+        dist.barrier()

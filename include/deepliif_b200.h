@@ -121,6 +121,15 @@ int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const fl
                  float* dgamma, float* dbeta, int accumulate_param_grads, float* dy_f32, void* dy_hi, void* dy_lo,
                  int fmt, void* workspace, size_t workspace_bytes, dlb_stream_t stream);
 
+/* Fused Adam on a flat fp32 bucket (torch.optim.Adam semantics, DeepLIIF_model.py:133-146); g is scaled by grad_scale
+ * first (1/world_size after a sum all-reduce).  step counts from 1. */
+int dlb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  int step, float grad_scale, dlb_stream_t stream);
+
+/* Bias gradient: out[c] (+)= sum_rows x[rows][C] (x = dy as fp32 NHWC, rows = N*OH*OW).  workspace >= 1024*C floats. */
+int dlb_channel_sum(const float* x, long long rows, int C, float* out, int accumulate, void* workspace,
+                    size_t workspace_bytes, dlb_stream_t stream);
+
 /* Weight gradient of a convolution on the tensor cores (autograd of nn.Conv2d / nn.ConvTranspose2d wrt weight):
  *   Conv2d:          dW[co][ci][r][s] = sum_{n,oh,ow} dy[n,oh,ow,co] * x[n, oh*st + r - pad, ow*st + s - pad, ci]
  *   ConvTranspose2d: dW[ci][co][r][s] = sum_{n,ih,iw} x[n,ih,iw,ci] * dy[n, ih*st + r - pad, iw*st + s - pad, co]
