@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent generator chains are spread over")
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-events", action="store_true")
     return ap.parse_args()
@@ -180,6 +182,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.workload == "train":
+        return bench_train(args, rank, world, local, dev, dist)
     from deepliif_b200 import engine as eng_mod
     from deepliif_b200 import ops
     from deepliif_b200.models import networks
@@ -293,6 +297,65 @@ def main():
             "algorithmic_tflops": value * N_HEADS * RESNET_GFLOP / 1e3,
         }
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_train(args, rank, world, local, dev, dist):
+    """BASELINE configs[3]: pix2pix L1+GAN step, 5x (ResNet-9 G + 70x70 PatchGAN D), batch 8/GPU, flat-bucket
+    all-reduce.  One step = DeepLIIFModel.optimize_parameters() on a synthetic batch resident in HBM."""
+    from deepliif_b200 import ops, training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.models import create_model
+    B = 8 if args.batch == 32 else args.batch
+    p = dict(TRAIN_DEFAULTS, dataroot="/tmp", checkpoints_dir="/tmp/dlb_bench_ckpt", name="bench", gpu_ids=(local,),
+             modalities_no=N_HEADS, seg_gen=False, norm="instance", no_dropout=True, padding="zero", net_g="resnet_9blocks",
+             net_d="basic", batch_size=B, precision=args.precision)
+    opt = training.build_options(p)
+    torch.manual_seed(0)
+    model = create_model(opt)
+    training.make_optimizers(model)
+    model.train()
+    g = torch.Generator().manual_seed(100 + rank)
+    batches = [{"A": (torch.rand((B, 3, HW, HW), generator=g) * 2 - 1).to(dev),
+                "B": [(torch.rand((B, 3, HW, HW), generator=g) * 2 - 1).to(dev) for _ in range(N_HEADS)], "A_paths": []}
+               for _ in range(2)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        model.set_input(batches[w % 2]); model.optimize_parameters()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        model.set_input(batches[k % 2]); model.optimize_parameters()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    if rank == 0:
+        losses = model.get_current_losses()
+        # algorithmic FLOPs per tile: G fwd + bwd (2x) for 5 heads, D: 3 fwd + 2 bwd(params) + 1 bwd(data) per head
+        gflop = N_HEADS * (3 * RESNET_GFLOP + (3 + 2 * 2 + 1) * 26.11)
+        v = B * world * args.steps / (t_ms / 1e3)
+        print(json.dumps({"metric": "512x512 training tiles/sec (pix2pix step, 5x ResNet-9 G + PatchGAN D)", "value": v,
+                          "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 via %s tensor-core operands" % args.precision, "data": "synthetic",
+                          "config": {"workload": "training: pix2pix L1+GAN, 5x (ResNet-9blocks G + 70x70 PatchGAN D), "
+                                                 "batch=%d/GPU, flat-bucket all-reduce" % B, "norm": "instance",
+                                     "parallelism": "dp%d" % world},
+                          "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
+                          "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -73,7 +73,8 @@ class BaseModel(ABC):
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
 
     def get_current_losses(self):
-        return OrderedDict((n, float(getattr(self, "loss_" + n))) for n in self.loss_names if hasattr(self, "loss_" + n))
+        return OrderedDict((n, float(torch.as_tensor(getattr(self, "loss_" + n)).detach())) for n in self.loss_names
+                           if hasattr(self, "loss_" + n))
 
     def _unwrap(self, net):
         return net.module if hasattr(net, "module") and isinstance(net.module, torch.nn.Module) and \

@@ -43,13 +43,15 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         need_params = any(ctx.needs_input_grad[2:])
-        eng = ctx.eng
+        eng, tape = ctx.eng, ctx.tape
+        ctx.tape = ctx.eng = None            # ctx attributes are not released by autograd: drop the activations now
         if isinstance(eng, engine_train.NLayerDTrainEngine):
-            grads, dx = eng.backward(ctx.tape, dy, need_dx=ctx.x_needs, param_grads=need_params)
+            grads, dx = eng.backward(tape, dy, need_dx=ctx.x_needs, param_grads=need_params)
         else:
             if ctx.x_needs:
                 raise NotImplementedError("generator input gradients (seg cascade) are not built yet")
-            grads, dx = eng.backward(ctx.tape, dy), None
+            grads, dx = eng.backward(tape, dy), None
+        tape.clear()
         out = [None, dx]
         for name, need in zip(ctx.names, ctx.needs_input_grad[2:]):
             out.append(grads.get(name) if (need and need_params) else None)

@@ -23,7 +23,7 @@ def _leafify(sd):
     return {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
 
 
-def _cmp(grads, ref_sd, tol_l2=5e-3):
+def _cmp(grads, ref_sd, tol_l2=2e-2):
     """Relative L2 error per gradient tensor.  A max-abs gate is ill-posed here: the (Leaky)ReLU derivative is a step,
     so a pre-activation within ~1e-4 of zero (the forward tolerance) flips one mask element, which moves single
     weight-gradient entries by a few % at these tiny test extents (K = a few hundred pixels) — in *any* two fp32
@@ -135,7 +135,7 @@ def test_one_optimisation_step_matches_oracle(norm, tmp_path):
     from deepliif_b200.cli import TRAIN_DEFAULTS
     from deepliif_b200.models import create_model
     p = dict(TRAIN_DEFAULTS, dataroot=str(tmp_path), checkpoints_dir=str(tmp_path), name="t", gpu_ids=(0,), modalities_no=2,
-             seg_gen=False, norm=norm, no_dropout=True, padding="zero", net_g="resnet_9blocks", batch_size=2)
+             seg_gen=False, norm=norm, no_dropout=True, padding="zero", net_g="resnet_3blocks", batch_size=2)
     opt = training.build_options(p)
     torch.manual_seed(0)
     model = create_model(opt)
@@ -148,8 +148,8 @@ def test_one_optimisation_step_matches_oracle(norm, tmp_path):
     model.optimize_parameters()
     torch.cuda.synchronize()
     got = model.get_current_losses()
-    cfg = dict(n_blocks=9, norm=norm, use_dropout=False, padding_type="zero")
-    torch.set_num_threads(os.cpu_count())
+    cfg = dict(n_blocks=3, norm=norm, use_dropout=False, padding_type="zero")
+    torch.set_num_threads(min(32, os.cpu_count()))
     G, D, want = _oracle_step(sds_g, sds_d, A, Bs, cfg, norm=norm)
     for k, v in want.items():
         print(f"loss {k}: ours {got[k]:.6f} oracle {v:.6f}")
