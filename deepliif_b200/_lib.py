@@ -33,7 +33,7 @@ SIGNATURES = {
     "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
     "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "dlb_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+    "dlb_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                           _i, _vp, _sz, _vp]),
     "dlb_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _i, _f, _vp]),
     "dlb_channel_sum": (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _sz, _vp]),

@@ -29,6 +29,7 @@ struct BwdParams {
   const float* dout; const float* dout2; const float* y;
   const float* scale; const float* shift; const float* mean; const float* rstd;
   int act, N, HW, C;
+  int act2;                 // activation of the branch dout2 flows through (UNet: LeakyReLU down path + ReLU skip path)
 };
 
 // grid (slices, N), block 256: thread = (pixel lane, channel quad); fixed-order merge over the pixel lanes.
@@ -54,15 +55,14 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const BwdParams p,
       for (int px = p0 + pl; px < p1; px += lanes) {
         const long long off = (static_cast<long long>(n) * p.HW + px) * p.C + cq * 4;
         const float4 yv = *reinterpret_cast<const float4*>(p.y + off);
-        float4 dv = *reinterpret_cast<const float4*>(p.dout + off);
-        if (p.dout2 != nullptr) {
-          const float4 d2 = *reinterpret_cast<const float4*>(p.dout2 + off);
-          dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
-        }
-        const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+        const float4 dv = *reinterpret_cast<const float4*>(p.dout + off);
+        float4 d2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dout2 != nullptr) d2 = *reinterpret_cast<const float4*>(p.dout2 + off);
+        const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float dn = dd[k] * dact(fmaf(yy[k], scv[k], shv[k]), p.act);
+          const float nn = fmaf(yy[k], scv[k], shv[k]);
+          const float dn = dd[k] * dact(nn, p.act) + d2v[k] * dact(nn, p.act2);
           a1[k] += dn;
           a2[k] = fmaf(dn, (yy[k] - muv[k]) * rsv[k], a2[k]);
         }
@@ -156,12 +156,10 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const BwdParams p, 
     const int n = static_cast<int>(q / (static_cast<long long>(p.HW) * c4n));
     const long long off = q * 4;
     const float4 yv = __ldcs(reinterpret_cast<const float4*>(p.y + off));
-    float4 dv = __ldcs(reinterpret_cast<const float4*>(p.dout + off));
-    if (p.dout2 != nullptr) {
-      const float4 d2 = __ldcs(reinterpret_cast<const float4*>(p.dout2 + off));
-      dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
-    }
-    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float4 dv = __ldcs(reinterpret_cast<const float4*>(p.dout + off));
+    float4 d2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dout2 != nullptr) d2 = __ldcs(reinterpret_cast<const float4*>(p.dout2 + off));
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
     float o[4];
     if (p.scale != nullptr) {
       const int b = n * p.C + cq * 4;
@@ -176,13 +174,14 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const BwdParams p, 
       const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k2v[4] = {k2.x, k2.y, k2.z, k2.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float dn = dd[k] * dact(fmaf(yy[k], scv[k], shv[k]), p.act);
+        const float nn = fmaf(yy[k], scv[k], shv[k]);
+        const float dn = dd[k] * dact(nn, p.act) + d2v[k] * dact(nn, p.act2);
         const float yh = (yy[k] - muv[k]) * rsv[k];
         o[k] = scv[k] * (dn - k1v[k] - yh * k2v[k]);
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = dd[k] * dact(yy[k], p.act);
+      for (int k = 0; k < 4; ++k) o[k] = dd[k] * dact(yy[k], p.act) + d2v[k] * dact(yy[k], p.act2);
     }
     if (dy_f32 != nullptr) *reinterpret_cast<float4*>(dy_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
     if (dy_hi != nullptr) {
@@ -239,12 +238,12 @@ extern "C" int dlb_channel_sum(const float* x, long long rows, int C, float* out
 // dout2 (nullable): second addend of the incoming gradient.  scale == NULL: the layer has no norm (then only `apply`
 // is meaningful: dy = dOut * act'(y)).  c1/c2: fp32 [N,C] scratch produced by reduce+finalize, consumed by apply.
 extern "C" int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const float* scale, const float* shift,
-                            const float* mean, const float* rstd, int act, int N, int HW, int C, int pooled,
+                            const float* mean, const float* rstd, int act, int act2, int N, int HW, int C, int pooled,
                             float* c1, float* c2, float* dgamma, float* dbeta, int accumulate_param_grads,
                             float* dy_f32, void* dy_hi, void* dy_lo, int fmt, void* workspace, size_t workspace_bytes,
                             dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_bwd: C % 4 != 0");
-  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C};
+  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C, act2};
   if (scale != nullptr) {
     const int c4n = C / 4;
     if ((c4n < 256 && 256 % c4n != 0) || (c4n > 256 && c4n % 256 != 0)) return set_error("dlb_norm_bwd: C/4 must divide 256");

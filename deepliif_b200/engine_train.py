@@ -12,8 +12,8 @@ names so the nn.Module containers can store them in ``param.grad``."""
 import torch
 
 from . import ops
-from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_ZERO, Act, ConvLayer, NLayerDEngine, ResnetEngine,
-                     _pad_cout32)
+from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_ZERO, Act, ConvLayer, NLayerDEngine, Precision,
+                     ResnetEngine, _EngineBase, _NormParams, _pad_cout32)
 
 
 class _Rec:
@@ -226,3 +226,179 @@ class NLayerDTrainEngine(NLayerDEngine, _TrainOps):
         _, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, pooled=self._pooled(),
                                  want_f32=False, want_split=True, fmt=self.prec.fmt, need_lo=self.prec.split)
         return rec.layer.dgrad(hi, lo, N, H, W, rec.pad)
+
+
+class UnetTrainEngine(_EngineBase, _TrainOps):
+    """UnetGenerator forward with tape + backward (incl. the gradient wrt the input: the seg generators of the DeepLIIF
+    cascade sit behind the modality generators, DeepLIIF_model.py:175-203, so dL/d(fake_B_i) flows through them).
+
+    n_k = norm(d_k) is consumed twice — LeakyReLU into the next down conv and ReLU (skip) into this level's up conv —
+    so its backward is one ``norm_bwd`` call with two (gradient, activation) pairs.  The skip concat is never
+    materialised: the up-conv weight gradient is computed per source into row slices of dW, and the data gradient per
+    source from the matching weight rows."""
+
+    def __init__(self, sd, *, num_downs=9, norm="batch", norm_mode="batch", precision="bf16x3", device="cuda", use_dropout=False):
+        if use_dropout:
+            raise NotImplementedError("training path: --no-dropout only (Philox dropout is not built yet)")
+        _EngineBase.__init__(self, norm, norm_mode, Precision.parse(precision) if isinstance(precision, str) else precision,
+                             "tc", device)
+        self.nd = num_downs
+        g = lambda k: sd[k].to(device) if k in sd else None
+        pre = ["model.model"]
+        for lvl in range(1, num_downs):
+            pre.append(f"{pre[-1]}.{1 if lvl == 1 else 3}.model")
+        self.dkey, self.ukey, self.dnkey, self.unkey = [], [], [], []
+        self.down, self.down_norm, self.up_w, self.up_b, self.up_norm, self.up_cins = [], [], [], [], [], []
+        prec = self.prec
+        for lvl in range(num_downs):
+            p, inner = pre[lvl], lvl == num_downs - 1
+            dk = f"{p}.0" if lvl == 0 else f"{p}.1"
+            uk = f"{p}.3" if (lvl == 0 or inner) else f"{p}.5"
+            self.dkey.append(dk); self.ukey.append(uk)
+            wd = g(dk + ".weight").to(torch.float32)
+            if lvl == 0:                                             # input_nc -> 64 zero lanes
+                self.in_nc = wd.shape[1]
+                wp = torch.zeros((wd.shape[0], 64, 4, 4), dtype=torch.float32, device=device); wp[:, : self.in_nc] = wd
+                wd = wp
+            self.down.append(ConvLayer(wd, g(dk + ".bias"), stride=2, pad=1, prec=prec, backend="tc"))
+            has_dn = 0 < lvl < num_downs - 1
+            self.dnkey.append(f"{p}.2" if has_dn else None)
+            self.down_norm.append(_NormParams(sd, f"{p}.2", norm, device) if has_dn else None)
+            wu = g(uk + ".weight").to(torch.float32)                 # ConvTranspose2d: (Cin_total, Cout, 4, 4)
+            if lvl == 0:
+                self.out_nc = wu.shape[1]
+                wp = torch.zeros((wu.shape[0], 64, 4, 4), dtype=torch.float32, device=device); wp[:, : self.out_nc] = wu
+                wu = wp
+            self.up_w.append(wu); self.up_b.append(g(uk + ".bias"))
+            ct = wu.shape[0]
+            self.up_cins.append([ct] if inner else [ct // 2, ct // 2])
+            nk = None if lvl == 0 else (f"{p}.4" if inner else f"{p}.6")
+            self.unkey.append(nk)
+            self.up_norm.append(_NormParams(sd, nk, norm, device) if nk else None)
+        # per-source up-conv layers: forward uses one dual-source layer, backward one single-source layer per source
+        self.up = [ConvLayer(self.up_w[l], None if l == 0 else self.up_b[l], transposed=True, stride=2, pad=1, cins=self.up_cins[l],
+                             prec=prec, backend="tc", n_tile=0) for l in range(num_downs)]
+        self.up_src = []
+        for l in range(num_downs):
+            off, layers = 0, []
+            for c in self.up_cins[l]:
+                layers.append(ConvLayer(self.up_w[l][off:off + c].contiguous(), None, transposed=True, stride=2, pad=1, prec=prec,
+                                        backend="tc"))
+                off += c
+            self.up_src.append(layers)
+        self.out_bias = self.up_b[0].detach().to(torch.float32).contiguous()
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def forward_train(self, x):
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        L = self.nd
+        xh, xl = ops.stem_window_pack(x, 0, 1, PAD_ZERO, self.prec.fmt, self.prec.split)
+        d_in, d_raw, d_stats, dims = [Act(None, xh, xl)], [], [], []
+        h, w = H, W
+        for lvl in range(L):
+            if lvl > 0:
+                sc, sh = d_stats[lvl - 1][0], d_stats[lvl - 1][1]
+                d_in.append(self._apply(d_raw[lvl - 1], sc, sh, ACT_LRELU02))
+            y, ws = self.down[lvl].run_tc([d_in[lvl]], N, h, w)
+            dims.append((h, w))
+            h, w = h // 2, w // 2
+            d_raw.append(y)
+            d_stats.append(self._stats(y, self.down_norm[lvl], ws, want_stats=True))
+        u_src, u_raw, u_stats = [None] * L, [None] * L, [None] * L
+        below = None
+        for lvl in range(L - 1, -1, -1):
+            hh, ww = dims[lvl][0] // 2, dims[lvl][1] // 2            # spatial extent of d_lvl = input of the up conv
+            sc, sh = d_stats[lvl][0], d_stats[lvl][1]
+            skip = self._apply(d_raw[lvl], sc, sh, ACT_RELU)
+            srcs = [skip] if lvl == L - 1 else [skip, below]
+            u_src[lvl] = srcs
+            y, ws = self.up[lvl].run_tc(srcs, N, hh, ww, fuse_stats=(lvl != 0))
+            u_raw[lvl] = y
+            if lvl == 0:
+                z32 = y[..., :32].contiguous() if y.shape[3] != 32 else y
+                out = ops.head_finish(z32, self.out_bias, 2 * ww, 1, self.out_nc, ACT_TANH)
+            else:
+                u_stats[lvl] = self._stats(y, self.up_norm[lvl], ws, want_stats=True)
+                below = self._apply(y, u_stats[lvl][0], u_stats[lvl][1], ACT_RELU)
+        return out, dict(N=N, H=H, W=W, dims=dims, d_in=d_in, d_raw=d_raw, d_stats=d_stats, u_src=u_src, u_raw=u_raw,
+                         u_stats=u_stats, out=out)
+
+    # ---- backward --------------------------------------------------------------------------------------------------
+    def _up_backward(self, lvl, ctx, grads, dy_hi, dy_lo, N, hh, ww):
+        """wgrad + per-source dgrad of the up ConvTranspose at `lvl`; returns the list of source gradients (fp32 NHWC)."""
+        srcs = ctx["u_src"][lvl]
+        dws, dxs = [], []
+        for layer, src in zip(self.up_src[lvl], srcs):
+            dws.append(layer.wgrad(src, dy_hi, dy_lo, N, hh, ww))
+            dxs.append(layer.dgrad(dy_hi, dy_lo, N, hh, ww))
+        dW = torch.cat(dws, dim=0)
+        if lvl == 0:
+            dW = dW[:, : self.out_nc].contiguous()
+        grads[self.ukey[lvl] + ".weight"] = dW
+        return dxs
+
+    def backward(self, ctx, dY, need_dx=True):
+        N, L, dims = ctx["N"], self.nd, ctx["dims"]
+        grads = {}
+        Y = ctx["out"]
+        dzz = (dY * (1.0 - Y * Y)).contiguous()
+        grads[self.ukey[0] + ".bias"] = dzz.sum(dim=(0, 2, 3))
+        dzh, dzl = ops.head_bwd_pack(dzz, 1, self.prec.fmt, self.prec.split)          # [N, H, W, 64 lanes]
+        g_relu, g_below = [None] * L, [None] * (L + 1)
+        # ---- up path, outermost -> innermost ------------------------------------------------------------------------
+        hh, ww = dims[0][0] // 2, dims[0][1] // 2
+        dxs = self._up_backward(0, ctx, grads, dzh, dzl, N, hh, ww)
+        g_relu[0] = dxs[0]
+        if L > 1:
+            g_below[1] = dxs[1]
+        for lvl in range(1, L):
+            hh, ww = dims[lvl][0] // 2, dims[lvl][1] // 2
+            sc, sh, mean, rstd = ctx["u_stats"][lvl]
+            np_ = self.up_norm[lvl]
+            dg = db = None
+            if np_ is not None and np_.gamma is not None:
+                dg, db = torch.empty_like(np_.gamma), torch.empty_like(np_.gamma)
+            has_bias = self.up_b[lvl] is not None
+            f32, hi, lo = ops.norm_bwd(g_below[lvl], ctx["u_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
+                                       dgamma=dg, dbeta=db, want_f32=has_bias, want_split=True, fmt=self.prec.fmt,
+                                       need_lo=self.prec.split)
+            if dg is not None:
+                grads[self.unkey[lvl] + ".weight"], grads[self.unkey[lvl] + ".bias"] = dg, db
+            if has_bias:
+                grads[self.ukey[lvl] + ".bias"] = ops.channel_sum(f32)
+            dxs = self._up_backward(lvl, ctx, grads, hi, lo, N, hh, ww)
+            g_relu[lvl] = dxs[0]
+            if lvl < L - 1:
+                g_below[lvl + 1] = dxs[1]
+        # ---- down path, innermost -> outermost ------------------------------------------------------------------------
+        g_lrelu = None
+        for lvl in range(L - 1, -1, -1):
+            h, w = dims[lvl]
+            sc, sh, mean, rstd = ctx["d_stats"][lvl]
+            np_ = self.down_norm[lvl]
+            dg = db = None
+            if np_ is not None and np_.gamma is not None:
+                dg, db = torch.empty_like(np_.gamma), torch.empty_like(np_.gamma)
+            layer = self.down[lvl]
+            has_bias = layer.bias is not None
+            if g_lrelu is None:       # innermost: d is consumed only through the skip ReLU
+                f32, hi, lo = ops.norm_bwd(g_relu[lvl], ctx["d_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
+                                           dgamma=dg, dbeta=db, want_f32=has_bias, want_split=True, fmt=self.prec.fmt,
+                                           need_lo=self.prec.split)
+            else:
+                f32, hi, lo = ops.norm_bwd(g_lrelu, ctx["d_raw"][lvl], sc, sh, mean, rstd, ACT_LRELU02, dout2=g_relu[lvl],
+                                           act2=ACT_RELU, pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=has_bias,
+                                           want_split=True, fmt=self.prec.fmt, need_lo=self.prec.split)
+            if dg is not None:
+                grads[self.dnkey[lvl] + ".weight"], grads[self.dnkey[lvl] + ".bias"] = dg, db
+            if has_bias:
+                grads[self.dkey[lvl] + ".bias"] = ops.channel_sum(f32)
+            dW = layer.wgrad(ctx["d_in"][lvl], hi, lo, N, h, w)
+            if lvl == 0:
+                dW = dW[:, : self.in_nc].contiguous()
+            grads[self.dkey[lvl] + ".weight"] = dW
+            if lvl > 0 or need_dx:
+                g_lrelu = layer.dgrad(hi, lo, N, h, w)
+        dx = g_lrelu[..., : self.in_nc].permute(0, 3, 1, 2).contiguous() if need_dx else None
+        return grads, dx

@@ -93,7 +93,11 @@ class DeepLIIFModel(BaseModel):
                 src = self.real_A if i == 0 else getattr(self, f"fake_B_{i}")
                 parts.append(self._net(name)(src))
                 setattr(self, f"fake_B_{S}_{i}", parts[-1])
-            seg, _, _ = ops.seg_finish([p.contiguous() for p in parts], self.seg_weights, want_u8=False, want_mask=False)
+            if self.is_train and torch.is_grad_enabled():
+                # differentiable form of the same weighted sum (3-channel images: autograd glue)
+                seg = torch.stack([torch.mul(p, w) for p, w in zip(parts, self.seg_weights)]).sum(dim=0)
+            else:
+                seg, _, _ = ops.seg_finish([p.contiguous() for p in parts], self.seg_weights, want_u8=False, want_mask=False)
             setattr(self, f"fake_B_{S}", seg)
 
     def optimize_parameters(self):

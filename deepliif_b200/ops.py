@@ -149,7 +149,7 @@ def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=Fals
     return (scale, shift, mean, rstd) if want_stats else (scale, shift)
 
 
-def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE, dout2=None, pooled=False,
+def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE, dout2=None, act2=None, pooled=False,
              dgamma=None, dbeta=None, accumulate=False, want_f32=False, want_split=True, fmt=FMT_BF16, need_lo=True):
     """Backward of norm(+affine)+activation: returns (dy_f32 | None, dy_hi | None, dy_lo | None); writes the
     parameter gradients into dgamma/dbeta (fp32 [C]) when given.  scale=None: layer without norm."""
@@ -162,7 +162,8 @@ def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE
     hi = torch.empty(y.shape, dtype=_dtype(fmt), device=dev) if want_split else None
     lo = torch.empty(y.shape, dtype=_dtype(fmt), device=dev) if (want_split and need_lo) else None
     ws = stats_workspace(N, H * W, Cc, dev)
-    check(_lib.load().dlb_norm_bwd(_p(dout), _p(dout2), _p(y), _p(scale), _p(shift), _p(mean), _p(rstd), act, N, H * W, Cc,
+    check(_lib.load().dlb_norm_bwd(_p(dout), _p(dout2), _p(y), _p(scale), _p(shift), _p(mean), _p(rstd), act,
+                                   act if act2 is None else act2, N, H * W, Cc,
                                    int(pooled), _p(c1), _p(c2), _p(dgamma), _p(dbeta), int(accumulate), _p(f32), _p(hi),
                                    _p(lo), fmt, _p(ws), ws.numel() * 4, _stream()), "dlb_norm_bwd")
     LAUNCHES["count"] += 3 if scale is not None else 1

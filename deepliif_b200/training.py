@@ -12,8 +12,8 @@ What is different underneath:
   * rank 0's initial weights are broadcast (the reference re-initialises after the DDP wrap with per-rank seeds, so
     its replicas start from different weights — SURVEY.md §5; not reproduced);
   * the VGG perceptual term needs downloaded VGG19 weights and is outside the scope (north_star: L1 + GAN).
-Round-1 limits: ResNet generators with `--padding zero --no-dropout`, `--seg-gen False` (the seg cascade needs
-generator input gradients and the UNet backward, planned next)."""
+Limits: `--padding zero --no-dropout` (reflect-pad backward and Philox dropout are not built); seg generators of the
+cascade must be UNets (`--net-gs unet_*`, the reference default): ResNet generators do not return input gradients yet."""
 import os
 import time
 
@@ -47,6 +47,8 @@ class _NetFn(torch.autograd.Function):
         ctx.tape = ctx.eng = None            # ctx attributes are not released by autograd: drop the activations now
         if isinstance(eng, engine_train.NLayerDTrainEngine):
             grads, dx = eng.backward(tape, dy, need_dx=ctx.x_needs, param_grads=need_params)
+        elif isinstance(eng, engine_train.UnetTrainEngine):
+            grads, dx = eng.backward(tape, dy, need_dx=ctx.x_needs)
         else:
             if ctx.x_needs:
                 raise NotImplementedError("generator input gradients (seg cascade) are not built yet")
@@ -71,6 +73,10 @@ def _train_engine(self):
             self._tengine = engine_train.NLayerDTrainEngine(sd, device=dev, precision=self.precision,
                                                            norm_mode="batch" if self.cfg["norm"] == "batch" else "sample",
                                                            **self.cfg)
+        elif isinstance(self, networks.UnetGenerator):
+            self._tengine = engine_train.UnetTrainEngine(sd, device=dev, precision=self.precision,
+                                                        norm_mode="batch" if self.cfg["norm"] == "batch" else "sample",
+                                                        **self.cfg)
         else:
             raise NotImplementedError(f"training path for {type(self).__name__} is not built yet")
         self._tengine_key = key

@@ -111,13 +111,14 @@ int dlb_norm_apply(const float* y, const float* scale, const float* shift, int a
 
 /* ---- training: backward of norm + activation -------------------------------------------------------------------
  * Autograd of BatchNorm2d (batch statistics) / InstanceNorm2d + ReLU / LeakyReLU(0.2) (networks.py:25-44, 391-404,
- * 490-513, 640-656).  With n = y*scale + shift, yhat = (y-mean)*rstd, dn = (dout [+ dout2]) * act'(n):
+ * 490-513, 640-656).  With n = y*scale + shift, yhat = (y-mean)*rstd, dn = dout*act'(n) [+ dout2*act2'(n)] (the second
+ * term: a tensor consumed through two activations, e.g. the UNet skip: LeakyReLU into the down conv, ReLU into the up conv):
  *   dbeta = sum dn, dgamma = sum dn*yhat (nullable; += when accumulate_param_grads),
  *   dy = scale * (dn - mean_g(dn) - yhat * mean_g(dn*yhat)),  g = (n,c) plane, or the batch when pooled.
  * scale == NULL: layer without norm, dy = dn with n = y.  c1/c2: fp32 [N,C] scratch.  dy is written as fp32 and/or
  * as hi/lo planes (operands of the dgrad / wgrad GEMMs).  workspace: dlb_norm_stats_workspace(N, HW, C) bytes. */
 int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const float* scale, const float* shift,
-                 const float* mean, const float* rstd, int act, int N, int HW, int C, int pooled, float* c1, float* c2,
+                 const float* mean, const float* rstd, int act, int act2, int N, int HW, int C, int pooled, float* c1, float* c2,
                  float* dgamma, float* dbeta, int accumulate_param_grads, float* dy_f32, void* dy_hi, void* dy_lo,
                  int fmt, void* workspace, size_t workspace_bytes, dlb_stream_t stream);
 

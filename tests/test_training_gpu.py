@@ -173,3 +173,76 @@ def test_one_optimisation_step_matches_oracle(norm, tmp_path):
             frac, cos = n_bad / n_all, dot / (na * nb) ** 0.5
             print(f"{tag}{i + 1}: Adam-step cosine {cos:.4f}; weights off by > lr/2: {100 * frac:.3f}% of {n_all}")
             assert cos > 0.95 and frac < 0.06
+
+
+@pytest.mark.parametrize("norm,norm_mode,nd,hw", [("instance", "sample", 5, 64), ("batch", "batch", 6, 128), ("batch", "batch", 9, 512)])
+def test_unet_generator_gradients_and_input_gradient(norm, norm_mode, nd, hw):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import engine_train
+    sd = nets.make_state_dict(nets.unet_param_shapes(nd, 64, 3, 3, norm), 9, "stress")
+    n = 1 if hw == 512 else 2
+    x = _rand((n, 3, hw, hw), 95).requires_grad_(True)
+    dY = _rand((n, 3, hw, hw), 96)
+    leaf = _leafify(sd)
+    torch.set_num_threads(min(32, os.cpu_count()))
+    y_ref = nets.unet_forward(x, leaf, num_downs=nd, norm=norm, norm_mode=norm_mode)
+    (y_ref * dY).sum().backward()
+    eng = engine_train.UnetTrainEngine(sd, num_downs=nd, norm=norm, norm_mode=norm_mode)
+    y, ctx = eng.forward_train(x.detach().cuda())
+    assert (y.cpu() - y_ref.detach()).abs().max().item() < 1e-3
+    grads, dx = eng.backward(ctx, dY.cuda(), need_dx=True)
+    expected = {k for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad}
+    assert set(grads) == expected, set(grads) ^ expected
+    worst = _cmp(grads, leaf, tol_l2=3e-2)
+    errx = (dx.cpu() - x.grad).norm().item() / x.grad.norm().item()
+    print(f"unet{nd} {norm}/{norm_mode} @{hw}: worst rel-L2 param-grad error {worst:.2e}, input-grad rel-L2 {errx:.2e}")
+    assert errx < 1e-2
+
+
+def test_default_cascade_step_runs_and_matches_oracle_losses(tmp_path):
+    """The reference's default topology (ResNet modality generators, UNet seg generators behind them, n_layers=4
+    PatchGANs, seg_gen=True) at reduced size: one optimize_parameters(); the D/G losses of the first step only
+    depend on the forward pass, so they must match the oracle cascade."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.models import create_model
+    p = dict(TRAIN_DEFAULTS, dataroot=str(tmp_path), checkpoints_dir=str(tmp_path), name="c", gpu_ids=(0,), modalities_no=2,
+             seg_gen=True, norm="batch", no_dropout=True, padding="zero", net_g="resnet_2blocks", net_gs="unet_128", batch_size=2)
+    opt = training.build_options(p)
+    torch.manual_seed(1)
+    model = create_model(opt)
+    sd = {nm: {k: v.detach().cpu().clone() for k, v in model._net(nm).module.state_dict().items()} for nm in model.model_names}
+    training.make_optimizers(model)
+    model.train()
+    A = _rand((2, 3, 128, 128), 60); Bs = [_rand((2, 3, 128, 128), 61 + i) for i in range(3)]
+    model.set_input({"A": A, "B": Bs, "A_paths": []})
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+    got = model.get_current_losses()
+    # oracle forward + first-step losses (BatchNorm in training mode: pooled statistics)
+    cfg = dict(n_blocks=2, norm="batch", use_dropout=False, padding_type="zero", norm_mode="batch")
+    with torch.no_grad():
+        fk = [nets.resnet_forward(A, sd[f"G{i + 1}"], **cfg) for i in range(2)]
+        us = lambda t, s: nets.unet_forward(t, s, num_downs=7, norm="batch", norm_mode="batch")
+        parts = [us(A, sd["GS0"]), us(fk[0], sd["GS1"]), us(fk[1], sd["GS2"])]
+        w = opt.seg_weights
+        seg = sum(p_ * w_ for p_, w_ in zip(parts, w))
+        D = lambda t, s: nets.nlayer_d_forward(t, s, n_layers=4, norm="batch", norm_mode="batch")
+        bce = torch.nn.BCEWithLogitsLoss(); mse = torch.nn.MSELoss(); sl1 = torch.nn.SmoothL1Loss()
+        want = {}
+        for i in range(2):
+            pf = D(torch.cat((A, fk[i]), 1), sd[f"D{i + 1}"]); pr = D(torch.cat((A, Bs[i]), 1), sd[f"D{i + 1}"])
+            want[f"D_fake_{i + 1}"] = bce(pf, torch.zeros_like(pf)).item(); want[f"D_real_{i + 1}"] = bce(pr, torch.ones_like(pr)).item()
+            want[f"G_L1_{i + 1}"] = (sl1(fk[i], Bs[i]) * 100).item()
+        conds = [A, Bs[0], Bs[1]]
+        pf = sum(D(torch.cat((c, seg), 1), sd[f"DS{i}"]) * w[i] for i, c in enumerate(conds))
+        pr = sum(D(torch.cat((c, Bs[2]), 1), sd[f"DS{i}"]) * w[i] for i, c in enumerate(conds))
+        want["D_fake_S"] = mse(pf, torch.zeros_like(pf)).item(); want["D_real_S"] = mse(pr, torch.ones_like(pr)).item()
+        want["G_L1_S"] = (sl1(seg, Bs[2]) * 100).item()
+    for k, v in want.items():
+        print(f"loss {k}: ours {got[k]:.6f} oracle {v:.6f}")
+        assert abs(got[k] - v) <= 2e-3 * max(1.0, abs(v)), k
+    assert all(torch.isfinite(p_).all() for nm in model.model_names for p_ in model._net(nm).parameters())
