@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 
 #include "internal.h"
+#include "rng.cuh"
 #include "stats_ws.h"
 
 namespace dlb {
@@ -168,6 +169,7 @@ struct ApplyParams {
   const float* y; const float* scale; const float* shift; int act; const float* residual;
   float* out_f32; void* out_hi; void* out_lo;
   int N, H, W, C, pad, pad_mode;
+  float drop_p; unsigned long long drop_seed;     // training-time nn.Dropout after the activation (0 = off)
 };
 
 // grid (x: quads of one padded output row, y: rows n*HP + hp).  One thread = 4 channels of one output pixel;
@@ -226,6 +228,11 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) o[k] = act1(o[k], p.act);
+          if (p.drop_p > 0.f) {
+            const unsigned long long e = (static_cast<unsigned long long>(n) * p.H + h) * p.W * p.C + srcs[u];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] *= dropout_scale(p.drop_seed, e + k, p.drop_p);
+          }
           o[0] += rv[u].x; o[1] += rv[u].y; o[2] += rv[u].z; o[3] += rv[u].w;
           if (frow != nullptr && !border[u])
             *reinterpret_cast<float4*>(frow + srcs[u]) = make_float4(o[0], o[1], o[2], o[3]);
@@ -379,11 +386,12 @@ extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, 
 
 extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                               float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
-                              int pad_mode, dlb_stream_t stream) {
+                              int pad_mode, float drop_p, unsigned long long drop_seed, dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_apply: C % 4 != 0");
   if (pad < 0 || (pad_mode == DLB_PAD_REFLECT && (pad >= H || pad >= W))) return set_error("dlb_norm_apply: bad pad");
   if (out_hi == nullptr && out_f32 == nullptr) return set_error("dlb_norm_apply: no output");
-  ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode};
+  if (drop_p < 0.f || drop_p >= 1.f) return set_error("dlb_norm_apply: dropout p must be in [0, 1)");
+  ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode, drop_p, drop_seed};
   const int row_quads = (W + 2 * pad) * (C / 4);
   const int rows = N * (H + 2 * pad);
   int gx = (row_quads + 1023) / 1024; if (gx > 64) gx = 64;

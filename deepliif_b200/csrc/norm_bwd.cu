@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 
 #include "internal.h"
+#include "rng.cuh"
 #include "stats_ws.h"
 
 namespace dlb {
@@ -30,6 +31,7 @@ struct BwdParams {
   const float* scale; const float* shift; const float* mean; const float* rstd;
   int act, N, HW, C;
   int act2;                 // activation of the branch dout2 flows through (UNet: LeakyReLU down path + ReLU skip path)
+  float drop_p; unsigned long long drop_seed;   // dropout that followed the activation on the dout branch (0 = off)
 };
 
 // grid (slices, N), block 256: thread = (pixel lane, channel quad); fixed-order merge over the pixel lanes.
@@ -58,7 +60,12 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const BwdParams p,
         const float4 dv = *reinterpret_cast<const float4*>(p.dout + off);
         float4 d2 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.dout2 != nullptr) d2 = *reinterpret_cast<const float4*>(p.dout2 + off);
-        const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
+        const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
+        float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+        if (p.drop_p > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(p.drop_seed, static_cast<unsigned long long>(off) + k, p.drop_p);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float nn = fmaf(yy[k], scv[k], shv[k]);
@@ -159,7 +166,12 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const BwdParams p, 
     const float4 dv = __ldcs(reinterpret_cast<const float4*>(p.dout + off));
     float4 d2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.dout2 != nullptr) d2 = __ldcs(reinterpret_cast<const float4*>(p.dout2 + off));
-    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, d2v[4] = {d2.x, d2.y, d2.z, d2.w};
+    float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+    if (p.drop_p > 0.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(p.drop_seed, static_cast<unsigned long long>(off) + k, p.drop_p);
+    }
     float o[4];
     if (p.scale != nullptr) {
       const int b = n * p.C + cq * 4;
@@ -240,10 +252,10 @@ extern "C" int dlb_channel_sum(const float* x, long long rows, int C, float* out
 extern "C" int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const float* scale, const float* shift,
                             const float* mean, const float* rstd, int act, int act2, int N, int HW, int C, int pooled,
                             float* c1, float* c2, float* dgamma, float* dbeta, int accumulate_param_grads,
-                            float* dy_f32, void* dy_hi, void* dy_lo, int fmt, void* workspace, size_t workspace_bytes,
-                            dlb_stream_t stream) {
+                            float* dy_f32, void* dy_hi, void* dy_lo, int fmt, float drop_p, unsigned long long drop_seed,
+                            void* workspace, size_t workspace_bytes, dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_bwd: C % 4 != 0");
-  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C, act2};
+  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C, act2, drop_p, drop_seed};
   if (scale != nullptr) {
     const int c4n = C / 4;
     if ((c4n < 256 && 256 % c4n != 0) || (c4n > 256 && c4n % 256 != 0)) return set_error("dlb_norm_bwd: C/4 must divide 256");

@@ -163,9 +163,10 @@ class _EngineBase:
         return ops.norm_stats(y, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats)
 
     def _apply(self, y, scale, shift, act, *, residual=None, want_f32=False, want_split=True, pad=0,
-               pad_mode=PAD_ZERO):
+               pad_mode=PAD_ZERO, drop=None):
+        dp, dseed = drop if drop is not None else (0.0, 0)
         f32, hi, lo = ops.norm_apply(y, scale, shift, act, residual, want_f32, want_split, self.prec.fmt, pad,
-                                     pad_mode, need_lo=self.prec.split)
+                                     pad_mode, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
         return Act(f32, hi, lo, pad)
 
     def _conv(self, layer, act, N, H, W):

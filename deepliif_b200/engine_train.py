@@ -6,8 +6,8 @@ kernels).  Per recorded layer  y = conv(x);  a = act(norm(y)) [+ residual]:
                dW        ConvLayer.wgrad   (tcgen05, K over pixels)   [+ bias grad = ops.channel_sum]
                dx        ConvLayer.dgrad   (conv_tc with the weight in the opposite role)
 
-Scope of round 1: ResnetGenerator with zero padding and no dropout (BASELINE config 4: `--norm instance|batch
---no-dropout --padding zero`) and NLayerDiscriminator.  Gradients are returned keyed by the reference's state_dict
+Scope: ResnetGenerator (zero padding), UnetGenerator, NLayerDiscriminator; nn.Dropout(0.5) with the counter-based mask
+of csrc/rng.cuh (regenerated in backward from (seed, element index)).  Gradients are returned keyed by the reference's state_dict
 names so the nn.Module containers can store them in ``param.grad``."""
 import torch
 
@@ -40,13 +40,20 @@ def _pad_lanes64(w, transposed=False):
 class _TrainOps:
     """Shared tape helpers (mixed into the engines below)."""
 
+    @staticmethod
+    def _new_seed():
+        """Dropout seed for one layer invocation, drawn from torch's CPU generator (reproducible under --seed)."""
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
     def _fwd(self, tape, layer, np_, srcs, N, H, W, pad, act, wkey, nkey, *, residual=None, want_f32=False,
-             want_split=True, out_pad=0):
+             want_split=True, out_pad=0, drop=None):
         y, ws = layer.run_tc(srcs, N, H, W, pad)
         sc, sh, mean, rstd = self._stats(y, np_, ws, want_stats=True)
-        a = self._apply(y, sc, sh, act, residual=residual, want_f32=want_f32, want_split=want_split, pad=out_pad)
-        tape.append(_Rec(layer=layer, x=srcs[0], dims=(N, H, W), pad=pad, y=y, sc=sc, sh=sh, mean=mean, rstd=rstd, act=act,
-                         np=np_, wkey=wkey, nkey=nkey))
+        a = self._apply(y, sc, sh, act, residual=residual, want_f32=want_f32, want_split=want_split, pad=out_pad, drop=drop)
+        rec = _Rec(layer=layer, x=srcs[0], dims=(N, H, W), pad=pad, y=y, sc=sc, sh=sh, mean=mean, rstd=rstd, act=act,
+                   np=np_, wkey=wkey, nkey=nkey)
+        rec.extra = drop
+        tape.append(rec)
         return a, y
 
     def _bwd(self, rec, grads, dout, dout2=None, need_dx=True):
@@ -56,9 +63,10 @@ class _TrainOps:
         if rec.np is not None and rec.np.gamma is not None:
             dg = torch.empty_like(rec.np.gamma); db = torch.empty_like(rec.np.gamma)
         need_f32 = layer.bias is not None
+        dp, dseed = rec.extra if rec.extra is not None else (0.0, 0)
         f32, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, dout2=dout2,
                                    pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=need_f32, want_split=True,
-                                   fmt=self.prec.fmt, need_lo=self.prec.split)
+                                   fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
         if dg is not None:
             grads[rec.nkey + ".weight"], grads[rec.nkey + ".bias"] = dg, db
         grads[rec.wkey + ".weight"] = layer.wgrad(rec.x, hi, lo, N, H, W, rec.pad)
@@ -71,8 +79,7 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
     def __init__(self, sd, **kw):
         if kw.get("padding_type", "zero") != "zero":
             raise NotImplementedError("training path: zero padding only (reflect-pad backward is not built yet)")
-        if kw.get("use_dropout", False):
-            raise NotImplementedError("training path: --no-dropout only (Philox dropout is not built yet)")
+        self.use_dropout = bool(kw.get("use_dropout", False))
         kw.setdefault("backend", "tc")
         super().__init__(sd, **kw)
         if not (self.stem_tc and self.head_tc):
@@ -91,7 +98,9 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
         for _ in range(2):
             down.append((f"model.{idx}", f"model.{idx + 1}")); idx += 3
         blocks = []
-        c1, n1, c2, n2 = 0, 1, 3, 4      # zero padding, no dropout (networks.py:479-506)
+        c1, n1 = 0, 1                    # zero padding; the Dropout module shifts the second conv by one (networks.py:479-506)
+        c2 = 4 if self.use_dropout else 3
+        n2 = c2 + 1
         for _ in range(self.n_blocks):
             pre = f"model.{idx}.conv_block"
             blocks.append(((f"{pre}.{c1}", f"{pre}.{n1}"), (f"{pre}.{c2}", f"{pre}.{n2}"))); idx += 1
@@ -115,7 +124,8 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
             h, w = h // 2, w // 2
         for b, (cv1, nm1, cv2, nm2) in enumerate(self.blocks):
             (k1, kn1), (k2, kn2) = K["blocks"][b]
-            t, _ = self._fwd(tape, cv1, nm1, [a], N, h, w, None, ACT_RELU, k1, kn1)
+            t, _ = self._fwd(tape, cv1, nm1, [a], N, h, w, None, ACT_RELU, k1, kn1,
+                             drop=(0.5, self._new_seed()) if self.use_dropout else None)
             a, _ = self._fwd(tape, cv2, nm2, [t], N, h, w, None, ACT_NONE, k2, kn2, residual=a.f32, want_f32=True)
         for i in range(2):
             last = i == 1
@@ -238,8 +248,8 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
     source from the matching weight rows."""
 
     def __init__(self, sd, *, num_downs=9, norm="batch", norm_mode="batch", precision="bf16x3", device="cuda", use_dropout=False):
-        if use_dropout:
-            raise NotImplementedError("training path: --no-dropout only (Philox dropout is not built yet)")
+        # Dropout(0.5) closes the num_downs-5 inner ngf*8 blocks (networks.py:536, 604-605): levels 4 .. num_downs-2
+        self.drop_levels = set(range(4, num_downs - 1)) if use_dropout else set()
         _EngineBase.__init__(self, norm, norm_mode, Precision.parse(precision) if isinstance(precision, str) else precision,
                              "tc", device)
         self.nd = num_downs
@@ -305,7 +315,7 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
             h, w = h // 2, w // 2
             d_raw.append(y)
             d_stats.append(self._stats(y, self.down_norm[lvl], ws, want_stats=True))
-        u_src, u_raw, u_stats = [None] * L, [None] * L, [None] * L
+        u_src, u_raw, u_stats, u_drop = [None] * L, [None] * L, [None] * L, [None] * L
         below = None
         for lvl in range(L - 1, -1, -1):
             hh, ww = dims[lvl][0] // 2, dims[lvl][1] // 2            # spatial extent of d_lvl = input of the up conv
@@ -320,9 +330,11 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
                 out = ops.head_finish(z32, self.out_bias, 2 * ww, 1, self.out_nc, ACT_TANH)
             else:
                 u_stats[lvl] = self._stats(y, self.up_norm[lvl], ws, want_stats=True)
-                below = self._apply(y, u_stats[lvl][0], u_stats[lvl][1], ACT_RELU)
+                u_drop[lvl] = (0.5, self._new_seed()) if lvl in self.drop_levels else None
+                # relu(dropout(norm(y))) == dropout(relu(norm(y))): the mask multiplier is non-negative
+                below = self._apply(y, u_stats[lvl][0], u_stats[lvl][1], ACT_RELU, drop=u_drop[lvl])
         return out, dict(N=N, H=H, W=W, dims=dims, d_in=d_in, d_raw=d_raw, d_stats=d_stats, u_src=u_src, u_raw=u_raw,
-                         u_stats=u_stats, out=out)
+                         u_stats=u_stats, u_drop=u_drop, out=out)
 
     # ---- backward --------------------------------------------------------------------------------------------------
     def _up_backward(self, lvl, ctx, grads, dy_hi, dy_lo, N, hh, ww):
@@ -360,9 +372,10 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
             if np_ is not None and np_.gamma is not None:
                 dg, db = torch.empty_like(np_.gamma), torch.empty_like(np_.gamma)
             has_bias = self.up_b[lvl] is not None
+            dp, dseed = ctx["u_drop"][lvl] if ctx["u_drop"][lvl] is not None else (0.0, 0)
             f32, hi, lo = ops.norm_bwd(g_below[lvl], ctx["u_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
                                        dgamma=dg, dbeta=db, want_f32=has_bias, want_split=True, fmt=self.prec.fmt,
-                                       need_lo=self.prec.split)
+                                       need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
             if dg is not None:
                 grads[self.unkey[lvl] + ".weight"], grads[self.unkey[lvl] + ".bias"] = dg, db
             if has_bias:

@@ -150,7 +150,8 @@ def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=Fals
 
 
 def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE, dout2=None, act2=None, pooled=False,
-             dgamma=None, dbeta=None, accumulate=False, want_f32=False, want_split=True, fmt=FMT_BF16, need_lo=True):
+             dgamma=None, dbeta=None, accumulate=False, want_f32=False, want_split=True, fmt=FMT_BF16, need_lo=True,
+             drop_p=0.0, drop_seed=0):
     """Backward of norm(+affine)+activation: returns (dy_f32 | None, dy_hi | None, dy_lo | None); writes the
     parameter gradients into dgamma/dbeta (fp32 [C]) when given.  scale=None: layer without norm."""
     _need_cuda(dout, dout2, y, scale, shift, mean, rstd, dgamma, dbeta)
@@ -165,7 +166,7 @@ def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE
     check(_lib.load().dlb_norm_bwd(_p(dout), _p(dout2), _p(y), _p(scale), _p(shift), _p(mean), _p(rstd), act,
                                    act if act2 is None else act2, N, H * W, Cc,
                                    int(pooled), _p(c1), _p(c2), _p(dgamma), _p(dbeta), int(accumulate), _p(f32), _p(hi),
-                                   _p(lo), fmt, _p(ws), ws.numel() * 4, _stream()), "dlb_norm_bwd")
+                                   _p(lo), fmt, float(drop_p), int(drop_seed), _p(ws), ws.numel() * 4, _stream()), "dlb_norm_bwd")
     LAUNCHES["count"] += 3 if scale is not None else 1
     return f32, hi, lo
 
@@ -234,7 +235,7 @@ def head_bwd_pack(dzz_nchw, S, fmt=FMT_BF16, need_lo=True):
 
 
 def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=False, want_split=True,
-               fmt=FMT_BF16, pad=0, pad_mode=PAD_ZERO, need_lo=True):
+               fmt=FMT_BF16, pad=0, pad_mode=PAD_ZERO, need_lo=True, drop_p=0.0, drop_seed=0):
     """out = act(y*scale+shift) (+ residual) -> (out_f32 | None, hi | None, lo | None)."""
     _need_cuda(y, scale, shift, residual)
     N, H, W, Cc = y.shape
@@ -245,7 +246,7 @@ def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=
         hi = torch.empty(shp, dtype=_dtype(fmt), device=y.device)
         lo = torch.empty(shp, dtype=_dtype(fmt), device=y.device) if need_lo else None
     check(_lib.load().dlb_norm_apply(_p(y), _p(scale), _p(shift), act, _p(residual), _p(f32), _p(hi), _p(lo), fmt,
-                                     N, H, W, Cc, pad, pad_mode, _stream()), "dlb_norm_apply")
+                                     N, H, W, Cc, pad, pad_mode, float(drop_p), int(drop_seed), _stream()), "dlb_norm_apply")
     LAUNCHES["count"] += 1
     return f32, hi, lo
 

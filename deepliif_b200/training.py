@@ -12,8 +12,8 @@ What is different underneath:
   * rank 0's initial weights are broadcast (the reference re-initialises after the DDP wrap with per-rank seeds, so
     its replicas start from different weights — SURVEY.md §5; not reproduced);
   * the VGG perceptual term needs downloaded VGG19 weights and is outside the scope (north_star: L1 + GAN).
-Limits: `--padding zero --no-dropout` (reflect-pad backward and Philox dropout are not built); seg generators of the
-cascade must be UNets (`--net-gs unet_*`, the reference default): ResNet generators do not return input gradients yet."""
+Limits: `--padding zero` (reflect-pad backward is not built); dropout masks come from our own counter-based generator,
+not ATen's Philox stream (no implementation can reproduce those); seg generators of the cascade must be UNets (`--net-gs unet_*`, the reference default): ResNet generators do not return input gradients yet."""
 import os
 import time
 

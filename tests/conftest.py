@@ -16,3 +16,11 @@ def pytest_configure(config):
 def lib_built():
     from deepliif_b200 import build
     return build.build_library()
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _bounded_cpu_threads():
+    """The oracle runs small convolutions at N=1: oversubscribing a 128-core GPU host makes them much slower."""
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    yield

@@ -38,7 +38,7 @@ def _write_model_dir(root, net_g="resnet_9blocks", net_gs="unet_512", n_blocks=9
 
 
 def _oracle_cascade(x, sds, net_gs):
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(32, os.cpu_count()))
     cfg = dict(n_blocks=9, norm="batch", use_dropout=True, padding_type="zero", norm_mode="sample")
     with torch.no_grad():
         run_g = lambda t, sd: nets.resnet_forward(t, sd, **cfg)
@@ -99,3 +99,35 @@ def test_cli_test_command_writes_outputs(tmp_path):
     assert "roi_Seg.png" in files and "roi_mod4-Marker.png" in files and "roi.json" in files
     assert Image.open(out / "roi_Seg.png").size == (700, 600)
     assert "num_pos_pixels" in json.load(open(out / "roi.json"))
+
+
+def test_cli_train_then_test_round_trip(tmp_path):
+    """`deepliif train` on a tiny synthetic aligned dataset (default topology: ResNet modality generators, UNet seg
+    generators, dropout on, seg_gen) writes reference-format checkpoints + train_opt.txt that `deepliif test` loads."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from click.testing import CliRunner
+    from deepliif_b200.cli import cli
+    root = tmp_path / "data"
+    (root / "train").mkdir(parents=True)
+    rng = np.random.default_rng(3)
+    for i in range(2):       # row of 6 tiles: IHC | Hema | DAPI | Lap2 | Marker | Seg
+        Image.fromarray((rng.random((128, 6 * 128, 3)) * 255).astype(np.uint8)).save(root / "train" / f"s{i}.png")
+    ck = tmp_path / "ck"
+    r = CliRunner().invoke(cli, ["train", "--dataroot", str(root), "--name", "exp", "--checkpoints-dir", str(ck), "--gpu-ids", "0",
+                                 "--batch-size", "2", "--net-g", "resnet_2blocks", "--net-gs", "unet_128", "--n-epochs", "1",
+                                 "--n-epochs-decay", "0", "--save-epoch-freq", "1", "--print-freq", "1", "--num-threads", "0",
+                                 "--seed", "0"])
+    assert r.exit_code == 0, r.output[-3000:]
+    files = set(os.listdir(ck / "exp"))
+    for k in ["G1", "G4", "GS0", "GS4", "D1", "DS4"]:
+        assert f"latest_net_{k}.pth" in files, files
+    assert "train_opt.txt" in files
+    assert "G_L1_1" in r.output and "D_real_S" in r.output
+    inp, out = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    Image.fromarray((rng.random((200, 300, 3)) * 255).astype(np.uint8)).save(inp / "roi.png")
+    r = CliRunner().invoke(cli, ["test", "--input-dir", str(inp), "--output-dir", str(out), "--tile-size", "128",
+                                 "--model-dir", str(ck / "exp"), "--gpu-ids", "0"])
+    assert r.exit_code == 0, r.output[-3000:]
+    assert Image.open(out / "roi_Seg.png").size == (300, 200)

@@ -44,7 +44,7 @@ def test_resnet_oracle_full_size_subsample():
     cfg = m["cfg"]
     sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 9, cfg["norm"], cfg["use_dropout"], cfg["padding_type"]),
                               m["seed"], m["init"])
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(32, os.cpu_count()))
     with torch.no_grad():
         y = nets.resnet_forward(_x(m), sd, norm_mode="sample", **cfg).numpy()
     assert np.abs(y[:, :, ::8, ::8] - z["y"]).max() <= TOL

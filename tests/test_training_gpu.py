@@ -246,3 +246,52 @@ def test_default_cascade_step_runs_and_matches_oracle_losses(tmp_path):
         print(f"loss {k}: ours {got[k]:.6f} oracle {v:.6f}")
         assert abs(got[k] - v) <= 2e-3 * max(1.0, abs(v)), k
     assert all(torch.isfinite(p_).all() for nm in model.model_names for p_ in model._net(nm).parameters())
+
+
+def dropout_mask_numpy(seed, n, p=0.5):
+    """numpy twin of dlb::dropout_scale (csrc/rng.cuh): multiplier per element index."""
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = idx + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x632BE59BD9B4E019)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = ((z >> np.uint64(32)).astype(np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return np.where(u >= p, np.float32(1.0 / (1.0 - p)), np.float32(0.0))
+
+
+def test_dropout_forward_backward_share_the_mask():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import ops
+    N, H, W, C, seed = 2, 8, 8, 64, 1234567
+    y = _rand((N, H, W, C), 1).cuda()
+    sc, sh, mean, rstd = ops.norm_stats(y, None, None, False, want_stats=True)
+    f32, _, _ = ops.norm_apply(y, sc, sh, ops.ACT_RELU, want_f32=True, want_split=False, drop_p=0.5, drop_seed=seed)
+    base, _, _ = ops.norm_apply(y, sc, sh, ops.ACT_RELU, want_f32=True, want_split=False)
+    m = torch.from_numpy(dropout_mask_numpy(seed, N * H * W * C)).view(N, H, W, C)
+    assert torch.equal(f32.cpu(), base.cpu() * m)
+    assert 0.45 < float((m > 0).float().mean()) < 0.55
+    dout = _rand((N, H, W, C), 2).cuda()
+    g1, _, _ = ops.norm_bwd(dout, y, sc, sh, mean, rstd, ops.ACT_RELU, want_f32=True, want_split=False, drop_p=0.5, drop_seed=seed)
+    g2, _, _ = ops.norm_bwd(dout * m.cuda(), y, sc, sh, mean, rstd, ops.ACT_RELU, want_f32=True, want_split=False)
+    assert (g1 - g2).abs().max().item() < 1e-6
+
+
+def test_resnet_training_with_dropout_runs_and_is_seeded():
+    """use_dropout=True (the reference default, `not opt.no_dropout`): state_dict indices shift by the Dropout module;
+    two forward passes differ unless the torch seed is restored."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import engine_train
+    cfg = dict(n_blocks=2, norm="batch", use_dropout=True, padding_type="zero")
+    sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 2, "batch", True, "zero"), 3, "stress")
+    eng = engine_train.ResnetTrainEngine(sd, norm_mode="batch", precision="bf16x3", **cfg)
+    x = _rand((2, 3, 64, 64), 5).cuda()
+    torch.manual_seed(7); y1, c1 = eng.forward_train(x)
+    y2, _ = eng.forward_train(x)
+    torch.manual_seed(7); y3, c3 = eng.forward_train(x)
+    assert (y1 - y2).abs().max().item() > 1e-3 and torch.equal(y1, y3)
+    g = eng.backward(c1, _rand((2, 3, 64, 64), 6).cuda())
+    expected = {k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    assert set(g) == expected and all(torch.isfinite(v).all() for v in g.values())
