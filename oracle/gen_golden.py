@@ -140,6 +140,30 @@ def main():
     assert np.array_equal(m_ref, pixel.create_posneg_mask(seg, 120)), "posneg restatement differs"
     save("pixel_ends", img=img, transform=t_ref.astype(np.float32), f=f, tensor2im=u8_ref,
          seg=seg, mask=m_ref)
+    # ---- InferenceTiler geometry + is_empty variance (deepliif/util/__init__.py:129-331, 478-485) ------------------
+    from deepliif.util import InferenceTiler, image_variance_gray as ref_var
+    tiler_cases = [(995, 1250, 512, 32), (600, 512, 512, 32), (300, 400, 512, 32), (1100, 1300, 512, 56), (512, 512, 512, 32),
+                   (513, 1025, 256, 16), (2207, 2662, 512, 32)]
+    arrs = {}
+    for ci, (h, w, ts, ov) in enumerate(tiler_cases):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        tiler = InferenceTiler(Image.fromarray(img), ts, ov)
+        origins, n = [], 0
+        for tile in tiler:
+            origins.append((tiler.x, tiler.y))
+            t = np.asarray(tile).astype(np.int32)
+            tiler.stitch({"a": Image.fromarray(((t * 7 + n * 13) % 256).astype(np.uint8))})   # tile-dependent result
+            n += 1
+        res = np.asarray(tiler.results()["a"])
+        arrs[f"c{ci}_cfg"] = np.array([h, w, ts, ov]); arrs[f"c{ci}_img_seed"] = np.array([ci])
+        arrs[f"c{ci}_origins"] = np.array(origins, dtype=np.int32)
+        arrs[f"c{ci}_res_sub"] = res[::23, ::17].copy(); arrs[f"c{ci}_res_sum"] = np.array([int(res.astype(np.int64).sum())])
+        arrs[f"c{ci}_img"] = img[::23, ::17].copy()          # spot check of the regenerated input
+    var_imgs = rng.integers(0, 256, (4, 32, 32, 3), dtype=np.uint8)
+    var_imgs[1] = 200; var_imgs[2] = (var_imgs[2] // 64) + 100
+    arrs["var_imgs"] = var_imgs
+    arrs["var_vals"] = np.array([ref_var(Image.fromarray(v)) for v in var_imgs])
+    save("tiler", **arrs)
     print("all fixtures written to", OUT)
 
 

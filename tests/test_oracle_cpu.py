@@ -121,3 +121,56 @@ def test_no_product_import_of_oracle():
     for path in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
         src = open(path).read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+
+
+def test_tilegrid_matches_reference_tiler_golden():
+    """TileGrid (batched tiles + stitch) against origins / stitched result recorded from the reference's InferenceTiler
+    (util/__init__.py:244-316), incl. ragged sizes, images smaller than a tile, and the last-tile clamp."""
+    from deepliif_b200.util import TileGrid, image_variance_gray
+    z = np.load(os.path.join(GOLD, "tiler.npz"))
+    rng = np.random.default_rng(7)
+    # replay gen_golden's random stream up to the tiler section
+    rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8); rng.random((1, 3, 64, 64), dtype=np.float32)
+    rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8)
+    ci = 0
+    while f"c{ci}_cfg" in z:
+        h, w, ts, ov = [int(v) for v in z[f"c{ci}_cfg"]]
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(img[::23, ::17], z[f"c{ci}_img"])
+        g = TileGrid(img, ts, ov)
+        assert np.array_equal(np.array(g.origins, dtype=np.int32), z[f"c{ci}_origins"])
+        tiles = g.tiles().astype(np.int32)
+        res_tiles = np.stack([((t * 7 + n * 13) % 256).astype(np.uint8) for n, t in enumerate(tiles)])
+        res = g.stitch(res_tiles)
+        assert res.shape[:2] == (h, w)
+        assert np.array_equal(res[::23, ::17], z[f"c{ci}_res_sub"]) and int(res.astype(np.int64).sum()) == int(z[f"c{ci}_res_sum"][0])
+        ci += 1
+    assert ci == 7
+    for im, v in zip(z["var_imgs"], z["var_vals"]):
+        assert abs(image_variance_gray(im) - float(v)) < 1e-6
+
+
+def test_options_round_trip_and_test_mode_defaults(tmp_path):
+    """train_opt.txt written by print_options is re-read in test mode with the reference's back-compat defaults."""
+    from deepliif_b200.options import Options, print_options
+    d = dict(model="DeepLIIF", name="m", checkpoints_dir=str(tmp_path), gpu_ids=(0,), modalities_no=4, seg_gen=True,
+             input_no=1, phase="train", norm="batch", net_g="resnet_9blocks", net_gs="unet_512", padding="zero", no_dropout=False)
+    print_options(Options(d_params=d, mode="train"), save=True)
+    mdir = tmp_path / "m"
+    for k in ["G1", "G2", "G3", "G4", "G51", "G52", "G53", "G54", "G55"]:       # legacy Zenodo naming
+        (mdir / f"latest_net_{k}.pth").write_bytes(b"")
+    opt = Options(path_file=str(mdir / "train_opt.txt"), mode="test")
+    assert opt.mod_id_seg == "5" and opt.input_id == 1
+    assert opt.modalities_names == ["IHC", "Hema", "DAPI", "Lap2", "Marker"] and opt.seg_weights == [0.5, 0, 0, 0, 0.5]
+    assert opt.is_train is False and opt.scale_size == 512 and opt.n_layers_D == 4 and opt.lambda_L1 == 100
+    assert opt.checkpoints_dir == str(tmp_path) and opt.name == "m"
+
+
+def test_unknown_names_raise_like_the_reference():
+    from deepliif_b200.models import networks
+    with pytest.raises(NotImplementedError):
+        networks.define_G(3, 3, 64, "nonsense")
+    with pytest.raises(NotImplementedError):
+        networks.define_D(6, 64, "nonsense")
+    with pytest.raises(NotImplementedError):
+        networks.get_norm_layer("nonsense")
