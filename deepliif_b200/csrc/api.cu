@@ -103,8 +103,8 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     if (stats_ws_bytes < L.total) return set_error("dlb_conv_tc_fwd: statistics workspace too small");
     sp = stats_ptrs(stats_ws, L);
     for (int i = 0; i < np; ++i) {
-      int tw, th, tn;
-      tc_tile_shape(geo[i].OH, geo[i].OW, &tw, &th, &tn);
+      int tw, th, tn, nt;
+      tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt);
       if (tn != 1) return set_error("dlb_conv_tc_fwd: fused statistics need OH*OW >= 128 per phase (use dlb_norm_stats)");
       slice_base[i] = S_total;
       S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw) * 4;

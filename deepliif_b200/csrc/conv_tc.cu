@@ -64,6 +64,11 @@ struct alignas(64) TcParams {
   float* st_cnt;
   int* st_S;
   int st_S_cap, st_slice_base, st_S_total;
+  // "vertical strip" mode (R x 1 filters with small weights: stem / head): the weights of all taps stay resident in
+  // shared memory, one A strip of tile_h + span rows is loaded per tile and channel chunk, and every tap is an MMA on
+  // a 1024-byte-aligned window of that strip (tile_w = 8 pixels = one 8-row swizzle atom per image row).
+  int vs, vs_rows, vs_dh_min;
+  int vs_row_off[kMaxTaps];
 };
 
 struct TileCoord {
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float tr_smem[4][32][33];   // per-epilogue-warp transpose buffer for the fused column statistics
 
@@ -94,7 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
-  const int stage_bytes = p.planes * (kABytes + b_bytes);
+  const int vs_a_bytes = p.vs_rows * p.tile_w * 128;                 // one plane of an A strip (vs mode)
+  const int stage_bytes = p.vs ? p.planes * vs_a_bytes : p.planes * (kABytes + b_bytes);
+  const int kch0 = p.kchunks[0];
+  const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : 0;
+  uint8_t* const stage_base = smem + bres_bytes;                     // resident weights first, then the stage ring
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
 
@@ -108,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (blockIdx.x == 0 && p.st_S != nullptr) *p.st_S = p.st_S_total;
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -123,6 +134,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       // ===================== TMA producer =====================
       int s = 0; uint32_t ph = 0;
+      if (p.vs) {
+        // resident weights: every tap / channel chunk / plane once per CTA
+        mbar_arrive_expect_tx(&bres_bar, static_cast<uint32_t>(bres_bytes));
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int kc = 0; kc < kch0; ++kc) {
+            uint8_t* dst = smem + static_cast<size_t>((tap * kch0 + kc) * p.planes) * b_bytes;
+            tma_load_3d(dst, &p.b_hi, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
+            if (p.planes == 2) tma_load_3d(dst + b_bytes, &p.b_lo, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
+          }
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          for (int kc = 0; kc < kch0; ++kc) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+            uint8_t* st = stage_base + static_cast<size_t>(s) * stage_bytes;
+            const int cw = tc.w0 + p.tap_off[0][1], chh = tc.h0 + p.vs_dh_min;
+            tma_load_5d(st, &p.a_hi[0], &full_bar[s], kc * kKC, cw, chh, tc.n0, 0);
+            if (p.planes == 2) tma_load_5d(st + vs_a_bytes, &p.a_lo[0], &full_bar[s], kc * kKC, cw, chh, tc.n0, 0);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      } else
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -139,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               int c[5];
 #pragma unroll
               for (int i = 0; i < 5; ++i) c[i] = base[i] + (p.dim_sel[i] == 0 ? kc * kKC : 0);
-              uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+              uint8_t* st = stage_base + static_cast<size_t>(s) * stage_bytes;
               tma_load_5d(st, &p.a_hi[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
               if (p.planes == 2) tma_load_5d(st + kABytes, &p.a_lo[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
               const int kw = p.src_koff[src] + kc * kKC;
@@ -158,6 +191,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
+      if (p.vs) {
+        mbar_wait(&bres_bar, 0);                      // resident weights have landed
+        tc_fence_after();
+        const uint32_t bres = smem_u32(smem);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+          uint32_t accumulate = 0;
+          for (int kc = 0; kc < kch0; ++kc) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(stage_base + static_cast<size_t>(s) * stage_bytes);
+            const uint32_t a_lo = a_hi + vs_a_bytes;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const uint32_t aoff = static_cast<uint32_t>(p.vs_row_off[tap]) * p.tile_w * 128u;   // whole image rows
+              const uint32_t b_hi = bres + static_cast<uint32_t>((tap * kch0 + kc) * p.planes) * b_bytes;
+              const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+              for (int k = 0; k < kKC / 16; ++k) {
+                const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + aoff + k * 32);
+                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + aoff + k * 32);
+                  const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
+                  umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                  umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+                } else {
+                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                }
+                accumulate = 1;
+              }
+            }
+            umma_commit(&empty_bar[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1; if (acc == 0) acc_ph ^= 1;
+        }
+      } else
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -166,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[s], ph);                // TMA bytes have landed
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t a_hi = smem_u32(stage_base + static_cast<size_t>(s) * stage_bytes);
           const uint32_t a_lo = a_hi + kABytes;
           const uint32_t b_hi = a_hi + p.planes * kABytes;
           const uint32_t b_lo = b_hi + b_bytes;
@@ -316,14 +390,43 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
 
-// 128 output pixels per CTA tile = tile_n x tile_h x tile_w (shared with api.cu for the statistics slices)
-void tc_tile_shape(int OH, int OW, int* tile_w, int* tile_h, int* tile_n) {
-  int tw = OW >= 128 ? 128 : pow2_ceil(OW);
-  int th = 128 / tw; { int hp = pow2_ceil(OH); if (th > hp) th = hp; }
+// 128 output pixels per CTA tile = tile_n x tile_h x tile_w (shared with api.cu for the statistics slices).
+// Returns 1 when the phase runs in vertical-strip mode (see TcParams::vs): R x 1 filter, stride 1, one source,
+// all output channels in one N tile, resident weights + two A strips fit in shared memory.
+int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
+                  int* tile_h, int* tile_n, int* n_tile_out) {
+  int n_tile = n_tile_req;
+  if (n_tile == 0) n_tile = cout >= 256 ? 256 : (cout >= 128 ? 128 : (cout > 32 ? 64 : 32));
+  *n_tile_out = n_tile;
+  int tw = g.OW >= 128 ? 128 : pow2_ceil(g.OW);
+  int th = 128 / tw; { int hp = pow2_ceil(g.OH); if (th > hp) th = hp; }
   *tile_w = tw; *tile_h = th; *tile_n = 128 / (tw * th);
+  // ---- vertical-strip eligibility ----
+  if (g.stride != 1 || nsrc != 1 || g.ntaps < 2 || g.ntaps > kMaxTaps || g.OW < 8 || g.OH < 16 || cout > n_tile) return 0;
+  int dh_min = g.tap_dh[0], dh_max = g.tap_dh[0];
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.tap_dw[t] != g.tap_dw[0]) return 0;
+    dh_min = min(dh_min, g.tap_dh[t]); dh_max = max(dh_max, g.tap_dh[t]);
+  }
+  const int planes = split ? 2 : 1;
+  const int kch = cin[0] / kKC;
+  const long long resident = static_cast<long long>(g.ntaps) * kch * planes * n_tile * 128;
+  const long long strip = static_cast<long long>(planes) * (16 + dh_max - dh_min) * 8 * 128;
+  if (resident + 2 * strip + 1024 > kMaxDynSmem) return 0;
+  *tile_w = 8; *tile_h = 16; *tile_n = 1;
+  return 1;
 }
 
 // One phase of a convolution on the tensor cores.  See internal.h for the argument contract.
+static void tc_plan_tiles_novs(const TcPhase& ph, int* tile_w, int* tile_h, int* tile_n, int* n_tile_out) {
+  int n_tile = ph.n_tile;
+  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : (ph.cout > 32 ? 64 : 32));
+  *n_tile_out = n_tile;
+  int tw = ph.OW >= 128 ? 128 : pow2_ceil(ph.OW);
+  int th = 128 / tw; { int hp = pow2_ceil(ph.OH); if (th > hp) th = hp; }
+  *tile_w = tw; *tile_h = th; *tile_n = 128 / (tw * th);
+}
+
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   static int num_sms = 0;
   static bool attr_set = false;
@@ -348,15 +451,15 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   if (ph.cout % 32 != 0) return set_error("conv_tc: Cout % 32 == 0 required");
 
   // ---- tile shape: 128 output pixels = tile_n x tile_h x tile_w ---------------------------------
-  int tile_w, tile_h, tile_n;
-  tc_tile_shape(ph.OH, ph.OW, &tile_w, &tile_h, &tile_n);
+  int tile_w, tile_h, tile_n, n_tile_plan;
+  const int use_vs = ph.no_vs ? (tc_plan_tiles_novs(ph, &tile_w, &tile_h, &tile_n, &n_tile_plan), 0)
+                             : tc_plan_tiles(ph, ph.nsrc, ph.cin, ph.cout, ph.split, ph.n_tile, &tile_w, &tile_h, &tile_n, &n_tile_plan);
   p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n;
   p.tiles_w = (ph.OW + tile_w - 1) / tile_w;
   p.tiles_h = (ph.OH + tile_h - 1) / tile_h;
   p.tiles_n = (ph.N + tile_n - 1) / tile_n;
 
-  int n_tile = ph.n_tile;
-  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : (ph.cout > 32 ? 64 : 32));
+  int n_tile = n_tile_plan;
   if (n_tile != 32 && n_tile != 64 && n_tile != 128 && n_tile != 256) return set_error("conv_tc: n_tile must be 32/64/128/256");
   p.n_tile = n_tile;
   p.tiles_c = (ph.cout + n_tile - 1) / n_tile;
@@ -376,6 +479,13 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 1;
       strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = H * W * C * 2; strides[3] = N * H * W * C * 2;
       box[0] = kKC; box[1] = tile_w; box[2] = tile_h; box[3] = tile_n; box[4] = 1;
+      if (use_vs) {
+        int dmin = ph.tap_dh[0], dmax = ph.tap_dh[0];
+        for (int t = 0; t < ph.ntaps; ++t) { dmin = min(dmin, ph.tap_dh[t]); dmax = max(dmax, ph.tap_dh[t]); }
+        p.vs = 1; p.vs_dh_min = dmin; p.vs_rows = tile_h + dmax - dmin;
+        for (int t = 0; t < ph.ntaps; ++t) p.vs_row_off[t] = ph.tap_dh[t] - dmin;
+        box[2] = p.vs_rows;
+      }
       p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 2; p.dim_sel[3] = 3; p.dim_sel[4] = 4;
     } else {
       if ((W & 1) || (H & 1)) return set_error("conv_tc: stride-2 needs even H and W");
@@ -415,13 +525,14 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   }
 
   const int b_bytes = n_tile * 128;
-  const int stage_bytes = p.planes * (kABytes + b_bytes);
-  int stages = (kMaxDynSmem - 1024) / stage_bytes;
+  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes : 0;
+  const int stage_bytes = use_vs ? p.planes * p.vs_rows * tile_w * 128 : p.planes * (kABytes + b_bytes);
+  int stages = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;
   if (stages < 2) return set_error("conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024;
+  const int smem_bytes = bres_bytes + stages * stage_bytes + 1024;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
       return set_cuda_error("cudaFuncSetAttribute(conv_tc_kernel)");

@@ -40,6 +40,7 @@ struct TcPhase : PhaseGeom {
   int n_tile;                  // 0 = auto
   int max_stages;              // 0 = as many as fit
   int max_ctas;                // 0 = #SMs
+  int no_vs;                   // 1 = never use the vertical-strip mode (A/B testing)
   // fused normalisation statistics (see stats_ws.h); st_partial == nullptr disables
   float2* st_partial;
   float* st_cnt;
@@ -47,7 +48,8 @@ struct TcPhase : PhaseGeom {
   int st_S_cap, st_slice_base, st_S_total;
 };
 
-void tc_tile_shape(int OH, int OW, int* tile_w, int* tile_h, int* tile_n);
+int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
+                  int* tile_h, int* tile_n, int* n_tile_out);
 
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream);
 

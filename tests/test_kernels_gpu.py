@@ -139,6 +139,9 @@ def test_conv_direct(ops, case):
 # ------------------------------------------------------------------------------------------------
 TC_CASES = [
     ("k7x1_64_32_head", 1, 22, 70, [64], 32, (7, 1), 1, 0, False, 0, 32),
+    ("k7x1_64_64_stem_vs", 2, 38, 40, [64], 64, (7, 1), 1, 0, False, 0, 0),
+    ("k3x1_128_64_vs_2chunks", 1, 33, 24, [128], 64, (3, 1), 1, 1, False, 0, 0),
+    ("k5x1_64_32_vs_ragged", 3, 21, 13, [64], 32, (5, 1), 1, 0, False, 0, 32),
     # name, N, H, W, cins, Cout, R, stride, pad, transposed, outpad, n_tile
     ("k3s1_64_64_w16", 1, 8, 16, [64], 64, 3, 1, 1, False, 0, 0),
     ("k1s1_64_64", 2, 8, 16, [64], 64, 1, 1, 0, False, 0, 0),
@@ -200,16 +203,18 @@ def test_conv_tc(ops, case, prec):
 
 @pytest.mark.parametrize("case", [("s1", 2, 16, 16, 64, 64, 3, 1, 1, False, 0), ("s2", 2, 32, 48, 64, 128, 3, 2, 1, False, 0),
                                   ("ct", 2, 16, 16, 128, 64, 3, 2, 1, True, 1), ("ragged", 1, 21, 37, 64, 128, 3, 1, 1, False, 0),
-                                  ("big", 1, 128, 128, 64, 256, 3, 1, 1, False, 0)], ids=lambda c: c[0])
+                                  ("big", 1, 128, 128, 64, 256, 3, 1, 1, False, 0),
+                                  ("vstrip", 2, 38, 24, 64, 64, (7, 1), 1, 0, False, 0)], ids=lambda c: c[0])
 @pytest.mark.parametrize("pooled", [False, True])
 def test_conv_tc_fused_stats(ops, case, pooled):
     """Partial statistics from the conv epilogue + dlb_norm_finalize == statistics of the stored output."""
     name, N, H, W, Cin, Cout, R, st, pad, tr, op = case
+    R, S = (R if isinstance(R, tuple) else (R, R))
     x = _rand((N, Cin, H, W), 31)
-    w = _rand((Cin, Cout, R, R) if tr else (Cout, Cin, R, R), 32, 0.05)
+    w = _rand((Cin, Cout, R, S) if tr else (Cout, Cin, R, S), 32, 0.05)
     b = _rand((Cout,), 33, 0.5)
     gamma = (1 + 0.1 * _rand((Cout,), 34)).cuda(); beta = (0.1 * _rand((Cout,), 35)).cuda()
-    d = ops.conv_desc(N, H, W, [Cin], Cout, R, R, st, pad, tr, op)
+    d = ops.conv_desc(N, H, W, [Cin], Cout, R, S, st, pad, tr, op)
     w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), ops.FMT_BF16, True)
     hi, lo = split16(nhwc(x), torch.bfloat16)
     oh, ow = ops.conv_out_shape(d)
