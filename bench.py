@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent generator chains are spread over")
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
-                    help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU)")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256"],
+                    help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU); "
+                         "unet256 = configs[4] (UNet-256 seg head, single-pass bf16, batch 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-events", action="store_true")
     return ap.parse_args()
@@ -184,6 +185,8 @@ def main():
 
     if args.workload == "train":
         return bench_train(args, rank, world, local, dev, dist)
+    if args.workload == "unet256":
+        return bench_unet256(args, rank, world, local, dev, dist)
     from deepliif_b200 import engine as eng_mod
     from deepliif_b200 import ops
     from deepliif_b200.models import networks
@@ -318,6 +321,85 @@ def main():
             "algorithmic_tflops": value * N_HEADS * RESNET_GFLOP / 1e3,
         }
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_unet256(args, rank, world, local, dev, dist):
+    """BASELINE configs[4]: UNet-256 generator (8 downs), single-pass bf16 operands, batch 64, seg head only,
+    256x256 tiles (bottleneck 1x1).  Exercises the ConvTranspose2d path (4-phase tcgen05 GEMMs, dual-source skip)."""
+    from deepliif_b200 import ops
+    from deepliif_b200.models import networks
+    from deepliif_b200.pipeline import TilePipeline
+    B = 64 if args.batch == 32 else args.batch
+    prec = "bf16" if args.precision == "bf16x3" else args.precision
+    torch.manual_seed(0)
+    net = networks.define_G(3, 3, 64, "unet_256", args.norm, False, "normal", 0.02, [])
+    net.precision = prec
+    net.to(dev).eval()
+    eng = net.engine()
+    pipe = TilePipeline([eng.forward], micro_batch=B, n_streams=1)
+    g = torch.Generator().manual_seed(4321 + rank)
+    xs = [(torch.rand((B, 3, 256, 256), generator=g) * 2 - 1).to(dev) for _ in range(3)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        pipe.forward_device(xs[w % 3])
+    barrier()
+    # The ~90 launches of this small network are launch-bound from Python: replay them from a CUDA graph.
+    graph, static_x = None, xs[0].clone()
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pipe.forward_device(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = pipe.forward_device(static_x)
+    except Exception as e:      # capture is an optimisation only
+        graph = None
+        print("cuda graph capture failed, running eagerly:", repr(e)[:200], file=sys.stderr)
+    launches_per_step = None
+
+    def step(k):
+        if graph is not None:
+            static_x.copy_(xs[k % 3]); graph.replay()
+        else:
+            pipe.forward_device(xs[k % 3])
+
+    for w in range(3):
+        step(w)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    pipe_l0 = l0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    if graph is not None:       # launches replayed by the graph are not seen by the Python counter: count one eager pass
+        c0 = ops.LAUNCHES["count"]; pipe.forward_device(xs[0]); torch.cuda.synchronize()
+        ops.LAUNCHES["count"] = l0 + (ops.LAUNCHES["count"] - c0) * args.steps
+    if rank == 0:
+        v = B * world * args.steps / (t_ms / 1e3)
+        print(json.dumps({"metric": "256x256 tiles/sec (UNet-256 seg head)", "cuda_graph": graph is not None, "value": v, "unit": "tiles/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+                          "config": {"workload": "UNet-256 generator, %s, batch=%d/GPU, seg head only, 256x256" % (prec, B),
+                                     "norm": args.norm}, "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
+                          "algorithmic_tflops": v * 12.10 / 1e3}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -76,3 +76,15 @@ def test_discriminator_512_basic(engine_mod):
     err = (y - y_orc).abs().max().item()
     print(f"D basic 512: max|d| vs oracle {err:.3e} (|y| max {y_orc.abs().max():.2f})")
     assert err <= 1e-3 * max(1.0, y_orc.abs().max().item())
+
+
+def test_unet256_single_pass_bf16_tolerance(engine_mod):
+    """BASELINE configs[4] precision: single-pass bf16 operands.  Not an fp32-parity mode: operand rounding alone gives
+    ~1e-2 (SURVEY.md 8d measured 9e-3 by emulation on UNet-512); the stated tolerance for this mode is 5e-2 max-abs."""
+    z, m = _load("unet256_batch_256")
+    sd = nets.make_state_dict(nets.unet_param_shapes(8, 64, 3, 3, "batch"), m["seed"], m["init"])
+    x = _x(m)
+    y = engine_mod.UnetEngine(sd, num_downs=8, norm="batch", precision="bf16").forward(x.cuda()).cpu()
+    err = np.abs(y.numpy()[:, :, ::4, ::4] - z["y"]).max()
+    print(f"unet256 single-pass bf16: max|d| vs reference golden {err:.3e}")
+    assert err <= 5e-2
