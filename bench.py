@@ -270,6 +270,10 @@ def main():
     tiles = B * world * args.steps
     value = tiles / (t_ms / 1e3)
     e2e = tiles / (t2_ms / 1e3)
+    if dist is not None:            # all ranks leave the group before rank 0 spends tens of seconds on the CPU baseline
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
 
     if rank == 0:
         peak_tf, peak_hbm, peak_kind = peaks()

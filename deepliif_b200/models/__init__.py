@@ -16,6 +16,7 @@ import torch
 from PIL import Image
 
 from .base_model import BaseModel
+from .. import ops
 from ..options import Options, print_options
 from ..pipeline import TilePipeline
 from ..util import TileGrid, disable_batchnorm_tracking_stats, image_variance_gray
@@ -98,7 +99,9 @@ def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch
     S = opt.mod_id_seg
     keys = list(gens) + ([f"G{S}"] + segs if (segs and not mod_only) else [])
     out = {k: np.zeros((T, ts, ts, 3), np.uint8) for k in keys}
-    live = [i for i in range(T) if image_variance_gray(tiles_u8[i]) >= EMPTY_TILE_VARIANCE]
+    # is_empty(): gray-level variance per tile, computed on the device from the uint8 batch (exact integer sums)
+    var = ops.tile_gray_variance(torch.from_numpy(np.ascontiguousarray(tiles_u8)).cuda())
+    live = [i for i in range(T) if var[i] >= EMPTY_TILE_VARIANCE]
     for i in set(range(T)) - set(live):
         for j, k in enumerate(gens):
             out[k][i] = np.array(opt.background_colors[j], np.uint8)

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "head_finish", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -273,6 +273,18 @@ def head_finish(z, bias, W, S, CO, act=ACT_TANH):
     check(_lib.load().dlb_head_finish(_p(z), _p(bias), N, H, W, S, CO, act, _p(out), _stream()), "dlb_head_finish")
     LAUNCHES["count"] += 1
     return out
+
+
+def tile_gray_variance(img_nhwc):
+    """uint8 [N,H,W,3] on device -> float64 numpy [N]: population variance of the PIL 'L' luma of every tile."""
+    _need_cuda(img_nhwc)
+    N, H, W, _ = img_nhwc.shape
+    sums = torch.empty((N, 2), dtype=torch.int64, device=img_nhwc.device)
+    check(_lib.load().dlb_tile_luma_sums(_p(img_nhwc), N, H, W, _p(sums), _stream()), "dlb_tile_luma_sums")
+    LAUNCHES["count"] += 1
+    s = sums.cpu().numpy().astype("float64")
+    n = float(H * W)
+    return s[:, 1] / n - (s[:, 0] / n) ** 2
 
 
 def u8_to_f32(img_nhwc):

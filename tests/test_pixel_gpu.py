@@ -47,3 +47,11 @@ def test_seg_finish_bit_exact(ops, N, H, W):
         assert np.array_equal(u8.cpu().numpy(), ref_u8)
         for i in range(N):
             assert np.array_equal(mask[i].cpu().numpy(), pixel.create_posneg_mask(ref_u8[i], 120))
+
+
+def test_tile_gray_variance_matches_reference_golden(ops):
+    """is_empty() statistic on the device vs values recorded from the reference's image_variance_gray."""
+    z = np.load(os.path.join(GOLD, "tiler.npz"))
+    v = ops.tile_gray_variance(torch.from_numpy(z["var_imgs"]).cuda())
+    assert np.abs(v - z["var_vals"]).max() < 1e-6
+    assert v[1] == 0.0 and (v[1] < 9) and (v[0] >= 9)      # constant tile is "empty", random tile is not

@@ -1,0 +1,29 @@
+"""Small end-to-end exercise for compute-sanitizer: every kernel family once at tiny sizes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle import nets
+from deepliif_b200 import engine, engine_train, ops
+
+def rnd(shape, seed):
+    g = torch.Generator().manual_seed(seed); return torch.rand(shape, generator=g) * 2 - 1
+
+sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "batch", False, "zero"), 3, "stress")
+x = rnd((1, 3, 64, 64), 1).cuda()
+eng = engine_train.ResnetTrainEngine(sd, n_blocks=1, norm="batch", use_dropout=False, padding_type="zero", norm_mode="batch")
+y, ctx = eng.forward_train(x)
+g = eng.backward(ctx, rnd((1, 3, 64, 64), 2).cuda())
+sdu = nets.make_state_dict(nets.unet_param_shapes(5, 64, 3, 3, "batch"), 4, "stress")
+u = engine_train.UnetTrainEngine(sdu, num_downs=5, norm="batch", norm_mode="batch")
+yu, cu = u.forward_train(rnd((1, 3, 32, 32), 3).cuda())
+gu, dx = u.backward(cu, rnd((1, 3, 32, 32), 4).cuda())
+sdd = nets.make_state_dict(nets.nlayer_d_param_shapes(3, 64, 6, "batch"), 5, "stress")
+d = engine_train.NLayerDTrainEngine(sdd, n_layers=3, norm="batch", norm_mode="batch")
+yd, cd = d.forward_train(rnd((1, 6, 64, 64), 5).cuda())
+gd, dxd = d.backward(cd, rnd(tuple(yd.shape), 6).cuda())
+sdr = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "instance", False, "reflect"), 6, "stress")
+yr = engine.ResnetEngine(sdr, n_blocks=1, norm="instance", padding_type="reflect").forward(x)
+_, u8, mask = ops.seg_finish([yr], [1.0])
+t = ops.u8_to_f32(u8)
+torch.cuda.synchronize()
+print("sanitize run ok", float(y.abs().sum()), float(yu.abs().sum()), float(yd.abs().sum()), int(mask.sum()))
