@@ -131,3 +131,21 @@ def test_cli_train_then_test_round_trip(tmp_path):
                                  "--model-dir", str(ck / "exp"), "--gpu-ids", "0"])
     assert r.exit_code == 0, r.output[-3000:]
     assert Image.open(out / "roi_Seg.png").size == (300, 200)
+
+
+def test_empty_tiles_skip_the_networks(tmp_path):
+    """run_wrapper semantics (models/__init__.py:399-443): a tile whose gray variance is < 9 is not inferred; its
+    modality outputs are the configured background colours and its Seg output is black."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200.models import get_opt, init_nets, run_batch
+    mdir, _ = _write_model_dir(tmp_path)
+    opt = get_opt(mdir)
+    nets_ = init_nets(mdir, True, opt)
+    rng = np.random.default_rng(2)
+    tiles = np.stack([(rng.random((512, 512, 3)) * 255).astype(np.uint8), np.full((512, 512, 3), 201, np.uint8)])
+    res = run_batch(tiles, nets_, opt, opt.seg_weights)
+    for j, k in enumerate(["G1", "G2", "G3", "G4"]):
+        assert (res[k][1] == np.array(opt.background_colors[j], np.uint8)).all()
+        assert res[k][0].std() > 1.0
+    assert (res["GS"][1] == 0).all() and res["GS"][0].std() > 1.0
