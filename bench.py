@@ -440,8 +440,10 @@ def bench_train(args, rank, world, local, dev, dist):
     l0 = ops.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_h0 = time.perf_counter()
     for k in range(args.steps):
         model.set_input(batches[k % 2]); model.optimize_parameters()
+    t_host = time.perf_counter() - t_h0
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -460,7 +462,7 @@ def bench_train(args, rank, world, local, dev, dist):
                           "dtype": "f32 via %s tensor-core operands" % args.precision, "data": "synthetic",
                           "config": {"workload": "training: pix2pix L1+GAN, 5x (ResNet-9blocks G + 70x70 PatchGAN D), "
                                                  "batch=%d/GPU, flat-bucket all-reduce" % B, "norm": "instance",
-                                     "parallelism": "dp%d" % world},
+                                     "parallelism": "dp%d" % world, "host_enqueue_ms_per_step": t_host * 1e3 / args.steps},
                           "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
                           "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")}), flush=True)
     if dist is not None:

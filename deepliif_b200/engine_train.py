@@ -62,7 +62,10 @@ class _TrainOps:
         dg = db = None
         if rec.np is not None and rec.np.gamma is not None:
             dg = torch.empty_like(rec.np.gamma); db = torch.empty_like(rec.np.gamma)
-        need_f32 = layer.bias is not None
+        # A bias in front of a norm layer has an analytically zero gradient (the norm removes per-channel constants;
+        # autograd only produces rounding noise there): it is returned as exact zeros without touching dy again.
+        normed = rec.sc is not None
+        need_f32 = layer.bias is not None and not normed
         dp, dseed = rec.extra if rec.extra is not None else (0.0, 0)
         f32, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, dout2=dout2,
                                    pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=need_f32, want_split=True,
@@ -71,7 +74,7 @@ class _TrainOps:
             grads[rec.nkey + ".weight"], grads[rec.nkey + ".bias"] = dg, db
         grads[rec.wkey + ".weight"] = layer.wgrad(rec.x, hi, lo, N, H, W, rec.pad)
         if layer.bias is not None:
-            grads[rec.wkey + ".bias"] = ops.channel_sum(f32)
+            grads[rec.wkey + ".bias"] = torch.zeros_like(layer.bias) if normed else ops.channel_sum(f32)
         return layer.dgrad(hi, lo, N, H, W, rec.pad) if need_dx else None
 
 
@@ -372,14 +375,15 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
             if np_ is not None and np_.gamma is not None:
                 dg, db = torch.empty_like(np_.gamma), torch.empty_like(np_.gamma)
             has_bias = self.up_b[lvl] is not None
+            normed = sc is not None
             dp, dseed = ctx["u_drop"][lvl] if ctx["u_drop"][lvl] is not None else (0.0, 0)
             f32, hi, lo = ops.norm_bwd(g_below[lvl], ctx["u_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
-                                       dgamma=dg, dbeta=db, want_f32=has_bias, want_split=True, fmt=self.prec.fmt,
-                                       need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
+                                       dgamma=dg, dbeta=db, want_f32=has_bias and not normed, want_split=True,
+                                       fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
             if dg is not None:
                 grads[self.unkey[lvl] + ".weight"], grads[self.unkey[lvl] + ".bias"] = dg, db
             if has_bias:
-                grads[self.ukey[lvl] + ".bias"] = ops.channel_sum(f32)
+                grads[self.ukey[lvl] + ".bias"] = torch.zeros_like(self.up_b[lvl]) if normed else ops.channel_sum(f32)
             dxs = self._up_backward(lvl, ctx, grads, hi, lo, N, hh, ww)
             g_relu[lvl] = dxs[0]
             if lvl < L - 1:
@@ -394,19 +398,21 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
             if np_ is not None and np_.gamma is not None:
                 dg, db = torch.empty_like(np_.gamma), torch.empty_like(np_.gamma)
             layer = self.down[lvl]
+            normed = sc is not None
             has_bias = layer.bias is not None
+            want32 = has_bias and not normed
             if g_lrelu is None:       # innermost: d is consumed only through the skip ReLU
                 f32, hi, lo = ops.norm_bwd(g_relu[lvl], ctx["d_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
-                                           dgamma=dg, dbeta=db, want_f32=has_bias, want_split=True, fmt=self.prec.fmt,
+                                           dgamma=dg, dbeta=db, want_f32=want32, want_split=True, fmt=self.prec.fmt,
                                            need_lo=self.prec.split)
             else:
                 f32, hi, lo = ops.norm_bwd(g_lrelu, ctx["d_raw"][lvl], sc, sh, mean, rstd, ACT_LRELU02, dout2=g_relu[lvl],
-                                           act2=ACT_RELU, pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=has_bias,
+                                           act2=ACT_RELU, pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=want32,
                                            want_split=True, fmt=self.prec.fmt, need_lo=self.prec.split)
             if dg is not None:
                 grads[self.dnkey[lvl] + ".weight"], grads[self.dnkey[lvl] + ".bias"] = dg, db
             if has_bias:
-                grads[self.dkey[lvl] + ".bias"] = ops.channel_sum(f32)
+                grads[self.dkey[lvl] + ".bias"] = torch.zeros_like(layer.bias) if normed else ops.channel_sum(f32)
             dW = layer.wgrad(ctx["d_in"][lvl], hi, lo, N, h, w)
             if lvl == 0:
                 dW = dW[:, : self.in_nc].contiguous()
