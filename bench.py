@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent generator chains are spread over")
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256"],
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade"],
                     help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU); "
                          "unet256 = configs[4] (UNet-256 seg head, single-pass bf16, batch 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -187,6 +187,8 @@ def main():
         return bench_train(args, rank, world, local, dev, dist)
     if args.workload == "unet256":
         return bench_unet256(args, rank, world, local, dev, dist)
+    if args.workload == "cascade":
+        return bench_cascade(args, rank, world, local, dev, dist)
     from deepliif_b200 import engine as eng_mod
     from deepliif_b200 import ops
     from deepliif_b200.models import networks
@@ -325,6 +327,61 @@ def main():
             "algorithmic_tflops": value * N_HEADS * RESNET_GFLOP / 1e3,
         }
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_cascade(args, rank, world, local, dev, dist):
+    """The reference's default `deepliif test` topology: 4 ResNet-9 modality generators + 5 UNet-512 seg generators in
+    cascade (DeepLIIF_model.py:175-203; 1827.8 GFLOP/tile), end to end from pinned-host uint8 tiles to uint8 results."""
+    from deepliif_b200 import ops
+    from deepliif_b200.models import networks
+    from deepliif_b200.pipeline import TilePipeline
+    B = args.batch
+    gens, segs = [], []
+    for i in range(4):
+        torch.manual_seed(i)
+        gens.append(networks.define_G(3, 3, 64, "resnet_9blocks", args.norm, True, "normal", 0.02, [], "zero").to(dev).eval())
+    for i in range(5):
+        torch.manual_seed(10 + i)
+        segs.append(networks.define_G(3, 3, 64, "unet_512", args.norm, True, "normal", 0.02, []).to(dev).eval())
+    pipe = TilePipeline([g.engine().forward for g in gens], [s_.engine().forward for s_ in segs], [0.25, 0.15, 0.25, 0.1, 0.25],
+                        micro_batch=args.micro_batch, n_streams=args.streams)
+    gen = torch.Generator().manual_seed(99 + rank)
+    u8s = [torch.randint(0, 256, (B, HW, HW, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(3)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for w in range(args.warmup):
+        out = pipe.infer_u8(u8s[w % 3], out)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        out = pipe.infer_u8(u8s[k % 3], out)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    if rank == 0:
+        v = B * world * args.steps / (t_ms / 1e3)
+        print(json.dumps({"metric": "512x512 IHC tiles/sec (default cascade: 4 ResNet-9 + 5 UNet-512), end to end", "value": v,
+                          "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 via %s" % args.precision, "data": "synthetic",
+                          "config": {"workload": "inference: DeepLIIF default cascade, batch=%d/GPU, host uint8 in/out" % B,
+                                     "norm": args.norm, "micro_batch": args.micro_batch, "streams": args.streams},
+                          "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
+                          "algorithmic_tflops": v * 1827.8 / 1e3}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -349,11 +349,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // --------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
@@ -367,7 +371,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-bool encode_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
+bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
@@ -386,9 +390,6 @@ bool encode_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const
   return true;
 }
 
-int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
-}  // namespace
 
 // 128 output pixels per CTA tile = tile_n x tile_h x tile_w (shared with api.cu for the statistics slices).
 // Returns 1 when the phase runs in vertical-strip mode (see TcParams::vs): R x 1 filter, stride 1, one source,
@@ -495,16 +496,16 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       box[0] = kKC; box[1] = tile_w; box[2] = 1; box[3] = tile_h; box[4] = tile_n;
       p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 4; p.dim_sel[3] = 2; p.dim_sel[4] = 3;
     }
-    if (!encode_map(&p.a_hi[s], ph.x_hi[s], is_bf16, 5, dims, strides, box)) return -1;
-    if (ph.split && !encode_map(&p.a_lo[s], ph.x_lo[s], is_bf16, 5, dims, strides, box)) return -1;
+    if (!encode_tiled_map(&p.a_hi[s], ph.x_hi[s], is_bf16, 5, dims, strides, box)) return -1;
+    if (ph.split && !encode_tiled_map(&p.a_lo[s], ph.x_lo[s], is_bf16, 5, dims, strides, box)) return -1;
   }
   // ---- weight tensor map: [taps_total][Cout][Cin_total] ---------------------------------------------
   {
     uint64_t dims[3] = {(uint64_t)cin_total, (uint64_t)ph.cout, (uint64_t)ph.w_taps};
     uint64_t strides[2] = {(uint64_t)cin_total * 2, (uint64_t)cin_total * ph.cout * 2};
     uint32_t box[3] = {(uint32_t)kKC, (uint32_t)n_tile, 1};
-    if (!encode_map(&p.b_hi, ph.w_hi, is_bf16, 3, dims, strides, box)) return -1;
-    if (ph.split && !encode_map(&p.b_lo, ph.w_lo, is_bf16, 3, dims, strides, box)) return -1;
+    if (!encode_tiled_map(&p.b_hi, ph.w_hi, is_bf16, 3, dims, strides, box)) return -1;
+    if (ph.split && !encode_tiled_map(&p.b_lo, ph.w_lo, is_bf16, 3, dims, strides, box)) return -1;
   }
   // ---- taps ---------------------------------------------------------------------------------------
   for (int t = 0; t < ph.ntaps; ++t) {

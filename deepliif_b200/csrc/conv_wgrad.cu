@@ -198,28 +198,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 bool encode5(CUtensorMap* map, const void* base, int is_bf16, const uint64_t* dims, const uint64_t* strides,
              const uint32_t* box) {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  cuuint64_t gd[5], gs[4]; cuuint32_t bx[5], es[5];
-  for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-  for (int i = 0; i < 4; ++i) gs[i] = strides[i];
-  const CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
-                        const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof(b), "wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); set_error(b); return false; }
-  return true;
+  return encode_tiled_map(map, base, is_bf16, 5, dims, strides, box);
 }
 
 int pow2c(int v) { int p = 1; while (p < v) p <<= 1; return p; }

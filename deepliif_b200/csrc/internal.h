@@ -48,6 +48,10 @@ struct TcPhase : PhaseGeom {
   int st_S_cap, st_slice_base, st_S_total;
 };
 
+// cuTensorMapEncodeTiled (16-bit elements, 128-byte swizzle, zero OOB fill) through the runtime's driver entry point.
+bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
+
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
                   int* tile_h, int* tile_n, int* n_tile_out);
 
