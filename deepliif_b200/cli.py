@@ -62,6 +62,13 @@ def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids,
         raise click.UsageError("deepliif_b200 has no CPU path: --gpu-ids -1 is not available")
     if not torch.cuda.is_available():
         raise click.UsageError("deepliif_b200 needs a CUDA (sm_100a) device")
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:       # torchrun: one process per GPU, tiles are sharded across ranks, rank 0 stitches and writes
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        gpu_ids = (local,)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(gpu_ids[0] if gpu_ids else 0)
     opt = Options(path_file=os.path.join(model_dir, "train_opt.txt"), mode="test")
     opt.epoch = epoch
@@ -74,6 +81,8 @@ def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids,
             images, scoring = infer_modalities(img, tile_size, model_dir, True, color_dapi, color_marker, opt,
                                                return_seg_intermediate=seg_intermediate, seg_only=seg_only,
                                                mod_only=mod_only, seg_weights=seg_weights)
+            if rank != 0:
+                continue
             stem = filename[: filename.rfind(".")]
             for name, im in images.items():
                 im.save(os.path.join(output_dir, f"{stem}_{name}.png"))

@@ -161,7 +161,27 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
     tiles = grid.tiles()
     if tile_size != opt.scale_size:
         tiles = np.stack([np.asarray(Image.fromarray(t).resize((opt.scale_size, opt.scale_size))) for t in tiles])
-    res = run_batch(tiles, nets, opt, seg_weights, mod_only)
+    # One process per GPU (torchrun): every rank infers tiles rank, rank+W, ... and rank 0 gathers the uint8 results —
+    # tile sharding with no data-path collective (BASELINE config 3).
+    import torch.distributed as dist
+    from .. import sharding
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if world > 1:
+        local = run_batch(sharding.shard(tiles, rank, world), nets, opt, seg_weights, mod_only) if len(tiles[rank::world]) else None
+        keys = sorted(local.keys()) if local is not None else None
+        klist = [keys]
+        dist.broadcast_object_list(klist, src=0)
+        res = {}
+        for k in klist[0]:
+            part = local[k] if local is not None else np.zeros((0,) + tuple(tiles.shape[1:]), np.uint8)
+            full = sharding.gather_to_rank0(torch.from_numpy(np.ascontiguousarray(part)), len(tiles))
+            if rank == 0:
+                res[k] = full
+        if rank != 0:
+            return {}
+    else:
+        res = run_batch(tiles, nets, opt, seg_weights, mod_only)
     results = {}
     for k, v in res.items():
         if tile_size != opt.scale_size:
@@ -213,5 +233,5 @@ def infer_modalities(img, tile_size, model_dir, eager_mode=True, color_dapi=Fals
                        eager_mode=True, color_dapi=color_dapi, color_marker=color_marker, opt=opt,
                        return_seg_intermediate=return_seg_intermediate, seg_only=seg_only, mod_only=mod_only,
                        seg_weights=seg_weights)
-    scoring = posneg_summary(images["Seg"]) if "Seg" in images else None
+    scoring = posneg_summary(images["Seg"]) if "Seg" in images else None      # non-zero ranks of a sharded run get {}
     return images, scoring

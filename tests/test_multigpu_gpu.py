@@ -79,3 +79,45 @@ def test_bench_under_torchrun_two_gpus():
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     print("2-GPU bench:", line["value"], "tiles/s; e2e", line["e2e"]["value"])
     assert line["n_gpus"] == 2 and line["value"] > 0
+
+
+SHARD_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["DLB_ROOT"])
+from click.testing import CliRunner
+from deepliif_b200.cli import cli
+r = CliRunner().invoke(cli, ["test", "--input-dir", os.environ["DLB_IN"], "--output-dir", os.environ["DLB_OUT"], "--tile-size", "512",
+                             "--model-dir", os.environ["DLB_MODEL"]])
+if r.exit_code != 0:
+    print(r.output[-3000:]); sys.exit(1)
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cli_test_tile_sharded_over_two_gpus_equals_one_gpu(tmp_path):
+    """`deepliif test` under torchrun shards the tiles of every image over the ranks; the stitched PNGs must be
+    byte-identical to a single-GPU run (per-sample statistics => tiles are independent)."""
+    import numpy as np
+    from PIL import Image
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_inference_api_gpu import _write_model_dir
+    mdir, _ = _write_model_dir(tmp_path)
+    inp = tmp_path / "in"; inp.mkdir()
+    rng = np.random.default_rng(21)
+    Image.fromarray((rng.random((995, 1250, 3)) * 255).astype(np.uint8)).save(inp / "roi.png")     # 9 tiles
+    script = tmp_path / "w.py"; script.write_text(SHARD_WORKER)
+    env = dict(os.environ, DLB_ROOT=ROOT, DLB_IN=str(inp), DLB_MODEL=mdir)
+    o1, o2 = str(tmp_path / "o1"), str(tmp_path / "o2")
+    r = subprocess.run([sys.executable, str(script)], env=dict(env, DLB_OUT=o1), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29579", str(script)], env=dict(env, DLB_OUT=o2), capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    names = sorted(f for f in os.listdir(o1) if f.endswith(".png"))
+    assert names and names == sorted(f for f in os.listdir(o2) if f.endswith(".png"))
+    for f in names:
+        assert np.array_equal(np.asarray(Image.open(os.path.join(o1, f))), np.asarray(Image.open(os.path.join(o2, f)))), f
