@@ -45,10 +45,14 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent generator chains are spread over")
     ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--trunk-n-tile", type=int, default=0, help="UMMA N of the ResNet-block convs (0 = 256)")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
     ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade"],
                     help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU); "
                          "unet256 = configs[4] (UNet-256 seg head, single-pass bf16, batch 64)")
+    ap.add_argument("--topology", default="flat5", choices=["flat5", "default"],
+                    help="train workload: flat5 = BASELINE configs[3]; default = the reference's default `deepliif train` "
+                         "(4 ResNet-9 + 5 UNet-512 seg cascade, 9 n_layers=4 PatchGANs, BatchNorm, dropout, batch 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-events", action="store_true")
     return ap.parse_args()
@@ -200,6 +204,7 @@ def main():
         torch.manual_seed(i)
         g = networks.define_G(3, 3, 64, "resnet_9blocks", args.norm, args.norm == "batch", "normal", 0.02, [], "zero")
         g.precision = args.precision
+        g.trunk_n_tile = args.trunk_n_tile
         g.to(dev).eval()
         gens.append(g)
     engines = [g.engine() for g in gens]
@@ -471,10 +476,15 @@ def bench_train(args, rank, world, local, dev, dist):
     from deepliif_b200 import ops, training
     from deepliif_b200.cli import TRAIN_DEFAULTS
     from deepliif_b200.models import create_model
-    B = 8 if args.batch == 32 else args.batch
-    p = dict(TRAIN_DEFAULTS, dataroot="/tmp", checkpoints_dir="/tmp/dlb_bench_ckpt", name="bench", gpu_ids=(local,),
-             modalities_no=N_HEADS, seg_gen=False, norm="instance", no_dropout=True, padding="zero", net_g="resnet_9blocks",
-             net_d="basic", batch_size=B, precision=args.precision)
+    default_topo = args.topology == "default"
+    B = (1 if default_topo else 8) if args.batch == 32 else args.batch
+    if default_topo:
+        p = dict(TRAIN_DEFAULTS, dataroot="/tmp", checkpoints_dir="/tmp/dlb_bench_ckpt", name="bench", gpu_ids=(local,),
+                 batch_size=B, precision=args.precision)          # everything else = the CLI defaults
+    else:
+        p = dict(TRAIN_DEFAULTS, dataroot="/tmp", checkpoints_dir="/tmp/dlb_bench_ckpt", name="bench", gpu_ids=(local,),
+                 modalities_no=N_HEADS, seg_gen=False, norm="instance", no_dropout=True, padding="zero", net_g="resnet_9blocks",
+                 net_d="basic", batch_size=B, precision=args.precision)
     opt = training.build_options(p)
     torch.manual_seed(0)
     model = create_model(opt)
@@ -482,7 +492,8 @@ def bench_train(args, rank, world, local, dev, dist):
     model.train()
     g = torch.Generator().manual_seed(100 + rank)
     batches = [{"A": (torch.rand((B, 3, HW, HW), generator=g) * 2 - 1).to(dev),
-                "B": [(torch.rand((B, 3, HW, HW), generator=g) * 2 - 1).to(dev) for _ in range(N_HEADS)], "A_paths": []}
+                "B": [(torch.rand((B, 3, HW, HW), generator=g) * 2 - 1).to(dev) for _ in range(5 if default_topo else N_HEADS)],
+                "A_paths": []}
                for _ in range(2)]
 
     def barrier():
@@ -511,14 +522,19 @@ def bench_train(args, rank, world, local, dev, dist):
     if rank == 0:
         losses = model.get_current_losses()
         # algorithmic FLOPs per tile: G fwd + bwd (2x) for 5 heads, D: 3 fwd + 2 bwd(params) + 1 bwd(data) per head
-        gflop = N_HEADS * (3 * RESNET_GFLOP + (3 + 2 * 2 + 1) * 26.11)
+        gflop = (N_HEADS * (3 * RESNET_GFLOP + (3 + 2 * 2 + 1) * 26.11) if not default_topo else
+                 3 * (4 * RESNET_GFLOP + 5 * 48.44) + 9 * (3 + 2 * 2 + 1) * 21.77)
         v = B * world * args.steps / (t_ms / 1e3)
-        print(json.dumps({"metric": "512x512 training tiles/sec (pix2pix step, 5x ResNet-9 G + PatchGAN D)", "value": v,
+        print(json.dumps({"metric": ("512x512 training tiles/sec (DeepLIIF default step: 4 ResNet-9 + 5 UNet-512 G, 9 PatchGAN D)"
+                                     if default_topo else
+                                     "512x512 training tiles/sec (pix2pix step, 5x ResNet-9 G + PatchGAN D)"), "value": v,
                           "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32 via %s tensor-core operands" % args.precision, "data": "synthetic",
-                          "config": {"workload": "training: pix2pix L1+GAN, 5x (ResNet-9blocks G + 70x70 PatchGAN D), "
-                                                 "batch=%d/GPU, flat-bucket all-reduce" % B, "norm": "instance",
+                          "config": {"workload": ("training: reference default topology (4 ResNet-9 + 5 UNet-512 cascade, 9 PatchGAN "
+                                                  "n_layers=4, BatchNorm, dropout), batch=%d/GPU" % B) if default_topo else
+                                                 ("training: pix2pix L1+GAN, 5x (ResNet-9blocks G + 70x70 PatchGAN D), "
+                                                  "batch=%d/GPU, flat-bucket all-reduce" % B), "norm": opt.norm,
                                      "parallelism": "dp%d" % world, "host_enqueue_ms_per_step": t_host * 1e3 / args.steps},
                           "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
                           "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")}), flush=True)

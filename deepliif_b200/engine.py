@@ -180,7 +180,7 @@ class ResnetEngine(_EngineBase):
     """ResnetGenerator forward (eval semantics: dropout = identity)."""
 
     def __init__(self, sd, *, n_blocks=9, norm="batch", use_dropout=False, padding_type="zero", norm_mode="sample",
-                 precision="bf16x3", backend="tc", device="cuda", n_tile=0):
+                 precision="bf16x3", backend="tc", device="cuda", n_tile=0, trunk_n_tile=0):
         prec = Precision.parse(precision) if isinstance(precision, str) else precision
         super().__init__(norm, norm_mode, prec, backend, device)
         if padding_type not in ("zero", "reflect"):
@@ -214,7 +214,9 @@ class ResnetEngine(_EngineBase):
         self.blocks = []
         for _ in range(n_blocks):
             pre = f"model.{idx}.conv_block"
-            self.blocks.append((mk(f"{pre}.{c1}", pad=1), nrm(f"{pre}.{n1}"), mk(f"{pre}.{c2}", pad=1), nrm(f"{pre}.{n2}")))
+            mkb = lambda k: ConvLayer(g(k + ".weight"), g(k + ".bias"), prec=prec, backend=backend, pad=1,
+                                      n_tile=trunk_n_tile or n_tile)
+            self.blocks.append((mkb(f"{pre}.{c1}"), nrm(f"{pre}.{n1}"), mkb(f"{pre}.{c2}"), nrm(f"{pre}.{n2}")))
             idx += 1
         self.up, self.up_norm = [], []
         for _ in range(2):

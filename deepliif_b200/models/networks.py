@@ -175,6 +175,7 @@ class ResnetGenerator(_EngineBacked):
 
     def _build_engine(self, device):
         return _engine.ResnetEngine(self.state_dict(), device=device, precision=self.precision, backend=self.backend,
+                                    trunk_n_tile=getattr(self, "trunk_n_tile", 0),
                                     norm_mode="batch" if (self.training and self.cfg["norm"] == "batch") else "sample",
                                     **self.cfg)
 
