@@ -43,7 +43,63 @@ def save(name, **arrs):
     print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrs.items()})
 
 
+CELL_CASES = [   # (H, W, seed, resolution, kwargs of compute_final_results)
+    (200, 260, 1, "40x", dict()),
+    (160, 300, 2, "20x", dict(marker_thresh="default", size_thresh_upper=400, large_noise_thresh="default")),
+    (128, 128, 3, "40x", dict(od_thresh_lower=20, od_thresh_upper=330, size_thresh=None)),
+    (96, 140, 4, "10x", dict(seg_thresh=90, noise_thresh=0, size_thresh=3, marker_thresh=100)),
+    (512, 512, 5, "40x", dict(marker_thresh="default")),
+    (64, 64, 6, "40x", dict(no_marker=True)),
+]
+
+
+def cells_fixture():
+    """Cell post-processing fixture: the reference's own numba functions (deepliif/postprocessing.py) on seeded
+    synthetic images; every stage of compute_final_results (:1223-1304) is stored, and the restatement in
+    oracle/cells.py is asserted equal before the file is written."""
+    import_reference()
+    import deepliif.postprocessing as P
+    from . import cells as C
+    arrs = {}
+    for ci, (H, W, seed, res, kw) in enumerate(CELL_CASES):
+        kw = dict(kw)
+        orig, seg, marker = C.synth_case(H, W, seed)
+        marker_in = None if kw.pop("no_marker", False) else marker
+        # stage by stage with the reference functions (body of compute_final_results)
+        lnt = P.calculate_large_noise_thresh(kw.get("large_noise_thresh"), res)
+        use_od = kw.get("od_thresh_lower") is not None or kw.get("od_thresh_upper") is not None
+        m0 = P.create_posneg_mask(seg, kw.get("seg_thresh", 120))
+        m1 = m0.copy(); P.mark_background(m1)
+        mask, cellsinfo, defaults = P.get_cells_info(seg, orig if use_od else marker_in, res, kw.get("noise_thresh", 4),
+                                                     kw.get("seg_thresh", 120), lnt, use_od=use_od)
+        cells = np.array([[c[0], int(c[1]), int(c[2]), c[3], c[4], c[5], c[6]] for c in cellsinfo], dtype=np.int64).reshape(-1, 7)
+        overlay, refined, scoring = P.compute_final_results(orig, seg, marker_in, res, **kw)
+        # the same through the restatement
+        st = {}
+        o2, r2, s2 = C.compute_final_results(orig, seg, marker_in, res, stages=st, **kw)
+        assert np.array_equal(C.mark_background(m0), m1), f"case {ci}: mark_background differs"
+        c2 = np.array([[c[0], int(c[1]), int(c[2]), c[3], c[4], c[5], c[6]] for c in st["cells"]], dtype=np.int64).reshape(-1, 7)
+        assert np.array_equal(c2, cells), f"case {ci}: cell list differs"
+        assert st["defaults"] == {k: int(v) for k, v in defaults.items()}, (ci, st["defaults"], defaults)
+        assert np.array_equal(o2, overlay) and np.array_equal(r2, refined), f"case {ci}: final images differ"
+        assert json.dumps(s2, sort_keys=True) == json.dumps(scoring, sort_keys=True), (ci, s2, scoring)
+        print("cells case", ci, "n_cells", len(cellsinfo), scoring)
+        arrs[f"c{ci}_bg"] = m1
+        arrs[f"c{ci}_cells"] = cells
+        arrs[f"c{ci}_defaults"] = np.array([defaults.get("size_thresh", -1), defaults.get("marker_thresh", -1)], dtype=np.int64)
+        arrs[f"c{ci}_scoring"] = np.frombuffer(json.dumps(scoring, sort_keys=True).encode(), dtype=np.uint8)
+        if H * W <= 200 * 300:
+            arrs[f"c{ci}_overlay"] = overlay; arrs[f"c{ci}_refined"] = refined
+        else:
+            arrs[f"c{ci}_refined_sub"] = refined[::3, ::5].copy()
+            arrs[f"c{ci}_sums"] = np.array([int(overlay.astype(np.int64).sum()), int(refined.astype(np.int64).sum()),
+                                            int((refined.astype(np.int64) * (np.arange(W)[None, :, None] + 1)).sum())])
+    save("cells", **arrs)
+
+
 def main():
+    if "cells" in sys.argv[1:]:
+        return cells_fixture()
     torch.set_num_threads(os.cpu_count())
     N = reference_networks()
     import_reference()
@@ -164,6 +220,7 @@ def main():
     arrs["var_imgs"] = var_imgs
     arrs["var_vals"] = np.array([ref_var(Image.fromarray(v)) for v in var_imgs])
     save("tiler", **arrs)
+    cells_fixture()
     print("all fixtures written to", OUT)
 
 
