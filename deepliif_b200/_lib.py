@@ -47,6 +47,15 @@ SIGNATURES = {
     "dlb_u8_to_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_f32_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_seg_finish": (_i, [_vpp, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dlb_cells_posneg_mask": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "dlb_cells_marker_plane": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dlb_cells_mark_background": (_i, [_vp, _i, _i, _vp, _vp]),
+    "dlb_cells_label_workspace": (_sz, [_i, _i]),
+    "dlb_cells_label": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dlb_cells_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dlb_cells_classify": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "dlb_cells_enlarge": (_i, [_vp, _vp, _i, _i, _vp]),
+    "dlb_cells_final_images": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

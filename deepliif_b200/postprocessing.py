@@ -1,0 +1,296 @@
+"""Cell post-processing of the stitched Seg / Marker images on the GPU — host mirror of the reference's
+deepliif/postprocessing.py for the path `infer_modalities -> postprocess -> compute_final_results`
+(models/__init__.py:582-611, postprocessing.py:1223-1304).  Same function names, arguments, return values and scoring
+keys; the pixel/graph work runs in libdeepliif_b200.so (csrc/cells.cu), the per-cell threshold logic (a few hundred
+cells) stays on the host exactly as the reference has it.  There is no CPU fallback: without the CUDA library these
+functions raise.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .ops import LAUNCHES, _p, _stream
+
+DEFAULT_SEG_THRESH = 120
+DEFAULT_NOISE_THRESH = 4
+LABEL_UNKNOWN, LABEL_POSITIVE, LABEL_NEGATIVE, LABEL_BACKGROUND, LABEL_CELL = 50, 200, 150, 0, 100
+LABEL_BORDER_POS, LABEL_BORDER_NEG = 220, 170
+
+
+def to_array(img, grayscale=False):
+    """postprocessing.py:98-120."""
+    if not isinstance(img, np.ndarray):
+        img = np.asarray(img) if img.mode == "RGB" else np.asarray(img.convert("RGB"))
+    if grayscale and img.ndim == 3:
+        img = img.max(axis=-1)
+    return img
+
+
+def _dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.DeepliifB200Error("deepliif_b200.postprocessing needs a CUDA device (no CPU path exists)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ---- device stages (thin wrappers over the C ABI) ---------------------------------------------------------------
+def create_posneg_mask_gpu(seg_d, thresh):
+    H, W, _ = seg_d.shape
+    mask = torch.empty((H, W), dtype=torch.uint8, device=seg_d.device)
+    check(_lib.load().dlb_cells_posneg_mask(_p(seg_d), H, W, int(thresh), _p(mask), _stream()), "dlb_cells_posneg_mask")
+    LAUNCHES["count"] += 1
+    return mask
+
+
+_OD_LUT = None
+
+
+def od_lut():
+    """create_od_image's LUT (postprocessing.py:125-129) as float64."""
+    global _OD_LUT
+    if _OD_LUT is None:
+        lut = [0.0] + [math.log10(255 / i) for i in range(1, 256)]
+        lut[0] = lut[1]
+        _OD_LUT = np.asarray(lut, dtype=np.float64)
+    return _OD_LUT
+
+
+def marker_plane_gpu(img_d, use_od=False, want_hist=False):
+    """uint8 [H,W,3] -> uint16 [H,W] (max over channels, or optical density) [+ histogram of non-zero values]."""
+    H, W, _ = img_d.shape
+    plane = torch.empty((H, W), dtype=torch.uint16, device=img_d.device)
+    hist = torch.empty(256, dtype=torch.int32, device=img_d.device) if (want_hist and not use_od) else None
+    lut = _dev(od_lut(), img_d.device) if use_od else None
+    check(_lib.load().dlb_cells_marker_plane(_p(img_d), H, W, 1 if use_od else 0, _p(lut), _p(plane), _p(hist), _stream()),
+          "dlb_cells_marker_plane")
+    LAUNCHES["count"] += 1
+    return plane, hist
+
+
+def mark_background_gpu(mask_d, labels_ws=None):
+    H, W = mask_d.shape
+    if labels_ws is None:
+        labels_ws = torch.empty(H * W, dtype=torch.int32, device=mask_d.device)
+    check(_lib.load().dlb_cells_mark_background(_p(mask_d), H, W, _p(labels_ws), _stream()), "dlb_cells_mark_background")
+    LAUNCHES["count"] += 5
+    return mask_d
+
+
+def label_cells_gpu(mask_d, labels=None):
+    """-> (labels int32 [H,W], roots int32 [n], n)."""
+    H, W = mask_d.shape
+    lib = _lib.load()
+    if labels is None:
+        labels = torch.empty(H * W, dtype=torch.int32, device=mask_d.device)
+    cap = ((H + 1) // 2) * ((W + 1) // 2)
+    roots = torch.empty(cap, dtype=torch.int32, device=mask_d.device)
+    n_d = torch.zeros(1, dtype=torch.int32, device=mask_d.device)
+    wsb = lib.dlb_cells_label_workspace(H, W)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=mask_d.device)
+    check(lib.dlb_cells_label(_p(mask_d), H, W, _p(labels), _p(roots), _p(n_d), _p(ws), C.c_size_t(wsb), _stream()),
+          "dlb_cells_label")
+    LAUNCHES["count"] += 8
+    n = int(n_d.item())
+    return labels.view(H, W), roots[:n], n
+
+
+def cell_stats_gpu(mask_d, marker_plane, labels, roots, use_avg=False):
+    H, W = mask_d.shape
+    n = roots.numel()
+    table = torch.empty((n, 8), dtype=torch.int64, device=mask_d.device)
+    check(_lib.load().dlb_cells_stats(_p(mask_d), _p(marker_plane), _p(labels), _p(roots), n, H, W, int(bool(use_avg)),
+                                      _p(table), _stream()), "dlb_cells_stats")
+    LAUNCHES["count"] += 2
+    return table
+
+
+def classify_gpu(labels, roots, cls_d, H, W):
+    out = torch.empty((H, W), dtype=torch.uint8, device=labels.device)
+    check(_lib.load().dlb_cells_classify(_p(labels), _p(roots), _p(cls_d), H, W, _p(out), _stream()), "dlb_cells_classify")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def enlarge_cell_boundaries_gpu(mask_d):
+    H, W = mask_d.shape
+    out = torch.empty_like(mask_d)
+    check(_lib.load().dlb_cells_enlarge(_p(mask_d), _p(out), H, W, _stream()), "dlb_cells_enlarge")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def create_final_images_gpu(orig_d, mask_d):
+    H, W = mask_d.shape
+    overlay = torch.empty_like(orig_d)
+    refined = torch.empty_like(orig_d)
+    check(_lib.load().dlb_cells_final_images(_p(orig_d), _p(mask_d), H, W, _p(overlay), _p(refined), _stream()),
+          "dlb_cells_final_images")
+    LAUNCHES["count"] += 1
+    return overlay, refined
+
+
+# ---- host logic over the cell list (postprocessing.py:365-488, 1125-1133) --------------------------------------
+def _round_div_half_even(num, den):
+    q, r = divmod(int(num), int(den))
+    return q + (1 if (2 * r > den or (2 * r == den and q % 2 == 1)) else 0)
+
+
+def create_kde(values, count, bandwidth=1.0):
+    """postprocessing.py:365-403: Gaussian KDE on `count` bins; float64 sums stored as float32."""
+    c = 1 / math.sqrt(2 * math.pi)
+    step = (float(values.max()) + 1) / count
+    n = values.shape[0]
+    x = (np.arange(count, dtype=np.float64) * step)[:, None]
+    val = (x - values[None, :]) * (1 / bandwidth)
+    total = np.cumsum(np.exp(-(val * val / 2)) * c, axis=1)[:, -1]      # left-to-right sums like the reference loop
+    return (total / (n * bandwidth)).astype(np.float32), step
+
+
+def calculate_default_size_threshold(cell_sizes, resolution="40x"):
+    """postprocessing.py:406-447."""
+    cell_sizes = np.asarray(cell_sizes, dtype=np.int64)
+    if cell_sizes.shape[0] <= 1:
+        return 0
+    kde, step = create_kde(np.sqrt(cell_sizes), 500)
+    interior = (kde[1:-1] < kde[:-2]) & (kde[1:-1] < kde[2:])
+    hits = np.flatnonzero(interior)
+    idx = int(hits[0]) + 1 if hits.size else 1
+    thresh_sqrt = (idx - 1) * step
+    lo, default, hi = {"20x": (3, 4, 6), "10x": (2, 2, 3)}.get(resolution, (4, 7, 10))
+    if thresh_sqrt < lo:
+        thresh_sqrt = lo
+    elif thresh_sqrt > hi:
+        thresh_sqrt = default
+    return int(round(thresh_sqrt * thresh_sqrt))
+
+
+def _percentile_from_hist(hist, q):
+    """np.percentile(values, q) (method 'linear') for uint8 values given as a histogram: same virtual index and
+    the same two-sided lerp numpy uses."""
+    n = int(hist.sum())
+    cum = np.cumsum(hist)
+    vi = n * (q / 100.0) + (1 + (q / 100.0) * (1 - 1 - 1)) - 1
+    prev = int(math.floor(vi))
+    nxt = min(prev + 1, n - 1)
+    prev = max(prev, 0)
+    g = vi - math.floor(vi)
+    a = float(np.searchsorted(cum, prev + 1, side="left"))          # value of the prev-th order statistic (0-based)
+    b = float(np.searchsorted(cum, nxt + 1, side="left"))
+    d = b - a
+    return (a + d * g) if g < 0.5 else (b - d * (1 - g))
+
+
+def calculate_stain_range_from_hist(hist):
+    """postprocessing.py:450-469 on the histogram of the non-zero marker values."""
+    hist = np.asarray(hist, dtype=np.int64).copy()
+    hist[0] = 0
+    if hist.sum() > 0:
+        return (round(_percentile_from_hist(hist, 0.1)), round(_percentile_from_hist(hist, 99.9)))
+    return (0, 0)
+
+
+def calculate_default_marker_threshold_from_hist(hist):
+    """postprocessing.py:472-488."""
+    lo, hi = calculate_stain_range_from_hist(hist)
+    return round((hi - lo) * 0.9) + lo
+
+
+def calculate_large_noise_thresh(large_noise_thresh, resolution):
+    if not (isinstance(large_noise_thresh, str) and large_noise_thresh == "default"):
+        return large_noise_thresh
+    return {"10x": 1000, "20x": 4000}.get(resolution, 16000)
+
+
+# ---- the reference's public functions ----------------------------------------------------------------------------
+class CellState:
+    """What get_cells_info leaves on the device for create_cell_classification (the reference keeps x0,y0 per cell
+    and re-floods; here the label image does that job)."""
+    __slots__ = ("labels", "roots", "kept", "H", "W")
+
+
+def get_cells_info(seg, marker, resolution, noise_thresh, seg_thresh, large_noise_thresh, use_od=False, _state=None):
+    """postprocessing.py:311-362.  Returns (mask uint8 [H,W] with cells = 100, cellsinfo list of 7-tuples, defaults)."""
+    dev = _device()
+    seg_d = _dev(to_array(seg), dev)
+    H, W, _ = seg_d.shape
+    plane = hist = None
+    if marker is not None:
+        plane, hist = marker_plane_gpu(_dev(to_array(marker), dev), use_od=use_od, want_hist=not use_od)
+    mask_d = create_posneg_mask_gpu(seg_d, seg_thresh)
+    labels = torch.empty(H * W, dtype=torch.int32, device=dev)
+    mark_background_gpu(mask_d, labels)
+    labels, roots, n = label_cells_gpu(mask_d, labels)
+    table = cell_stats_gpu(mask_d, plane, labels, roots, use_avg=use_od).cpu().numpy()
+    cells, kept = [], []
+    for i in range(n):
+        cnt, cp, cn, mv, x0, y0, sx, sy = (int(v) for v in table[i])
+        if cnt > noise_thresh and (large_noise_thresh is None or cnt < large_noise_thresh):
+            if use_od:
+                mv = _round_div_half_even(mv, cnt)
+            cells.append((cnt, cp >= cn, mv, x0, y0, _round_div_half_even(sx, cnt), _round_div_half_even(sy, cnt)))
+            kept.append(i)
+    defaults = {"size_thresh": calculate_default_size_threshold([c[0] for c in cells], resolution)}
+    if marker is not None and not use_od:
+        defaults["marker_thresh"] = calculate_default_marker_threshold_from_hist(hist.cpu().numpy())
+    if _state is not None:
+        _state.labels, _state.roots, _state.kept, _state.H, _state.W = labels, roots, kept, H, W
+        return None, cells, defaults
+    mask = torch.where(labels >= 0, torch.full_like(mask_d, LABEL_CELL), mask_d)
+    return mask.cpu().numpy(), cells, defaults
+
+
+def _classes(cells, kept, n, size_thresh, marker_thresh, size_thresh_upper, od_thresh_lower, od_thresh_upper):
+    """The per-cell decisions of create_cell_classification (postprocessing.py:958-980)."""
+    cls = np.zeros(max(n, 1), dtype=np.uint8)
+    num_pos = num_neg = 0
+    for cell, ci in zip(cells, kept):
+        if cell[0] > size_thresh and (size_thresh_upper is None or cell[0] < size_thresh_upper):
+            is_pos = bool(cell[1])
+            if marker_thresh is not None and cell[2] > marker_thresh:
+                is_pos = True
+            if od_thresh_lower is not None and cell[2] < od_thresh_lower:
+                is_pos = False
+            elif od_thresh_upper is not None and cell[2] > od_thresh_upper:
+                is_pos = False
+            cls[ci] = 2 if is_pos else 1
+            num_pos += is_pos
+            num_neg += not is_pos
+    return cls, {"num_total": num_pos + num_neg, "num_pos": num_pos, "num_neg": num_neg}
+
+
+def compute_final_results(orig, seg, marker, resolution, size_thresh="default", marker_thresh=None,
+                          size_thresh_upper=None, seg_thresh=DEFAULT_SEG_THRESH, noise_thresh=DEFAULT_NOISE_THRESH,
+                          large_noise_thresh=None, od_thresh_lower=None, od_thresh_upper=None, return_mask=False):
+    """postprocessing.py:1223-1304 -> (overlay uint8 [H,W,3], refined uint8 [H,W,3], scoring dict)."""
+    large_noise_thresh = calculate_large_noise_thresh(large_noise_thresh, resolution)
+    use_od = od_thresh_lower is not None or od_thresh_upper is not None
+    st = CellState()
+    _, cells, defaults = get_cells_info(seg, orig if use_od else marker, resolution, noise_thresh, seg_thresh,
+                                        large_noise_thresh, use_od=use_od, _state=st)
+    if size_thresh is None:
+        size_thresh = 0
+    elif isinstance(size_thresh, str) and size_thresh == "default":
+        size_thresh = defaults["size_thresh"]
+    if isinstance(marker_thresh, str) and marker_thresh == "default":
+        marker_thresh = defaults["marker_thresh"]
+    cls, counts = _classes(cells, st.kept, st.roots.numel(), size_thresh, marker_thresh, size_thresh_upper,
+                           od_thresh_lower, od_thresh_upper)
+    dev = st.labels.device
+    mask_d = classify_gpu(st.labels, st.roots, _dev(cls, dev), st.H, st.W)
+    mask_d = enlarge_cell_boundaries_gpu(enlarge_cell_boundaries_gpu(mask_d))
+    overlay, refined = create_final_images_gpu(_dev(to_array(orig), dev), mask_d)
+    scoring = {
+        "num_total": counts["num_total"], "num_pos": counts["num_pos"], "num_neg": counts["num_neg"],
+        "percent_pos": round(counts["num_pos"] / counts["num_total"] * 100, 1) if counts["num_pos"] > 0 else 0,
+        "seg_thresh": seg_thresh, "size_thresh": size_thresh, "size_thresh_upper": size_thresh_upper,
+        "marker_thresh": marker_thresh if marker is not None else None,
+    }
+    out = (overlay.cpu().numpy(), refined.cpu().numpy(), scoring)
+    return out + (mask_d.cpu().numpy(), cells) if return_mask else out

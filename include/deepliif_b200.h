@@ -182,6 +182,40 @@ int dlb_f32_to_u8(const float* x_nchw, uint8_t* out_nhwc, int N, int H, int W, d
 int dlb_seg_finish(const float* const* segs, const float* weights, int nseg, int N, int H, int W, int thresh,
                    float* seg_f32_nchw, uint8_t* seg_u8_nhwc, uint8_t* mask, dlb_stream_t stream);
 
+/* ---- cell post-processing on the stitched uint8 images ----------------------------------------
+ * The integer graph work of deepliif/postprocessing.py, each call = one reference function, results bit-exact:
+ *   dlb_cells_posneg_mask      create_posneg_mask (:163-190): seg uint8 [H,W,3] -> mask uint8 [H,W] (50/150/200).
+ *   dlb_cells_marker_plane     mode 0: to_array(marker, grayscale=True) (:98-120) = max over channels, plus the 256-bin
+ *                              histogram of the non-zero values (calculate_stain_range :450-469; hist256 may be NULL);
+ *                              mode 1: create_od_image (:123-138) with the caller's float64 LUT [256]
+ *                              (lut[0] = lut[1] = log10(255), lut[i] = log10(255 / i)).  plane: uint16 [H,W].
+ *   dlb_cells_mark_background  mark_background (:193-232), in place; labels_ws: int32 [H*W] scratch.
+ *   dlb_cells_label            the cell search of compute_cell_mapping (:235-308): 8-connected components of the pixels
+ *                              that are neither BACKGROUND (0) nor CELL (100), numbered in raster order of their first
+ *                              pixel.  labels: int32 [H*W] (component index, -1 elsewhere); roots: int32 [cap] first
+ *                              pixel (y*W+x) per component, cap >= ceil(H/2)*ceil(W/2); n_cells: device int32.
+ *   dlb_cells_stats            per component int64 [n][8] = count, count_pos, count_neg, marker (max, or sum when
+ *                              use_avg), x0, y0, sum_x, sum_y (the host applies the noise filter and the rounding).
+ *   dlb_cells_classify         create_cell_classification (:923-1000): cls uint8 [n] = 0 (left as LABEL_CELL 100),
+ *                              1 (negative), 2 (positive) -> mask_out uint8 [H,W] with 200/150 cells and 220/170 borders.
+ *   dlb_cells_enlarge          one enlarge_cell_boundaries pass (:1003-1030), out of place.
+ *   dlb_cells_final_images     create_final_images (:1033-1071): overlay (copy of orig with coloured borders), refined.
+ * All pointers are device pointers; H*W < 2^31. */
+int dlb_cells_posneg_mask(const uint8_t* seg_hwc, int H, int W, int thresh, uint8_t* mask, dlb_stream_t stream);
+int dlb_cells_marker_plane(const uint8_t* img_hwc, int H, int W, int mode, const double* od_lut, uint16_t* plane,
+                           unsigned int* hist256, dlb_stream_t stream);
+int dlb_cells_mark_background(uint8_t* mask, int H, int W, int* labels_ws, dlb_stream_t stream);
+size_t dlb_cells_label_workspace(int H, int W);
+int dlb_cells_label(const uint8_t* mask, int H, int W, int* labels, int* roots, int* n_cells, void* ws, size_t ws_bytes,
+                    dlb_stream_t stream);
+int dlb_cells_stats(const uint8_t* mask, const uint16_t* marker, const int* labels, const int* roots, int n, int H, int W,
+                    int use_avg, long long* table, dlb_stream_t stream);
+int dlb_cells_classify(const int* labels, const int* roots, const uint8_t* cls, int H, int W, uint8_t* mask_out,
+                       dlb_stream_t stream);
+int dlb_cells_enlarge(const uint8_t* mask_in, uint8_t* mask_out, int H, int W, dlb_stream_t stream);
+int dlb_cells_final_images(const uint8_t* orig_hwc, const uint8_t* mask, int H, int W, uint8_t* overlay_hwc,
+                           uint8_t* refined_hwc, dlb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,9 +298,9 @@ def compute_final_results(orig, seg, marker, resolution, size_thresh="default", 
 def synth_case(H, W, seed, n_cells=None):
     """Seeded synthetic (orig, seg, marker) uint8 images with the features the reference's loops branch on: red and
     blue blobs, rings with enclosed UNKNOWN holes, blobs cut by the image border, abutting cells of both classes,
-    isolated specks below the noise threshold, and green-vetoed pixels."""
+    isolated specks below the noise threshold, and green-vetoed pixels.  Each blob only touches its bounding box, so
+    region-sized cases stay cheap to build."""
     rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:H, 0:W]
     seg = rng.integers(0, 40, size=(H, W, 3), dtype=np.int64)
     marker = rng.integers(0, 30, size=(H, W, 3), dtype=np.int64)
     n_cells = n_cells or max(6, H * W // 900)
@@ -308,21 +308,31 @@ def synth_case(H, W, seed, n_cells=None):
         cy, cx = rng.uniform(-4, H + 4), rng.uniform(-4, W + 4)
         a, b = rng.uniform(2.5, 11), rng.uniform(2.5, 11)
         th = rng.uniform(0, math.pi)
+        ring = rng.random() < 0.25
+        inner = rng.uniform(0.2, 0.5)
+        pos = rng.random() < 0.5
+        mval = int(rng.integers(40, 256))
+        r = int(math.ceil(max(a, b))) + 1
+        y0, y1, x0, x1 = max(0, int(cy) - r), min(H, int(cy) + r + 1), max(0, int(cx) - r), min(W, int(cx) + r + 1)
+        if y0 >= y1 or x0 >= x1:
+            continue
+        yy, xx = np.mgrid[y0:y1, x0:x1]
         u = (xx - cx) * math.cos(th) + (yy - cy) * math.sin(th)
         v = -(xx - cx) * math.sin(th) + (yy - cy) * math.cos(th)
         d = (u / a) ** 2 + (v / b) ** 2
         inside = d <= 1
-        if rng.random() < 0.25:
-            inside &= d >= rng.uniform(0.2, 0.5)                    # ring: encloses an UNKNOWN hole
-        pos = rng.random() < 0.5
-        hi = rng.integers(110, 256, size=(H, W))
-        lo = rng.integers(0, 90, size=(H, W))
-        seg[..., 0] = np.where(inside, hi if pos else lo, seg[..., 0])
-        seg[..., 2] = np.where(inside, lo if pos else hi, seg[..., 2])
-        seg[..., 1] = np.where(inside, rng.integers(0, 95, size=(H, W)), seg[..., 1])   # some G > 80 vetoes
+        if ring:
+            inside &= d >= inner                                       # ring: encloses an UNKNOWN hole
+        shp = inside.shape
+        hi = rng.integers(110, 256, size=shp)
+        lo = rng.integers(0, 90, size=shp)
+        w = seg[y0:y1, x0:x1]
+        w[..., 0] = np.where(inside, hi if pos else lo, w[..., 0])
+        w[..., 2] = np.where(inside, lo if pos else hi, w[..., 2])
+        w[..., 1] = np.where(inside, rng.integers(0, 95, size=shp), w[..., 1])        # some G > 80 vetoes
         if pos:
-            mval = rng.integers(40, 256)
-            marker = np.where(inside[..., None], rng.integers(0, mval + 1, size=(H, W, 3)), marker)
+            mw = marker[y0:y1, x0:x1]
+            mw[...] = np.where(inside[..., None], rng.integers(0, mval + 1, size=shp + (3,)), mw)
     speck = rng.random((H, W)) < 0.004
     seg[..., 0] = np.where(speck, 200, seg[..., 0])
     seg[..., 1] = np.where(speck, 0, seg[..., 1])
