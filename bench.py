@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--trunk-n-tile", type=int, default=0, help="UMMA N of the ResNet-block convs (0 = 256)")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade"],
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade", "postprocess"],
                     help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU); "
                          "unet256 = configs[4] (UNet-256 seg head, single-pass bf16, batch 64)")
     ap.add_argument("--topology", default="flat5", choices=["flat5", "default"],
@@ -193,6 +193,8 @@ def main():
         return bench_unet256(args, rank, world, local, dev, dist)
     if args.workload == "cascade":
         return bench_cascade(args, rank, world, local, dev, dist)
+    if args.workload == "postprocess":
+        return bench_postprocess(args, rank, world, local, dev, dist)
     from deepliif_b200 import engine as eng_mod
     from deepliif_b200 import ops
     from deepliif_b200.models import networks
@@ -387,6 +389,82 @@ def bench_cascade(args, rank, world, local, dev, dist):
                                      "norm": args.norm, "micro_batch": args.micro_batch, "streams": args.streams},
                           "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
                           "algorithmic_tflops": v * 1827.8 / 1e3}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_postprocess(args, rank, world, local, dev, dist):
+    """compute_final_results (postprocessing.py:1223-1304) on one stitched region — create_posneg_mask,
+    mark_background, cell labelling + statistics, classification, boundary growth, overlay / refined images.  Each rank
+    processes its own region (regions are independent: no collective)."""
+    import numpy as np
+    from oracle import cells as C                          # input synthesis + the cpu_baseline leg only
+    from deepliif_b200 import ops
+    from deepliif_b200 import postprocessing as P
+    T, REP = 2048, 4
+    o, s_, m = C.synth_case(T, T, 500 + rank)
+    orig, seg, marker = (np.ascontiguousarray(np.tile(a, (REP, REP, 1))) for a in (o, s_, m))
+    H, W = orig.shape[:2]
+    kw = dict(marker_thresh="default", large_noise_thresh="default")
+    d_in = [torch.from_numpy(a).to(dev) for a in (orig, seg, marker)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    t_dev = timed(lambda: P.compute_final_results_device(d_in[0], d_in[1], d_in[2], "40x", **kw))
+    launches = (ops.LAUNCHES["count"] - l0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop()
+
+    t_e2e = timed(lambda: P.compute_final_results(orig, seg, marker, "40x", **kw))     # the public call: numpy in, numpy out
+    clock = P.StageClock()
+    _, _, scoring, _, cells = P.compute_final_results_device(d_in[0], d_in[1], d_in[2], "40x", clock=clock, **kw)
+    stages = clock.ms()
+    if rank == 0:
+        mp = H * W / 1e6
+        v = mp * world * args.steps / (t_dev / 1e3)
+        pk = peaks()
+        alg_bytes = 15.0 * H * W                           # 3 uint8 images read, 2 written: the floor for this function
+        dev_ms = sum(v_ for k, v_ in stages.items() if k != "host thresholds")
+        line = {"metric": "stitched-region cell post-processing (compute_final_results), Mpixel/s", "value": v, "unit": "Mpixel/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 / int32", "data": "synthetic",
+                "config": {"workload": "postprocess: %dx%d region (%dx%d synthetic tile repeated %dx%d), %d cells, 40x defaults"
+                                       % (H, W, T, T, REP, REP, len(cells)),
+                           "l2": "per-step working set %.0f MB >> 126 MB L2" % (H * W * 25 / 1e6)},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": mp * world * args.steps / (t_e2e / 1e3), "unit": "Mpixel/s", "h2d_bytes_per_step": 9 * H * W,
+                        "d2h_bytes_per_step": 6 * H * W},
+                "stages_ms": stages,
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (dev_ms / 1e3) / 1e9, "peak": pk[1], "unit": "GB/s",
+                             "frac": alg_bytes / (dev_ms / 1e3) / 1e9 / pk[1], "peak_source": pk[2], "traffic": None,
+                             "note": "whole device pipeline (all kernels of the function; host threshold step excluded); "
+                                     "algorithmic bytes = 15 B/pixel"}}
+        if not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            C.compute_final_results(o, s_, m, "40x", **kw)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": T * T / 1e6 / dt, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+                                    "sample": "one %dx%d tile of the region through oracle/cells.py (numpy/scipy)" % (T, T)}
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

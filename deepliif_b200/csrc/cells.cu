@@ -89,11 +89,10 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
   }
 }
 
-__global__ void ccl_compress_kernel(int* __restrict__ L, long long total) {
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+__global__ void ccl_compress_kernel(int* __restrict__ L, unsigned total) {
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     const int v = L[p];
-    if (v >= 0 && v != p) L[p] = find_root(L, v);
+    if (v >= 0 && v != static_cast<int>(p)) L[p] = find_root(L, v);
   }
 }
 
@@ -101,11 +100,10 @@ __global__ void ccl_compress_kernel(int* __restrict__ L, long long total) {
 // Roots of components that touch the border or an existing BACKGROUND pixel are overwritten with -2 (only root
 // entries are ever rewritten, so the non-root entries other threads read stay valid).
 __global__ void flood_flag_kernel(const uint8_t* __restrict__ mask, int* __restrict__ L, int H, int W) {
-  const long long total = static_cast<long long>(H) * W;
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(H) * W;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     if (mask[p] != kUnknown) continue;
-    const int y = static_cast<int>(p / W), x = static_cast<int>(p % W);
+    const int y = static_cast<int>(p / static_cast<unsigned>(W)), x = static_cast<int>(p - static_cast<unsigned>(y) * W);
     bool seed = (y == 0 || x == 0 || y == H - 1 || x == W - 1);
     if (!seed) seed = mask[p - W] == kBackground || mask[p + W] == kBackground || mask[p - 1] == kBackground ||
                       mask[p + 1] == kBackground;
@@ -115,9 +113,8 @@ __global__ void flood_flag_kernel(const uint8_t* __restrict__ mask, int* __restr
   }
 }
 
-__global__ void flood_apply_kernel(uint8_t* __restrict__ mask, const int* __restrict__ L, long long total) {
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+__global__ void flood_apply_kernel(uint8_t* __restrict__ mask, const int* __restrict__ L, unsigned total) {
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     const int v = L[p];
     if (v == -1) continue;
     if (v == -2 || L[v] == -2) mask[p] = kBackground;
@@ -134,9 +131,8 @@ __global__ void root_code_kernel(int* __restrict__ L, const int* __restrict__ ro
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < *n; i += gridDim.x * blockDim.x) L[roots[i]] = -(i + 2);
 }
 
-__global__ void relabel_kernel(int* __restrict__ L, long long total) {          // -> component index, -1 elsewhere
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+__global__ void relabel_kernel(int* __restrict__ L, unsigned total) {          // -> component index, -1 elsewhere
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     const int v = L[p];
     if (v >= 0) L[p] = -(L[v] + 2);            // L[v] is a coded root entry: never rewritten by this kernel's non-roots
   }
@@ -151,16 +147,16 @@ __global__ void relabel_roots_kernel(int* __restrict__ L, const int* __restrict_
 __global__ void __launch_bounds__(256) cell_stats_kernel(const uint8_t* __restrict__ mask, const uint16_t* __restrict__ marker,
                                                          const int* __restrict__ lab, int H, int W, int use_avg,
                                                          unsigned long long* __restrict__ table) {
-  const long long total = static_cast<long long>(H) * W;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < total; base += stride) {
-    const long long p = base + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(H) * W;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned base = blockIdx.x * blockDim.x; base < total; base += stride) {
+    const unsigned p = base + threadIdx.x;
     const int c = p < total ? lab[p] : -1;
     const unsigned active = __ballot_sync(0xffffffffu, c >= 0);
     if (c < 0) continue;
     const unsigned peers = __match_any_sync(active, c);
     const uint8_t v = mask[p];
-    const unsigned x = static_cast<unsigned>(p % W), y = static_cast<unsigned>(p / W);
+    const unsigned y = p / static_cast<unsigned>(W), x = p - y * W;
     const unsigned mv = marker ? marker[p] : 0u;
     const unsigned cnt = __popc(peers);
     const unsigned pos = __reduce_add_sync(peers, v == kPositive ? 1u : 0u);
@@ -191,22 +187,21 @@ __global__ void cell_first_kernel(const int* __restrict__ roots, int n, int W, u
 // cls[c]: 0 = cell not counted (stays LABEL_CELL), 1 = negative, 2 = positive.
 __global__ void classify_kernel(const int* __restrict__ lab, const int* __restrict__ roots, const uint8_t* __restrict__ cls,
                                 int H, int W, uint8_t* __restrict__ out) {
-  const long long total = static_cast<long long>(H) * W;
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(H) * W;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     const int c = lab[p];
     if (c >= 0) {
       const uint8_t k = cls[c];
       if (k == 0) out[p] = kCell;
-      else if (roots[c] == p) out[p] = (k == 2) ? kBorderPos : kBorderNeg;     // the flood's start pixel keeps the border label
+      else if (roots[c] == static_cast<int>(p)) out[p] = (k == 2) ? kBorderPos : kBorderNeg;     // the flood's start pixel keeps the border label
       else out[p] = (k == 2) ? kPositive : kNegative;
       continue;
     }
-    const int y = static_cast<int>(p / W), x = static_cast<int>(p % W);
+    const int y = static_cast<int>(p / static_cast<unsigned>(W)), x = static_cast<int>(p - static_cast<unsigned>(y) * W);
     int best = 0x7fffffff;
-    auto look = [&](long long q) {
+    auto look = [&](unsigned q) {
       const int cq = lab[q];
-      if (cq >= 0 && cq < best && cls[cq] != 0 && roots[cq] != q) best = cq;
+      if (cq >= 0 && cq < best && cls[cq] != 0 && roots[cq] != static_cast<int>(q)) best = cq;
     };
     if (y > 0) look(p - W);
     if (y + 1 < H) look(p + W);
@@ -217,12 +212,11 @@ __global__ void classify_kernel(const int* __restrict__ lab, const int* __restri
 }
 
 __global__ void enlarge_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W) {
-  const long long total = static_cast<long long>(H) * W;
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(H) * W;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     uint8_t v = in[p];
     if (v == kBackground) {
-      const int y = static_cast<int>(p / W), x = static_cast<int>(p % W);
+      const int y = static_cast<int>(p / static_cast<unsigned>(W)), x = static_cast<int>(p - static_cast<unsigned>(y) * W);
       bool found = false;
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy)
@@ -231,7 +225,7 @@ __global__ void enlarge_kernel(const uint8_t* __restrict__ in, uint8_t* __restri
           if ((dy == 0 && dx == 0) || found) continue;
           const int yy = y + dy, xx = x + dx;
           if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          const uint8_t nb = in[static_cast<long long>(yy) * W + xx];
+          const uint8_t nb = in[static_cast<unsigned>(yy) * W + xx];
           if (nb == kBorderPos || nb == kBorderNeg) { v = nb; found = true; }
         }
     }
@@ -239,25 +233,43 @@ __global__ void enlarge_kernel(const uint8_t* __restrict__ in, uint8_t* __restri
   }
 }
 
-__global__ void final_images_kernel(const uint8_t* __restrict__ orig, const uint8_t* __restrict__ mask, long long total,
+__device__ __forceinline__ void final_pixel(uint8_t m, uint8_t* o, uint8_t* r) {
+  r[0] = r[1] = r[2] = 0;
+  if (m == kBorderPos) { o[0] = 255; o[1] = 0; o[2] = 0; r[1] = 255; }
+  else if (m == kBorderNeg) { o[0] = 0; o[1] = 0; o[2] = 255; r[1] = 255; }
+  else if (m == kPositive) r[0] = 255;
+  else if (m == kNegative) r[2] = 255;
+}
+
+// 4 pixels per thread: one 32-bit mask word, three 32-bit words of each RGB image (all buffers 4-byte aligned).
+__global__ void final_images_kernel(const uint8_t* __restrict__ orig, const uint8_t* __restrict__ mask, unsigned total,
                                     uint8_t* __restrict__ overlay, uint8_t* __restrict__ refined) {
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint8_t m = mask[p];
-    uint8_t o0 = orig[p * 3], o1 = orig[p * 3 + 1], o2 = orig[p * 3 + 2], r0 = 0, r1 = 0, r2 = 0;
-    if (m == kBorderPos) { o0 = 255; o1 = 0; o2 = 0; r1 = 255; }
-    else if (m == kBorderNeg) { o0 = 0; o1 = 0; o2 = 255; r1 = 255; }
-    else if (m == kPositive) r0 = 255;
-    else if (m == kNegative) r2 = 255;
-    overlay[p * 3] = o0; overlay[p * 3 + 1] = o1; overlay[p * 3 + 2] = o2;
-    refined[p * 3] = r0; refined[p * 3 + 1] = r1; refined[p * 3 + 2] = r2;
+  const unsigned quads = total / 4;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+    union { uint32_t w; uint8_t b[4]; } m;
+    union { uint32_t w[3]; uint8_t b[12]; } o, r;
+    m.w = reinterpret_cast<const uint32_t*>(mask)[q];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(orig) + static_cast<size_t>(q) * 3;
+    o.w[0] = src[0]; o.w[1] = src[1]; o.w[2] = src[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) final_pixel(m.b[k], o.b + 3 * k, r.b + 3 * k);
+    uint32_t* po = reinterpret_cast<uint32_t*>(overlay) + static_cast<size_t>(q) * 3;
+    uint32_t* pr = reinterpret_cast<uint32_t*>(refined) + static_cast<size_t>(q) * 3;
+    po[0] = o.w[0]; po[1] = o.w[1]; po[2] = o.w[2];
+    pr[0] = r.w[0]; pr[1] = r.w[1]; pr[2] = r.w[2];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < total % 4) {                       // tail pixels
+    const size_t p = static_cast<size_t>(quads) * 4 + threadIdx.x;
+    uint8_t o[3] = {orig[p * 3], orig[p * 3 + 1], orig[p * 3 + 2]}, r[3];
+    final_pixel(mask[p], o, r);
+    for (int c = 0; c < 3; ++c) { overlay[p * 3 + c] = o[c]; refined[p * 3 + c] = r[c]; }
   }
 }
 
-__global__ void posneg_mask_kernel(const uint8_t* __restrict__ seg, long long total, int thresh, uint8_t* __restrict__ mask) {
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = seg[p * 3], g = seg[p * 3 + 1], b = seg[p * 3 + 2];
+__global__ void posneg_mask_kernel(const uint8_t* __restrict__ seg, unsigned total, int thresh, uint8_t* __restrict__ mask) {
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    const size_t o = static_cast<size_t>(p) * 3;
+    const int r = seg[o], g = seg[o + 1], b = seg[o + 2];
     uint8_t m = kUnknown;
     if (r + b > thresh && g <= 80) m = (r >= b) ? kPositive : kNegative;
     mask[p] = m;
@@ -266,14 +278,14 @@ __global__ void posneg_mask_kernel(const uint8_t* __restrict__ seg, long long to
 
 // mode 0: max over the channels (+ histogram of the non-zero values); mode 1: optical density, the reference's
 // round(100 * (lut[r] + lut[g] + lut[b])) with the caller's 256-entry float64 LUT (left-to-right adds, ties to even).
-__global__ void __launch_bounds__(256) marker_plane_kernel(const uint8_t* __restrict__ img, long long total, int mode,
+__global__ void __launch_bounds__(256) marker_plane_kernel(const uint8_t* __restrict__ img, unsigned total, int mode,
                                                            const double* __restrict__ lut, uint16_t* __restrict__ out,
                                                            unsigned int* __restrict__ hist) {
   __shared__ unsigned int sh[256];
   if (hist) { sh[threadIdx.x] = 0; __syncthreads(); }
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = img[p * 3], g = img[p * 3 + 1], b = img[p * 3 + 2];
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    const size_t o = static_cast<size_t>(p) * 3;
+    const int r = img[o], g = img[o + 1], b = img[o + 2];
     if (mode == 0) {
       const int v = max(r, max(g, b));
       out[p] = static_cast<uint16_t>(v);

@@ -5,8 +5,9 @@ What changes underneath: the reference runs one tile at a time (batch 1, PIL <->
 threads across nets, nets spread over GPUs).  Here all tiles of an image form one uint8 batch that goes through
 ``TilePipeline`` (H2D once, on-GPU transform, all generators on the sm_100a kernels in micro-batches, on-GPU
 quantisation, D2H of uint8 results); several GPUs shard tiles, not networks (deepliif_b200/sharding.py).
-Out of scope: TorchScript (.pt) loading, TorchServe, Dask, WSI readers, numba cell post-processing —
-``infer_modalities`` returns the on-device posneg mask statistics instead of the cell-level scoring dict."""
+``infer_modalities`` ends, as in the reference, with ``postprocess`` (cell-level scoring, SegOverlaid, SegRefined), whose
+pixel/graph work runs on the GPU (deepliif_b200/postprocessing.py).
+Out of scope: TorchScript (.pt) loading, TorchServe, Dask, WSI readers."""
 import importlib
 import os
 from functools import lru_cache
@@ -212,15 +213,27 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
     return images
 
 
-def posneg_summary(seg_img, thresh=120):
-    """Pixel-level summary of create_posneg_mask on the stitched Seg image (the cell-level numba post-processing
-    of the reference, postprocessing.py:1223-1304, is out of scope)."""
-    a = np.asarray(seg_img).astype(np.int64)
-    hit = (a[..., 0] + a[..., 2] > thresh) & (a[..., 1] <= 80)
-    pos = int((hit & (a[..., 0] >= a[..., 2])).sum())
-    neg = int((hit & (a[..., 0] < a[..., 2])).sum())
-    return {"num_pos_pixels": pos, "num_neg_pixels": neg,
-            "percent_pos_pixels": round(100.0 * pos / (pos + neg), 1) if pos + neg else 0.0}
+def find_marker_key(dictionary):
+    """models/__init__.py:950-954."""
+    for key in dictionary:
+        if key.endswith("Marker"):
+            return key
+    return None
+
+
+def postprocess(orig, images, tile_size, model, seg_thresh=120, size_thresh="default", marker_thresh=None,
+                size_thresh_upper=None):
+    """Reference models/__init__.py:582-610: cell-level scoring + SegOverlaid / SegRefined from the stitched Seg (and
+    Marker) image; the pixel and graph work runs on the GPU (deepliif_b200.postprocessing, csrc/cells.cu)."""
+    from ..postprocessing import compute_final_results
+    if model in ("DeepLIIF", "DeepLIIFKD"):
+        resolution = "40x" if tile_size > 384 else ("20x" if tile_size > 192 else "10x")
+        marker_key = find_marker_key(images)
+        overlay, refined, scoring = compute_final_results(
+            orig, images["Seg"], images.get(marker_key) if marker_key else None, resolution, size_thresh, marker_thresh,
+            size_thresh_upper, seg_thresh)
+        return {"SegOverlaid": Image.fromarray(overlay), "SegRefined": Image.fromarray(refined)}, scoring
+    raise Exception(f"postprocess() not implemented for model {model}")
 
 
 def infer_modalities(img, tile_size, model_dir, eager_mode=True, color_dapi=False, color_marker=False, opt=None,
@@ -233,5 +246,12 @@ def infer_modalities(img, tile_size, model_dir, eager_mode=True, color_dapi=Fals
                        eager_mode=True, color_dapi=color_dapi, color_marker=color_marker, opt=opt,
                        return_seg_intermediate=return_seg_intermediate, seg_only=seg_only, mod_only=mod_only,
                        seg_weights=seg_weights)
-    scoring = posneg_summary(images["Seg"]) if "Seg" in images else None      # non-zero ranks of a sharded run get {}
-    return images, scoring
+    if not images:                                  # non-zero ranks of a tile-sharded run: rank 0 holds the results
+        return images, None
+    if getattr(opt, "seg_gen", True) and not mod_only:          # models/__init__.py:648-657
+        post_images, scoring = postprocess(img, images, tile_size, opt.model)
+        images = {**images, **post_images}
+        if seg_only:
+            images = {k: v for k, v in images.items() if "Seg" in k}
+        return images, scoring
+    return images, None

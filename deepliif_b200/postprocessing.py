@@ -34,6 +34,14 @@ def _dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
 
+def _to_host(t):
+    """D2H through pinned memory (torch's caching host allocator keeps the buffer for the next call)."""
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy()
+
+
 def _device():
     if not torch.cuda.is_available():
         raise _lib.DeepliifB200Error("deepliif_b200.postprocessing needs a CUDA device (no CPU path exists)")
@@ -138,18 +146,33 @@ def create_final_images_gpu(orig_d, mask_d):
 
 # ---- host logic over the cell list (postprocessing.py:365-488, 1125-1133) --------------------------------------
 def _round_div_half_even(num, den):
-    q, r = divmod(int(num), int(den))
-    return q + (1 if (2 * r > den or (2 * r == den and q % 2 == 1)) else 0)
+    """int(round(num / den)) for non-negative int64 arrays with python3 / numba semantics (ties to even)."""
+    q, r = np.divmod(num, np.maximum(den, 1))
+    return q + ((2 * r > den) | ((2 * r == den) & (q % 2 == 1)))
+
+
+class CellTable:
+    """The reference's cellsinfo list (7-tuples: count, positive, marker, x0, y0, cx, cy) held as columns."""
+    __slots__ = ("count", "positive", "marker", "x0", "y0", "cx", "cy")
+
+    def __len__(self):
+        return int(self.count.shape[0])
+
+    def as_tuples(self):
+        return list(zip(self.count.tolist(), self.positive.tolist(), self.marker.tolist(), self.x0.tolist(),
+                        self.y0.tolist(), self.cx.tolist(), self.cy.tolist()))
 
 
 def create_kde(values, count, bandwidth=1.0):
-    """postprocessing.py:365-403: Gaussian KDE on `count` bins; float64 sums stored as float32."""
+    """postprocessing.py:365-403: Gaussian KDE of `values` on `count` bins (float64 sums stored as float32).  Cell
+    sizes repeat, so the kernel is evaluated once per distinct value and weighted by its multiplicity."""
     c = 1 / math.sqrt(2 * math.pi)
     step = (float(values.max()) + 1) / count
     n = values.shape[0]
+    uniq, mult = np.unique(values, return_counts=True)
     x = (np.arange(count, dtype=np.float64) * step)[:, None]
-    val = (x - values[None, :]) * (1 / bandwidth)
-    total = np.cumsum(np.exp(-(val * val / 2)) * c, axis=1)[:, -1]      # left-to-right sums like the reference loop
+    val = (x - uniq[None, :]) * (1 / bandwidth)
+    total = (np.exp(-(val * val / 2)) * c) @ mult.astype(np.float64)
     return (total / (n * bandwidth)).astype(np.float32), step
 
 
@@ -212,68 +235,100 @@ def calculate_large_noise_thresh(large_noise_thresh, resolution):
 class CellState:
     """What get_cells_info leaves on the device for create_cell_classification (the reference keeps x0,y0 per cell
     and re-floods; here the label image does that job)."""
-    __slots__ = ("labels", "roots", "kept", "H", "W")
+    __slots__ = ("mask", "labels", "roots", "kept", "H", "W")
 
 
-def get_cells_info(seg, marker, resolution, noise_thresh, seg_thresh, large_noise_thresh, use_od=False, _state=None):
-    """postprocessing.py:311-362.  Returns (mask uint8 [H,W] with cells = 100, cellsinfo list of 7-tuples, defaults)."""
-    dev = _device()
-    seg_d = _dev(to_array(seg), dev)
+class StageClock:
+    """Optional per-stage device timing (CUDA events on the current stream) for bench.py."""
+
+    def __init__(self):
+        self.marks = [("start", self._ev())]
+
+    @staticmethod
+    def _ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def mark(self, name):
+        self.marks.append((name, self._ev()))
+
+    def ms(self):
+        torch.cuda.synchronize()
+        return {n: self.marks[i][1].elapsed_time(e) for i, (n, e) in enumerate(self.marks[1:])}
+
+
+def _cells_device(seg_d, marker_d, resolution, noise_thresh, seg_thresh, large_noise_thresh, use_od, st, clock=None):
+    """Device part of get_cells_info: uint8 [H,W,3] device tensors -> (cells, defaults); label state left in `st`."""
+    mark = clock.mark if clock is not None else (lambda name: None)
     H, W, _ = seg_d.shape
     plane = hist = None
-    if marker is not None:
-        plane, hist = marker_plane_gpu(_dev(to_array(marker), dev), use_od=use_od, want_hist=not use_od)
+    if marker_d is not None:
+        plane, hist = marker_plane_gpu(marker_d, use_od=use_od, want_hist=not use_od)
     mask_d = create_posneg_mask_gpu(seg_d, seg_thresh)
-    labels = torch.empty(H * W, dtype=torch.int32, device=dev)
+    mark("mask+marker")
+    labels = torch.empty(H * W, dtype=torch.int32, device=seg_d.device)
     mark_background_gpu(mask_d, labels)
+    mark("mark_background")
     labels, roots, n = label_cells_gpu(mask_d, labels)
+    mark("label")
     table = cell_stats_gpu(mask_d, plane, labels, roots, use_avg=use_od).cpu().numpy()
-    cells, kept = [], []
-    for i in range(n):
-        cnt, cp, cn, mv, x0, y0, sx, sy = (int(v) for v in table[i])
-        if cnt > noise_thresh and (large_noise_thresh is None or cnt < large_noise_thresh):
-            if use_od:
-                mv = _round_div_half_even(mv, cnt)
-            cells.append((cnt, cp >= cn, mv, x0, y0, _round_div_half_even(sx, cnt), _round_div_half_even(sy, cnt)))
-            kept.append(i)
-    defaults = {"size_thresh": calculate_default_size_threshold([c[0] for c in cells], resolution)}
-    if marker is not None and not use_od:
+    mark("stats+d2h")
+    keep = table[:, 0] > noise_thresh
+    if large_noise_thresh is not None:
+        keep &= table[:, 0] < large_noise_thresh
+    kept = np.flatnonzero(keep)
+    t = table[kept]
+    cnt = t[:, 0]
+    cells = CellTable()
+    cells.count, cells.positive = cnt, t[:, 1] >= t[:, 2]
+    cells.marker = _round_div_half_even(t[:, 3], cnt) if use_od else t[:, 3]
+    cells.x0, cells.y0 = t[:, 4], t[:, 5]
+    cells.cx, cells.cy = _round_div_half_even(t[:, 6], cnt), _round_div_half_even(t[:, 7], cnt)
+    defaults = {"size_thresh": calculate_default_size_threshold(cells.count, resolution)}
+    if marker_d is not None and not use_od:
         defaults["marker_thresh"] = calculate_default_marker_threshold_from_hist(hist.cpu().numpy())
-    if _state is not None:
-        _state.labels, _state.roots, _state.kept, _state.H, _state.W = labels, roots, kept, H, W
-        return None, cells, defaults
-    mask = torch.where(labels >= 0, torch.full_like(mask_d, LABEL_CELL), mask_d)
-    return mask.cpu().numpy(), cells, defaults
+    mark("host thresholds")
+    st.mask, st.labels, st.roots, st.kept, st.H, st.W = mask_d, labels, roots, kept, H, W
+    return cells, defaults
+
+
+def get_cells_info(seg, marker, resolution, noise_thresh, seg_thresh, large_noise_thresh, use_od=False):
+    """postprocessing.py:311-362.  Returns (mask uint8 [H,W] with cells = 100, cellsinfo list of 7-tuples, defaults)."""
+    dev = _device()
+    st = CellState()
+    cells, defaults = _cells_device(_dev(to_array(seg), dev), _dev(to_array(marker), dev) if marker is not None else None,
+                                    resolution, noise_thresh, seg_thresh, large_noise_thresh, use_od, st)
+    mask = torch.where(st.labels >= 0, torch.full_like(st.mask, LABEL_CELL), st.mask)
+    return mask.cpu().numpy(), cells.as_tuples(), defaults
 
 
 def _classes(cells, kept, n, size_thresh, marker_thresh, size_thresh_upper, od_thresh_lower, od_thresh_upper):
-    """The per-cell decisions of create_cell_classification (postprocessing.py:958-980)."""
+    """The per-cell decisions of create_cell_classification (postprocessing.py:958-980), on the columns."""
     cls = np.zeros(max(n, 1), dtype=np.uint8)
-    num_pos = num_neg = 0
-    for cell, ci in zip(cells, kept):
-        if cell[0] > size_thresh and (size_thresh_upper is None or cell[0] < size_thresh_upper):
-            is_pos = bool(cell[1])
-            if marker_thresh is not None and cell[2] > marker_thresh:
-                is_pos = True
-            if od_thresh_lower is not None and cell[2] < od_thresh_lower:
-                is_pos = False
-            elif od_thresh_upper is not None and cell[2] > od_thresh_upper:
-                is_pos = False
-            cls[ci] = 2 if is_pos else 1
-            num_pos += is_pos
-            num_neg += not is_pos
+    sel = cells.count > size_thresh
+    if size_thresh_upper is not None:
+        sel &= cells.count < size_thresh_upper
+    is_pos = cells.positive.copy()
+    if marker_thresh is not None:
+        is_pos |= cells.marker > marker_thresh
+    low = cells.marker < od_thresh_lower if od_thresh_lower is not None else np.zeros(len(cells), dtype=bool)
+    up = (cells.marker > od_thresh_upper) & ~low if od_thresh_upper is not None else np.zeros(len(cells), dtype=bool)
+    is_pos &= ~(low | up)
+    cls[kept[sel]] = np.where(is_pos[sel], 2, 1)
+    num_pos, num_neg = int((sel & is_pos).sum()), int((sel & ~is_pos).sum())
     return cls, {"num_total": num_pos + num_neg, "num_pos": num_pos, "num_neg": num_neg}
 
 
-def compute_final_results(orig, seg, marker, resolution, size_thresh="default", marker_thresh=None,
-                          size_thresh_upper=None, seg_thresh=DEFAULT_SEG_THRESH, noise_thresh=DEFAULT_NOISE_THRESH,
-                          large_noise_thresh=None, od_thresh_lower=None, od_thresh_upper=None, return_mask=False):
-    """postprocessing.py:1223-1304 -> (overlay uint8 [H,W,3], refined uint8 [H,W,3], scoring dict)."""
+def compute_final_results_device(orig_d, seg_d, marker_d, resolution, size_thresh="default", marker_thresh=None,
+                                 size_thresh_upper=None, seg_thresh=DEFAULT_SEG_THRESH, noise_thresh=DEFAULT_NOISE_THRESH,
+                                 large_noise_thresh=None, od_thresh_lower=None, od_thresh_upper=None, clock=None):
+    """compute_final_results on uint8 [H,W,3] CUDA tensors -> (overlay_d, refined_d, scoring, mask_d, cells)."""
     large_noise_thresh = calculate_large_noise_thresh(large_noise_thresh, resolution)
     use_od = od_thresh_lower is not None or od_thresh_upper is not None
     st = CellState()
-    _, cells, defaults = get_cells_info(seg, orig if use_od else marker, resolution, noise_thresh, seg_thresh,
-                                        large_noise_thresh, use_od=use_od, _state=st)
+    cells, defaults = _cells_device(seg_d, orig_d if use_od else marker_d, resolution, noise_thresh, seg_thresh,
+                                    large_noise_thresh, use_od, st, clock)
     if size_thresh is None:
         size_thresh = 0
     elif isinstance(size_thresh, str) and size_thresh == "default":
@@ -282,15 +337,28 @@ def compute_final_results(orig, seg, marker, resolution, size_thresh="default", 
         marker_thresh = defaults["marker_thresh"]
     cls, counts = _classes(cells, st.kept, st.roots.numel(), size_thresh, marker_thresh, size_thresh_upper,
                            od_thresh_lower, od_thresh_upper)
-    dev = st.labels.device
-    mask_d = classify_gpu(st.labels, st.roots, _dev(cls, dev), st.H, st.W)
+    mask_d = classify_gpu(st.labels, st.roots, _dev(cls, seg_d.device), st.H, st.W)
     mask_d = enlarge_cell_boundaries_gpu(enlarge_cell_boundaries_gpu(mask_d))
-    overlay, refined = create_final_images_gpu(_dev(to_array(orig), dev), mask_d)
+    overlay, refined = create_final_images_gpu(orig_d, mask_d)
+    if clock is not None:
+        clock.mark("classify+enlarge+images")
     scoring = {
         "num_total": counts["num_total"], "num_pos": counts["num_pos"], "num_neg": counts["num_neg"],
         "percent_pos": round(counts["num_pos"] / counts["num_total"] * 100, 1) if counts["num_pos"] > 0 else 0,
         "seg_thresh": seg_thresh, "size_thresh": size_thresh, "size_thresh_upper": size_thresh_upper,
-        "marker_thresh": marker_thresh if marker is not None else None,
+        "marker_thresh": marker_thresh if marker_d is not None else None,
     }
-    out = (overlay.cpu().numpy(), refined.cpu().numpy(), scoring)
-    return out + (mask_d.cpu().numpy(), cells) if return_mask else out
+    return overlay, refined, scoring, mask_d, cells
+
+
+def compute_final_results(orig, seg, marker, resolution, size_thresh="default", marker_thresh=None,
+                          size_thresh_upper=None, seg_thresh=DEFAULT_SEG_THRESH, noise_thresh=DEFAULT_NOISE_THRESH,
+                          large_noise_thresh=None, od_thresh_lower=None, od_thresh_upper=None, return_mask=False):
+    """postprocessing.py:1223-1304 -> (overlay uint8 [H,W,3], refined uint8 [H,W,3], scoring dict)."""
+    dev = _device()
+    overlay, refined, scoring, mask_d, cells = compute_final_results_device(
+        _dev(to_array(orig), dev), _dev(to_array(seg), dev), _dev(to_array(marker), dev) if marker is not None else None,
+        resolution, size_thresh, marker_thresh, size_thresh_upper, seg_thresh, noise_thresh, large_noise_thresh,
+        od_thresh_lower, od_thresh_upper)
+    out = (_to_host(overlay), _to_host(refined), scoring)
+    return out + (mask_d.cpu().numpy(), cells.as_tuples()) if return_mask else out

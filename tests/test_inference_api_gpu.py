@@ -60,7 +60,7 @@ def test_infer_modalities_matches_oracle_cascade(tmp_path):
     img = (rng.random((512, 512, 3)) * 255).astype(np.uint8)
     images, scoring = infer_modalities(Image.fromarray(img), 512, mdir, return_seg_intermediate=True)
     assert set(images) == {"mod1-Hema", "mod2-DAPI", "mod3-Lap2", "mod4-Marker", "Seg", "mod0-IHC_s", "mod1-Hema_s",
-                           "mod2-DAPI_s", "mod3-Lap2_s", "mod4-Marker_s"}
+                           "mod2-DAPI_s", "mod3-Lap2_s", "mod4-Marker_s", "SegOverlaid", "SegRefined"}
     x = torch.from_numpy(pixel.transform(img))
     mods, parts, seg = _oracle_cascade(x, sds, "unet_512")
     worst = 0
@@ -79,7 +79,12 @@ def test_infer_modalities_matches_oracle_cascade(tmp_path):
     mism = int((mask_ref != mask_got).sum())
     print(f"posneg mask pixel mismatches vs oracle-from-fp32: {mism} of {mask_ref.size}")
     assert mism <= 0.005 * mask_ref.size
-    assert set(scoring) == {"num_pos_pixels", "num_neg_pixels", "percent_pos_pixels"}
+    # postprocess (models/__init__.py:582-591): integer work on the stitched uint8 images -> bit-exact vs the oracle
+    from oracle import cells
+    ov, rf, sc = cells.compute_final_results(img, np.asarray(images["Seg"]), np.asarray(images["mod4-Marker"]), "40x")
+    assert scoring == sc and list(scoring) == ["num_total", "num_pos", "num_neg", "percent_pos", "seg_thresh", "size_thresh",
+                                               "size_thresh_upper", "marker_thresh"]
+    assert np.array_equal(np.asarray(images["SegOverlaid"]), ov) and np.array_equal(np.asarray(images["SegRefined"]), rf)
 
 
 def test_cli_test_command_writes_outputs(tmp_path):
@@ -97,8 +102,9 @@ def test_cli_test_command_writes_outputs(tmp_path):
     assert r.exit_code == 0, r.output
     files = sorted(os.listdir(out))
     assert "roi_Seg.png" in files and "roi_mod4-Marker.png" in files and "roi.json" in files
+    assert "roi_SegOverlaid.png" in files and "roi_SegRefined.png" in files
     assert Image.open(out / "roi_Seg.png").size == (700, 600)
-    assert "num_pos_pixels" in json.load(open(out / "roi.json"))
+    assert "num_total" in json.load(open(out / "roi.json"))
 
 
 def test_cli_train_then_test_round_trip(tmp_path):
