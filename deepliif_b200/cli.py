@@ -132,6 +132,12 @@ TRAIN_DEFAULTS = dict(
 @click.option("--epoch", default="latest")
 @click.option("--num-threads", default=4)
 @click.option("--max-dataset-size", type=int, default=None)
+@click.option("--serial-batches", is_flag=True, help="take images in order to make batches, otherwise at random")
+@click.option("--load-size", default=512, help="scale images to this size")
+@click.option("--crop-size", default=512, help="then crop to this size")
+@click.option("--preprocess", type=str, default="resize_and_crop",
+              help="resize_and_crop | crop | scale_width | scale_width_and_crop | none")
+@click.option("--no-flip", is_flag=True, help="if specified, do not flip the images for data augmentation")
 def train(**kw):
     """General-purpose training script for the DeepLIIF multi-task image-to-image translation model."""
     from . import training

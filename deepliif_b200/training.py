@@ -223,42 +223,6 @@ def _sync_and_step(optimizer):
 # -------------------------------------------------------------------------------------------------------------------
 # data: AlignedDataset semantics (row of equally sized tiles: A | B_1 | ... ) — deepliif/data/aligned_dataset.py:36-113
 # -------------------------------------------------------------------------------------------------------------------
-class AlignedTiles(torch.utils.data.Dataset):
-    EXT = (".png", ".jpg", ".jpeg", ".tif", ".tiff", ".bmp")
-
-    def __init__(self, root, phase, n_targets, no_flip=True, max_dataset_size=None, seed=0):
-        d = os.path.join(root, phase)
-        self.paths = sorted(os.path.join(d, f) for f in os.listdir(d) if f.lower().endswith(self.EXT))
-        if max_dataset_size:
-            self.paths = self.paths[:max_dataset_size]
-        self.n_targets, self.no_flip = n_targets, no_flip
-        self.rng = np.random.default_rng(seed)
-
-    def __len__(self):
-        return len(self.paths)
-
-    def __getitem__(self, idx):
-        from PIL import Image
-        from .data import transform_array
-        img = np.asarray(Image.open(self.paths[idx]).convert("RGB"))
-        k = self.n_targets + 1
-        w = img.shape[1] // k
-        flip = (not self.no_flip) and self.rng.random() < 0.5
-        tiles = []
-        for j in range(k):
-            t = img[:, j * w:(j + 1) * w]
-            if flip:
-                t = t[:, ::-1]
-            tiles.append(torch.from_numpy(transform_array(np.ascontiguousarray(t))[0]))
-        return {"A": tiles[0], "B": tiles[1:], "A_paths": self.paths[idx]}
-
-
-def _collate(items):
-    return {"A": torch.stack([it["A"] for it in items]),
-            "B": [torch.stack([it["B"][j] for it in items]) for j in range(len(items[0]["B"]))],
-            "A_paths": [it["A_paths"] for it in items]}
-
-
 # -------------------------------------------------------------------------------------------------------------------
 # `deepliif train`
 # -------------------------------------------------------------------------------------------------------------------
@@ -310,12 +274,15 @@ def run_training(params):
     opt = build_options(params)
     if rank == 0:
         print_options(opt, save=True)
-    n_targets = opt.modalities_no + (1 if opt.seg_gen else 0)
-    ds = AlignedTiles(opt.dataroot, "train", n_targets, no_flip=opt.no_flip, max_dataset_size=opt.max_dataset_size,
-                      seed=(params.get("seed") or 0) + rank)
+    import random
+    from .data.aligned_dataset import AlignedDataset, DeviceBatches, collate_u8
+    if params.get("seed") is not None:
+        random.seed(params["seed"] + rank)            # crop / flip parameters (base_dataset.py:62-78 uses `random`)
+    ds = AlignedDataset(opt, "train")                 # uint8 tiles; ToTensor + Normalize run on the device
     sampler = torch.utils.data.distributed.DistributedSampler(ds, world, rank, shuffle=True) if world > 1 else None
-    dl = torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=sampler is None, sampler=sampler,
-                                     num_workers=opt.num_threads, collate_fn=_collate, pin_memory=True, drop_last=False)
+    loader = torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=sampler is None and not opt.serial_batches,
+                                         sampler=sampler, num_workers=opt.num_threads, collate_fn=collate_u8, drop_last=False)
+    dl = DeviceBatches(loader, torch.device("cuda", local), input_no=getattr(opt, "input_no", 1))
     model = create_model(opt)
     model.setup(opt)
     make_optimizers(model)

@@ -97,9 +97,63 @@ def cells_fixture():
     save("cells", **arrs)
 
 
+DATASET_CASES = [("resize_and_crop", 48, 32, False), ("resize_and_crop", 40, 40, True), ("crop", 48, 24, False),
+                 ("scale_width_and_crop", 52, 36, False), ("none", 48, 48, False)]
+
+
+def dataset_rows(n=3, h=40, w=44, k=6, seed=0):
+    rng = np.random.default_rng(seed)
+    return [rng.integers(0, 256, (h, k * w, 3), dtype=np.uint8) for _ in range(n)]
+
+
+def dataset_opt(root, pre, ls, cs, nf):
+    class O:
+        pass
+    o = O()
+    o.dataroot, o.preprocess, o.max_dataset_size, o.load_size, o.crop_size, o.direction = root, pre, None, ls, cs, "AtoB"
+    o.input_nc = o.output_nc = 3
+    o.no_flip, o.modalities_no, o.seg_no, o.input_no, o.seg_gen, o.model = nf, 4, 1, 1, True, "DeepLIIF"
+    return o
+
+
+def checksum(a):
+    a = a.astype(np.int64).ravel()
+    return np.array([a.sum(), (a * (np.arange(a.size) % 8191 + 1)).sum()], dtype=np.int64)
+
+
+def dataset_fixture():
+    """Training data path: the reference's AlignedDataset (deepliif/data/aligned_dataset.py:36-113) on seeded row
+    images with `random.seed(100 + index)` before each item; stored as uint8 (its fp32 output is exactly
+    (u8/255 - 0.5)/0.5, inverted here) — checksums of every item plus a subsample."""
+    import random
+    import tempfile
+    from PIL import Image
+    import_reference()
+    from deepliif.data.aligned_dataset import AlignedDataset as RefDS
+    root = tempfile.mkdtemp()
+    os.makedirs(os.path.join(root, "train"))
+    for i, row in enumerate(dataset_rows()):
+        Image.fromarray(row).save(os.path.join(root, "train", f"s{i}.png"))
+    arrs = {}
+    for ci, (pre, ls, cs, nf) in enumerate(DATASET_CASES):
+        ds = RefDS(dataset_opt(root, pre, ls, cs, nf))
+        for i in range(len(ds)):
+            random.seed(100 + i)
+            r = ds[i]
+            t = torch.stack([r["A"]] + r["B"]).numpy()                       # [k,3,H,W] fp32
+            u8 = np.rint((t * 0.5 + 0.5) * 255).astype(np.uint8).transpose(0, 2, 3, 1)
+            assert np.array_equal(np.concatenate([pixel.transform(u8[j]) for j in range(u8.shape[0])]), t)
+            arrs[f"c{ci}_i{i}_sum"] = checksum(u8)
+            arrs[f"c{ci}_i{i}_shape"] = np.array(u8.shape)
+            arrs[f"c{ci}_i{i}_sub"] = u8[:, ::3, ::3].copy()
+    save("aligned_dataset", **arrs)
+
+
 def main():
     if "cells" in sys.argv[1:]:
         return cells_fixture()
+    if "dataset" in sys.argv[1:]:
+        return dataset_fixture()
     torch.set_num_threads(os.cpu_count())
     N = reference_networks()
     import_reference()
@@ -221,6 +275,7 @@ def main():
     arrs["var_vals"] = np.array([ref_var(Image.fromarray(v)) for v in var_imgs])
     save("tiler", **arrs)
     cells_fixture()
+    dataset_fixture()
     print("all fixtures written to", OUT)
 
 

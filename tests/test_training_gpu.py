@@ -295,3 +295,31 @@ def test_resnet_training_with_dropout_runs_and_is_seeded():
     g = eng.backward(c1, _rand((2, 3, 64, 64), 6).cuda())
     expected = {k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
     assert set(g) == expected and all(torch.isfinite(v).all() for v in g.values())
+
+
+def test_device_batches_prefetch_matches_host_transform(tmp_path):
+    """uint8 batches -> pinned -> async H2D -> dlb_u8_to_f32 on a side stream == the reference's ToTensor + Normalize
+    of the same tiles (oracle.pixel.transform), for every batch including the ragged last one."""
+    import random
+    import numpy as np
+    from PIL import Image
+    from oracle import pixel
+    from oracle.gen_golden import dataset_opt, dataset_rows
+    from deepliif_b200.data.aligned_dataset import AlignedDataset, DeviceBatches, collate_u8
+    (tmp_path / "train").mkdir()
+    for i, row in enumerate(dataset_rows(n=5)):
+        Image.fromarray(row).save(tmp_path / "train" / f"s{i}.png")
+    ds = AlignedDataset(dataset_opt(str(tmp_path), "resize_and_crop", 48, 32, False))
+    random.seed(5)
+    want = [ds[i][0].numpy() for i in range(5)]
+    random.seed(5)
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=0, collate_fn=collate_u8)
+    got = list(DeviceBatches(loader, torch.device("cuda", 0)))
+    assert [b["A"].shape[0] for b in got] == [2, 2, 1] and all(len(b["B"]) == 5 for b in got)
+    k = 0
+    for b in got:
+        for n in range(b["A"].shape[0]):
+            planes = [b["A"][n]] + [t[n] for t in b["B"]]
+            for j, pl in enumerate(planes):
+                assert np.array_equal(pl.cpu().numpy()[None], pixel.transform(want[k][j]))
+            k += 1
