@@ -31,14 +31,10 @@ def to_array(img, grayscale=False):
 
 
 def _dev(a, device):
-    a = np.ascontiguousarray(a)
-    if not a.flags.writeable:                       # np.asarray(PIL image) is read-only; torch only needs to read it
-        a = a.view()
-        try:
-            a.flags.writeable = True
-        except ValueError:
-            a = a.copy()
-    return torch.from_numpy(a).to(device, non_blocking=False)
+    import warnings
+    with warnings.catch_warnings():                 # np.asarray(PIL image) is read-only; it is only read here
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
 
 def _to_host(t):
