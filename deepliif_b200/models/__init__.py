@@ -7,7 +7,7 @@ threads across nets, nets spread over GPUs).  Here all tiles of an image form on
 quantisation, D2H of uint8 results); several GPUs shard tiles, not networks (deepliif_b200/sharding.py).
 ``infer_modalities`` ends, as in the reference, with ``postprocess`` (cell-level scoring, SegOverlaid, SegRefined), whose
 pixel/graph work runs on the GPU (deepliif_b200/postprocessing.py).
-Out of scope: TorchScript (.pt) loading, TorchServe, Dask, WSI readers."""
+Out of scope: executing TorchScript graphs (their weights do load), TorchServe, Dask, WSI readers."""
 import importlib
 import os
 from functools import lru_cache
@@ -68,7 +68,9 @@ def get_opt(model_dir, mode="test"):
 @lru_cache
 def init_nets(model_dir, eager_mode=True, opt=None, phase="test"):
     """dict[name -> callable net] for a model directory (train_opt.txt + latest_net_*.pth), built once.
-    Only the eager path exists here: serialized TorchScript (.pt) models are cuDNN graphs, out of scope."""
+    A directory written by the reference's `deepliif serialize` (G1.pt, ..., TorchScript) loads too: the weights are
+    extracted from the archives into the native layout (the traced cuDNN graphs themselves are not executed), so
+    `eager_mode` only selects which files are looked for first."""
     if opt is None:
         opt = get_opt(model_dir, mode=phase)
     if opt.model != "DeepLIIF":

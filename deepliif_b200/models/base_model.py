@@ -94,8 +94,19 @@ class BaseModel(ABC):
         for name in self.model_names:
             path = os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch, name))
             net = self._unwrap(self._net(name))
-            print("loading the model from %s" % path)
-            sd = torch.load(path, map_location="cpu")
+            pt = os.path.join(self.save_dir, "%s.pt" % name)
+            if not os.path.exists(path) and os.path.exists(pt):
+                # a `deepliif serialize` directory (reference cli.py:770-811): TorchScript archives of the traced nets.
+                # Only the weights are taken (the traced graph is a cuDNN program); keys equal the eager state_dict's.
+                print("loading the weights of the serialized model %s" % pt)
+                have = net.state_dict()
+                sd = {k: v for k, v in torch.jit.load(pt, map_location="cpu").state_dict().items()}
+                for k, v in have.items():      # traced eval nets carry no BatchNorm running statistics: keep the fresh ones
+                    if k not in sd and k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                        sd[k] = v
+            else:
+                print("loading the model from %s" % path)
+                sd = torch.load(path, map_location="cpu")
             if hasattr(sd, "_metadata"):
                 del sd._metadata
             # InstanceNorm checkpoints written by torch < 0.4 may carry running stats: drop them

@@ -156,3 +156,54 @@ def test_empty_tiles_skip_the_networks(tmp_path):
         assert (res[k][1] == np.array(opt.background_colors[j], np.uint8)).all()
         assert res[k][0].std() > 1.0
     assert (res["GS"][1] == 0).all() and res["GS"][0].std() > 1.0
+
+
+class _Stub(torch.nn.Module):
+    """A torch module with the reference's parameter names (what `deepliif serialize` traces, cli.py:800-811)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        for k, v in sd.items():
+            mod, parts = self, k.split(".")
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, torch.nn.Module())
+                mod = mod._modules[p]
+            mod.register_parameter(parts[-1], torch.nn.Parameter(v.clone()))
+
+    def forward(self, x):
+        return x + 0
+
+
+def test_legacy_names_and_serialized_pt_dirs_load_identically(tmp_path):
+    """(i) legacy Zenodo naming latest_net_G51..G55 and (ii) a `deepliif serialize` directory of
+    TorchScript archives G1.pt.. give the same images as the S-named .pth directory with the same weights."""
+    import shutil
+    from deepliif_b200.models import infer_modalities, init_nets
+    mdir, sds = _write_model_dir(tmp_path, net_g="resnet_2blocks", net_gs="unet_128", n_blocks=2)
+    # _write_model_dir builds 9-block / unet_512 shapes: rewrite the files for the small topology
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, 2, "batch", True, "zero")
+    s_shapes = nets.unet_param_shapes(7, 64, 3, 3, "batch")
+    sds = {**{f"G{i}": nets.make_state_dict(g_shapes, 50 + i, "stress") for i in range(1, 5)},
+           **{f"GS{i}": nets.make_state_dict(s_shapes, 60 + i, "stress") for i in range(5)}}
+    for k, sd in sds.items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    legacy, serialized = str(tmp_path / "legacy"), str(tmp_path / "serialized")
+    for d in (legacy, serialized):
+        os.makedirs(d)
+        with open(os.path.join(mdir, "train_opt.txt")) as f, open(os.path.join(d, "train_opt.txt"), "w") as g:
+            g.writelines(l for l in f if "mod_id_seg" not in l and "input_id" not in l)
+    for k, sd in sds.items():
+        old = k if not k.startswith("GS") else f"G5{int(k[2:]) + 1}"
+        torch.save(sd, os.path.join(legacy, f"latest_net_{old}.pth"))
+        keep = {n: v for n, v in sd.items() if not n.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+        torch.jit.trace(_Stub(keep), torch.zeros(1)).save(os.path.join(serialized, f"{k}.pt"))
+    rng = np.random.default_rng(21)
+    img = Image.fromarray((rng.random((256, 256, 3)) * 255).astype(np.uint8))
+    base, _ = infer_modalities(img, 256, mdir, return_seg_intermediate=True)
+    for d, eager in ((legacy, True), (serialized, False)):
+        init_nets.cache_clear()
+        got, _ = infer_modalities(img, 256, d, eager_mode=eager, return_seg_intermediate=True)
+        assert set(got) == set(base)
+        for k in base:
+            assert np.array_equal(np.asarray(got[k]), np.asarray(base[k])), (d, k)
