@@ -47,6 +47,8 @@ SIGNATURES = {
     "dlb_u8_to_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_f32_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dlb_seg_finish": (_i, [_vpp, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dlb_reflect_fold": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dlb_stem_window_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dlb_cells_posneg_mask": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "dlb_cells_marker_plane": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dlb_cells_mark_background": (_i, [_vp, _i, _i, _vp, _vp]),

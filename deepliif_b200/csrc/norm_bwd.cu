@@ -226,6 +226,69 @@ __global__ void chsum_final_kernel(const float* __restrict__ part, int slices, i
   out[c] = accumulate ? out[c] + static_cast<float>(a) : static_cast<float>(a);
 }
 
+
+// ---- padding backward ------------------------------------------------------------------------------------------------
+// Reflection padding copies interior pixels into the border, so its backward sums every padded position that reads a
+// pixel:  dx[h] = dpad[h + p] + (1 <= h <= p ? dpad[p - h] : 0) + (H-1-p <= h <= H-2 ? dpad[2(H-1) - h + p] : 0), same in w.
+__device__ __forceinline__ int fold_sources(int h, int H, int p, int out[3]) {
+  int n = 0;
+  out[n++] = h + p;
+  if (h >= 1 && h <= p) out[n++] = p - h;
+  if (h >= H - 1 - p && h <= H - 2) out[n++] = 2 * (H - 1) - h + p;
+  return n;
+}
+
+__global__ void __launch_bounds__(256) reflect_fold_kernel(const float* __restrict__ dpad, const float* __restrict__ add,
+                                                           float* __restrict__ dx, int N, int H, int W, int C, int p) {
+  const int c4n = C / 4, HP = H + 2 * p, WP = W + 2 * p;
+  const long long total = static_cast<long long>(N) * H * W * c4n;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % c4n);
+    long long r = i / c4n;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    int hs[3], ws[3];
+    const int nh = fold_sources(h, H, p, hs), nw = fold_sources(w, W, p, ws);
+    float4 acc = add ? *reinterpret_cast<const float4*>(add + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(dpad + ((static_cast<long long>(n) * HP + hs[a]) * WP + ws[b]) * C + cq * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    *reinterpret_cast<float4*>(dx + i * 4) = acc;
+  }
+}
+
+// Backward of dlb_stem_window_pack: dXw fp32 [N, H+2p, W, 64] (lane s*8 + c) -> dx fp32 NCHW [N, C, H, W].
+//   Xw[n, hp, w, s*8+c] = xpad[n, c, hp, w + s]  =>  dxpad[n, c, hp, wp] = sum_s dXw[n, hp, wp - s, s*8 + c]
+// then the padding backward (crop for zero padding, the reflection sum above otherwise).
+__global__ void __launch_bounds__(256) stem_window_bwd_kernel(const float* __restrict__ dxw, int N, int C, int H, int W, int p,
+                                                              int S, int pad_mode, float* __restrict__ dx) {
+  const long long total = static_cast<long long>(N) * H * W;
+  const int HP = H + 2 * p;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % W);
+    const int h = static_cast<int>((i / W) % H);
+    const int n = static_cast<int>(i / (static_cast<long long>(W) * H));
+    int hs[3], ws[3], nh = 1, nw = 1;
+    hs[0] = h + p; ws[0] = w + p;
+    if (pad_mode == DLB_PAD_REFLECT) { nh = fold_sources(h, H, p, hs); nw = fold_sources(w, W, p, ws); }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b)
+        for (int s = 0; s < S; ++s) {
+          const int wq = ws[b] - s;
+          if (wq < 0 || wq >= W) continue;
+          const float* q = dxw + ((static_cast<long long>(n) * HP + hs[a]) * W + wq) * 64 + s * 8;
+          for (int c = 0; c < C; ++c) acc[c] += q[c];
+        }
+    for (int c = 0; c < C; ++c) dx[((static_cast<long long>(n) * C + c) * H + h) * W + w] = acc[c];
+  }
+}
+
 }  // namespace
 }  // namespace dlb
 
@@ -279,5 +342,28 @@ extern "C" int dlb_norm_bwd(const float* dout, const float* dout2, const float* 
         reinterpret_cast<__half*>(dy_hi), reinterpret_cast<__half*>(dy_lo));
   else return set_error("dlb_norm_bwd: bad fmt");
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("norm_bwd_apply_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_reflect_fold(const float* dpad_nhwc, const float* add_nhwc, int N, int H, int W, int C, int pad,
+                                float* dx_nhwc, dlb_stream_t stream) {
+  if (C % 4 != 0) return set_error("dlb_reflect_fold: C must be a multiple of 4");
+  if (pad < 0 || pad >= H || pad >= W) return set_error("dlb_reflect_fold: need 0 <= pad < H, W");
+  const long long total = static_cast<long long>(N) * H * W * (C / 4);
+  long long g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+  reflect_fold_kernel<<<static_cast<int>(g), 256, 0, stream>>>(dpad_nhwc, add_nhwc, dx_nhwc, N, H, W, C, pad);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("reflect_fold_kernel launch");
+  return 0;
+}
+
+extern "C" int dlb_stem_window_bwd(const float* dxw, int N, int C, int H, int W, int pad, int S, int pad_mode,
+                                   float* dx_nchw, dlb_stream_t stream) {
+  if (C < 1 || C > 8 || S < 1 || S > 8) return set_error("dlb_stem_window_bwd: needs C <= 8 and S <= 8");
+  if (S != 2 * pad + 1) return set_error("dlb_stem_window_bwd: S must equal 2*pad + 1");
+  if (pad_mode == DLB_PAD_REFLECT && (pad >= H || pad >= W)) return set_error("dlb_stem_window_bwd: bad pad");
+  const long long total = static_cast<long long>(N) * H * W;
+  long long g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+  stem_window_bwd_kernel<<<static_cast<int>(g), 256, 0, stream>>>(dxw, N, C, H, W, pad, S, pad_mode, dx_nchw);
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stem_window_bwd_kernel launch");
   return 0;
 }

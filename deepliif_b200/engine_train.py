@@ -6,14 +6,14 @@ kernels).  Per recorded layer  y = conv(x);  a = act(norm(y)) [+ residual]:
                dW        ConvLayer.wgrad   (tcgen05, K over pixels)   [+ bias grad = ops.channel_sum]
                dx        ConvLayer.dgrad   (conv_tc with the weight in the opposite role)
 
-Scope: ResnetGenerator (zero padding), UnetGenerator, NLayerDiscriminator; nn.Dropout(0.5) with the counter-based mask
+Scope: ResnetGenerator (zero / reflect padding, input gradient), UnetGenerator, NLayerDiscriminator; nn.Dropout(0.5) with the counter-based mask
 of csrc/rng.cuh (regenerated in backward from (seed, element index)).  Gradients are returned keyed by the reference's state_dict
 names so the nn.Module containers can store them in ``param.grad``."""
 import torch
 
 from . import ops
-from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_ZERO, Act, ConvLayer, NLayerDEngine, Precision,
-                     ResnetEngine, _EngineBase, _NormParams, _pad_cout32)
+from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO, Act, ConvLayer, NLayerDEngine,
+                     Precision, ResnetEngine, _EngineBase, _NormParams, _pad_cout32)
 
 
 class _Rec:
@@ -46,10 +46,11 @@ class _TrainOps:
         return int(torch.randint(0, 2 ** 62, (1,)).item())
 
     def _fwd(self, tape, layer, np_, srcs, N, H, W, pad, act, wkey, nkey, *, residual=None, want_f32=False,
-             want_split=True, out_pad=0, drop=None):
+             want_split=True, out_pad=0, out_pad_mode=PAD_ZERO, drop=None):
         y, ws = layer.run_tc(srcs, N, H, W, pad)
         sc, sh, mean, rstd = self._stats(y, np_, ws, want_stats=True)
-        a = self._apply(y, sc, sh, act, residual=residual, want_f32=want_f32, want_split=want_split, pad=out_pad, drop=drop)
+        a = self._apply(y, sc, sh, act, residual=residual, want_f32=want_f32, want_split=want_split, pad=out_pad,
+                        pad_mode=out_pad_mode, drop=drop)
         rec = _Rec(layer=layer, x=srcs[0], dims=(N, H, W), pad=pad, y=y, sc=sc, sh=sh, mean=mean, rstd=rstd, act=act,
                    np=np_, wkey=wkey, nkey=nkey)
         rec.extra = drop
@@ -80,8 +81,6 @@ class _TrainOps:
 
 class ResnetTrainEngine(ResnetEngine, _TrainOps):
     def __init__(self, sd, **kw):
-        if kw.get("padding_type", "zero") != "zero":
-            raise NotImplementedError("training path: zero padding only (reflect-pad backward is not built yet)")
         self.use_dropout = bool(kw.get("use_dropout", False))
         kw.setdefault("backend", "tc")
         super().__init__(sd, **kw)
@@ -101,8 +100,10 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
         for _ in range(2):
             down.append((f"model.{idx}", f"model.{idx + 1}")); idx += 3
         blocks = []
-        c1, n1 = 0, 1                    # zero padding; the Dropout module shifts the second conv by one (networks.py:479-506)
-        c2 = 4 if self.use_dropout else 3
+        # ReflectionPad2d modules (padding_type='reflect') and the Dropout module shift the indices (networks.py:479-506)
+        padm = 1 if self.pad_mode == PAD_REFLECT else 0
+        c1 = padm; n1 = c1 + 1
+        c2 = n1 + 2 + (1 if self.use_dropout else 0) + padm
         n2 = c2 + 1
         for _ in range(self.n_blocks):
             pre = f"model.{idx}.conv_block"
@@ -118,30 +119,36 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
         N, _, H, W = x.shape
         tape = []
         K = self.keys
-        xh, xl = ops.stem_window_pack(x, 3, self.stem_S, PAD_ZERO, self.prec.fmt, self.prec.split)
+        pm = self.pad_mode
+        p = 1 if pm == PAD_REFLECT else 0        # reflect: block operands are materialised with their border, convs run unpadded
+        xh, xl = ops.stem_window_pack(x, 3, self.stem_S, pm, self.prec.fmt, self.prec.split)
         a, _ = self._fwd(tape, self.stem, self.stem_norm, [Act(None, xh, xl)], N, H + 6, W, 0, ACT_RELU, *K["stem"])
         h, w = H, W
         for i in range(2):
+            last = i == 1
             a, _ = self._fwd(tape, self.down[i], self.down_norm[i], [a], N, h, w, None, ACT_RELU, *K["down"][i],
-                             want_f32=(i == 1))
+                             want_f32=last, out_pad=p if (last and self.n_blocks > 0) else 0, out_pad_mode=pm)
             h, w = h // 2, w // 2
         for b, (cv1, nm1, cv2, nm2) in enumerate(self.blocks):
             (k1, kn1), (k2, kn2) = K["blocks"][b]
-            t, _ = self._fwd(tape, cv1, nm1, [a], N, h, w, None, ACT_RELU, k1, kn1,
-                             drop=(0.5, self._new_seed()) if self.use_dropout else None)
-            a, _ = self._fwd(tape, cv2, nm2, [t], N, h, w, None, ACT_NONE, k2, kn2, residual=a.f32, want_f32=True)
+            last = b == self.n_blocks - 1
+            t, _ = self._fwd(tape, cv1, nm1, [a], N, h + 2 * p, w + 2 * p, 0 if p else None, ACT_RELU, k1, kn1,
+                             out_pad=p, out_pad_mode=pm, drop=(0.5, self._new_seed()) if self.use_dropout else None)
+            a, _ = self._fwd(tape, cv2, nm2, [t], N, h + 2 * p, w + 2 * p, 0 if p else None, ACT_NONE, k2, kn2,
+                             residual=a.f32, want_f32=True, out_pad=0 if last else p, out_pad_mode=pm)
         for i in range(2):
             last = i == 1
             a, _ = self._fwd(tape, self.up[i], self.up_norm[i], [a], N, h, w, None, ACT_RELU, *K["up"][i],
-                             out_pad=3 if last else 0)
+                             out_pad=3 if last else 0, out_pad_mode=pm)
             h, w = h * 2, w * 2
         z, _ = self.head.run_tc([a], N, h + 6, w + 6, fuse_stats=False)
         out = ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
         return out, dict(tape=tape, a_pad=a, out=out, N=N, H=H, W=W)
 
-    def backward(self, ctx, dY):
-        """dY: fp32 NCHW gradient wrt the tanh output.  Returns {state_dict key: gradient}."""
+    def backward(self, ctx, dY, need_dx=False):
+        """dY: fp32 NCHW gradient wrt the tanh output.  Returns ({state_dict key: gradient}, dx fp32 NCHW | None)."""
         tape, N, H, W = ctx["tape"], ctx["N"], ctx["H"], ctx["W"]
+        refl = self.pad_mode == PAD_REFLECT
         grads = {}
         Y = ctx["out"]
         dzz = (dY * (1.0 - Y * Y)).contiguous()                     # tanh'  (3-channel image: glue)
@@ -153,11 +160,14 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
         G = self.head64.wgrad(a_pad, dzh, dzl, N, H + 6, W + 6, 0)                 # [64 j][ngf][R][1]
         ngf, R = G.shape[1], G.shape[2]
         grads[hk + ".weight"] = G[:, :, :, 0].reshape(16, 4, ngf, R)[:S, :co].permute(1, 2, 3, 0).contiguous()
-        # data gradient wrt the un-padded head input: ConvTranspose(dz, wv64) cropped by 3 on every side
-        dd = ops.conv_desc(N, H, W + 6, [64], ngf, R, 1, 1, 3, True, 0)
+        # data gradient wrt the head input: ConvTranspose(dz, wv64); zero padding = crop by 3 on every side (the
+        # transposed conv's own padding), reflection padding = full padded extent folded back onto the interior
+        dd = ops.conv_desc(N, H, W + 6, [64], ngf, R, 1, 1, 0 if refl else 3, True, 0)
         if getattr(self, "_head_wT", None) is None:
             self._head_wT = ops.pack_weights_tc(dd, self.head64.w_f32, self.prec.fmt, self.prec.split)
         dout = ops.conv_tc(dd, [dzh], [dzl], self._head_wT[0], self._head_wT[1], None, self.prec.fmt, self.prec.split)
+        if refl:
+            dout = ops.reflect_fold(dout, 3)
         # ---- up convs ------------------------------------------------------------------------------------------------
         n_rec = len(tape)
         i = n_rec - 1
@@ -166,19 +176,25 @@ class ResnetTrainEngine(ResnetEngine, _TrainOps):
         # ---- ResNet blocks: x_{k+1} = x_k + n2(c2(relu(n1(c1(x_k))))) ---------------------------------------------------
         for _ in range(self.n_blocks):
             dt = self._bwd(tape[i], grads, dout); i -= 1            # through norm2 + conv2 -> d(relu(n1(.)))
+            if refl:
+                dt = ops.reflect_fold(dt, 1)
             dxb = self._bwd(tape[i], grads, dt); i -= 1             # through relu + norm1 + conv1 -> branch part of dx_k
-            dout, _, _ = ops.norm_apply(dxb, None, None, ACT_NONE, dout, want_f32=True, want_split=False)   # + skip part
+            if refl:
+                dout = ops.reflect_fold(dxb, 1, add=dout)           # padding backward + skip part
+            else:
+                dout, _, _ = ops.norm_apply(dxb, None, None, ACT_NONE, dout, want_f32=True, want_split=False)   # + skip part
         # ---- down convs + stem ----------------------------------------------------------------------------------------
         dout = self._bwd(tape[i], grads, dout); i -= 1
         dout = self._bwd(tape[i], grads, dout); i -= 1
         rec = tape[i]
-        self._bwd(rec, grads, dout, need_dx=False)
+        dxw = self._bwd(rec, grads, dout, need_dx=need_dx)          # wrt the horizontal-window operand [N,H+6,W,64]
         # stem weight: G[co][s*8 + c][r][0] -> w[co][c][r][s]
         G = grads[rec.wkey + ".weight"]
         cin = self.stem_in_nc
         grads[rec.wkey + ".weight"] = G[:, :, :, 0].reshape(G.shape[0], 8, 8, G.shape[2])[:, :self.stem_S, :cin] \
             .permute(0, 2, 3, 1).contiguous()
-        return grads
+        dx = ops.stem_window_bwd(dxw, cin, 3, self.stem_S, self.pad_mode) if need_dx else None
+        return grads, dx
 
 
 class NLayerDTrainEngine(NLayerDEngine, _TrainOps):

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -249,6 +249,29 @@ def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=
                                      N, H, W, Cc, pad, pad_mode, float(drop_p), int(drop_seed), _stream()), "dlb_norm_apply")
     LAUNCHES["count"] += 1
     return f32, hi, lo
+
+
+def reflect_fold(dpad, pad, add=None):
+    """Backward of ReflectionPad2d(pad): dpad fp32 [N,H+2p,W+2p,C] (+ add [N,H,W,C]) -> fp32 [N,H,W,C]."""
+    _need_cuda(dpad, add)
+    N, HP, WP, Cc = dpad.shape
+    H, W = HP - 2 * pad, WP - 2 * pad
+    out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=dpad.device)
+    check(_lib.load().dlb_reflect_fold(_p(dpad), _p(add), N, H, W, Cc, pad, _p(out), _stream()), "dlb_reflect_fold")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def stem_window_bwd(dxw, C, pad, S, pad_mode=PAD_ZERO):
+    """Backward of stem_window_pack: dxw fp32 [N,H+2p,W,64] -> dx fp32 NCHW [N,C,H,W]."""
+    _need_cuda(dxw)
+    N, HP, W, lanes = dxw.shape
+    assert lanes == 64
+    H = HP - 2 * pad
+    dx = torch.empty((N, C, H, W), dtype=torch.float32, device=dxw.device)
+    check(_lib.load().dlb_stem_window_bwd(_p(dxw), N, C, H, W, pad, S, pad_mode, _p(dx), _stream()), "dlb_stem_window_bwd")
+    LAUNCHES["count"] += 1
+    return dx
 
 
 def stem_window_pack(x_nchw, pad, S, pad_mode=PAD_ZERO, fmt=FMT_BF16, need_lo=True):

@@ -50,9 +50,7 @@ class _NetFn(torch.autograd.Function):
         elif isinstance(eng, engine_train.UnetTrainEngine):
             grads, dx = eng.backward(tape, dy, need_dx=ctx.x_needs)
         else:
-            if ctx.x_needs:
-                raise NotImplementedError("generator input gradients (seg cascade) are not built yet")
-            grads, dx = eng.backward(tape, dy), None
+            grads, dx = eng.backward(tape, dy, need_dx=ctx.x_needs)
         tape.clear()
         out = [None, dx]
         for name, need in zip(ctx.names, ctx.needs_input_grad[2:]):

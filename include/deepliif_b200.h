@@ -182,6 +182,18 @@ int dlb_f32_to_u8(const float* x_nchw, uint8_t* out_nhwc, int N, int H, int W, d
 int dlb_seg_finish(const float* const* segs, const float* weights, int nseg, int N, int H, int W, int thresh,
                    float* seg_f32_nchw, uint8_t* seg_u8_nhwc, uint8_t* mask, dlb_stream_t stream);
 
+/* ---- padding backward (training with padding_type='reflect', generator input gradients) ----------------------------
+ * dlb_reflect_fold: backward of nn.ReflectionPad2d(pad) (networks.py:386, 438, 481-499) on fp32 NHWC:
+ *   dx[n,h,w,c] = (add ? add[n,h,w,c] : 0) + sum of dpad over every padded position that mirrors (h,w);
+ *   dpad [N,H+2pad,W+2pad,C], dx / add [N,H,W,C]; pad = 0 is a plain (add +) copy.
+ * dlb_stem_window_bwd: backward of dlb_stem_window_pack incl. its zero / reflect padding:
+ *   dxw fp32 [N,H+2pad,W,64] (lane s*8+c, S = 2*pad+1) -> dx fp32 NCHW [N,C,H,W] (the generator's input gradient:
+ *   in the DeepLIIF cascade the seg generators sit behind the modality generators, DeepLIIF_model.py:175-203). */
+int dlb_reflect_fold(const float* dpad_nhwc, const float* add_nhwc, int N, int H, int W, int C, int pad, float* dx_nhwc,
+                     dlb_stream_t stream);
+int dlb_stem_window_bwd(const float* dxw, int N, int C, int H, int W, int pad, int S, int pad_mode, float* dx_nchw,
+                        dlb_stream_t stream);
+
 /* ---- cell post-processing on the stitched uint8 images ----------------------------------------
  * The integer graph work of deepliif/postprocessing.py, each call = one reference function, results bit-exact:
  *   dlb_cells_posneg_mask      create_posneg_mask (:163-190): seg uint8 [H,W,3] -> mask uint8 [H,W] (50/150/200).

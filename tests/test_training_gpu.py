@@ -45,26 +45,32 @@ def _cmp(grads, ref_sd, tol_l2=2e-2):
     return worst
 
 
-@pytest.mark.parametrize("norm,norm_mode", [("instance", "sample"), ("batch", "batch")])
-def test_resnet_generator_gradients(norm, norm_mode):
+@pytest.mark.parametrize("norm,norm_mode,padding", [("instance", "sample", "zero"), ("batch", "batch", "zero"),
+                                                    ("batch", "batch", "reflect"), ("instance", "sample", "reflect")])
+def test_resnet_generator_gradients(norm, norm_mode, padding):
+    """Parameter gradients and the input gradient (the seg generators of the cascade sit behind the modality generators;
+    define_G's default padding_type is 'reflect', networks.py:142-144)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from deepliif_b200 import engine_train
-    cfg = dict(n_blocks=2, norm=norm, use_dropout=False, padding_type="zero")
-    sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 2, norm, False, "zero"), 7, "stress")
-    x = _rand((2, 3, 64, 64), 70)
+    cfg = dict(n_blocks=2, norm=norm, use_dropout=False, padding_type=padding)
+    sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 2, norm, False, padding), 7, "stress")
+    x = _rand((2, 3, 64, 64), 70).requires_grad_(True)
     dY = _rand((2, 3, 64, 64), 71)
     leaf = _leafify(sd)
     y_ref = nets.resnet_forward(x, leaf, norm_mode=norm_mode, **cfg)
     (y_ref * dY).sum().backward()
     eng = engine_train.ResnetTrainEngine(sd, norm_mode=norm_mode, precision="bf16x3", **cfg)
-    y, ctx = eng.forward_train(x.cuda())
+    y, ctx = eng.forward_train(x.detach().cuda())
     assert (y.cpu() - y_ref.detach()).abs().max().item() < 1e-3
-    grads = eng.backward(ctx, dY.cuda())
+    grads, dx = eng.backward(ctx, dY.cuda(), need_dx=True)
     expected = {k for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad}
     assert set(grads) == expected, set(grads) ^ expected
     worst = _cmp(grads, leaf)
-    print(f"resnet {norm}/{norm_mode}: worst relative grad error {worst:.2e} over {len(grads)} tensors")
+    rel_dx = (dx.cpu() - x.grad).norm().item() / x.grad.norm().item()
+    print(f"resnet {norm}/{norm_mode}/{padding}: worst relative grad error {worst:.2e} over {len(grads)} tensors; "
+          f"input gradient rel-L2 {rel_dx:.2e}")
+    assert rel_dx < 2e-2
 
 
 @pytest.mark.parametrize("norm,n_layers", [("instance", 3), ("batch", 3), ("batch", 4)])
@@ -292,7 +298,7 @@ def test_resnet_training_with_dropout_runs_and_is_seeded():
     y2, _ = eng.forward_train(x)
     torch.manual_seed(7); y3, c3 = eng.forward_train(x)
     assert (y1 - y2).abs().max().item() > 1e-3 and torch.equal(y1, y3)
-    g = eng.backward(c1, _rand((2, 3, 64, 64), 6).cuda())
+    g, _ = eng.backward(c1, _rand((2, 3, 64, 64), 6).cuda())
     expected = {k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
     assert set(g) == expected and all(torch.isfinite(v).all() for v in g.values())
 
@@ -323,3 +329,30 @@ def test_device_batches_prefetch_matches_host_transform(tmp_path):
             for j, pl in enumerate(planes):
                 assert np.array_equal(pl.cpu().numpy()[None], pixel.transform(want[k][j]))
             k += 1
+
+
+def test_padding_backward_kernels_match_autograd():
+    """dlb_reflect_fold / dlb_stem_window_bwd against torch autograd of F.pad (fp32, pure sums: tight tolerance)."""
+    from deepliif_b200 import ops
+    from deepliif_b200.ops import PAD_REFLECT, PAD_ZERO
+    for (N, H, W, C, p) in [(2, 9, 7, 8, 1), (1, 5, 6, 4, 3), (2, 16, 16, 64, 3), (1, 4, 4, 4, 3), (1, 6, 5, 4, 0)]:
+        x = _rand((N, C, H, W), 1).requires_grad_(True)
+        g = _rand((N, C, H + 2 * p, W + 2 * p), 2)
+        add = _rand((N, H, W, C), 3)
+        (F.pad(x, (p, p, p, p), mode="reflect") * g).sum().backward()
+        got = ops.reflect_fold(g.permute(0, 2, 3, 1).contiguous().cuda(), p, add=add.cuda())
+        want = x.grad.permute(0, 2, 3, 1) + add
+        assert (got.cpu() - want).abs().max().item() < 1e-5, (N, H, W, C, p)
+    for mode, tmode in ((PAD_ZERO, "constant"), (PAD_REFLECT, "reflect")):
+        for (N, C, H, W) in [(2, 3, 12, 10), (1, 1, 8, 8), (1, 8, 5, 9)]:
+            S, p = 7, 3
+            x = _rand((N, C, H, W), 4).requires_grad_(True)
+            dxw = _rand((N, H + 2 * p, W, 64), 5)
+            xp = F.pad(x, (p, p, p, p), mode=tmode)
+            # Xw[n, hp, w, s*8 + c] = xpad[n, c, hp, w + s]
+            xw = torch.zeros((N, H + 2 * p, W, 64))
+            for s_ in range(S):
+                xw[..., s_ * 8:s_ * 8 + C] = xp[:, :, :, s_:s_ + W].permute(0, 2, 3, 1)
+            (xw * dxw).sum().backward()
+            got = ops.stem_window_bwd(dxw.cuda(), C, p, S, mode)
+            assert (got.cpu() - x.grad).abs().max().item() < 1e-5, (mode, N, C, H, W)
