@@ -78,6 +78,13 @@ WG_CASES = [
     ("k7x1_64_64_stem", 1, 22, 40, 64, 64, (7, 1), 1, 0, False, 0),
     ("k3s1_w200", 1, 5, 200, 64, 64, 3, 1, 1, False, 0),
     ("k3s1_tiny", 3, 4, 4, 128, 64, 3, 1, 1, False, 0),
+    # multi-tap kernel edge cases: extents that are not multiples of the 8 x 8 pixel tile, odd outputs, many K splits
+    ("k4s1_63_dlayer", 1, 63, 63, 64, 128, 4, 1, 1, False, 0),
+    ("k3s1_odd_21x19", 2, 21, 19, 64, 128, 3, 1, 1, False, 0),
+    ("k4s2_64_64_dfirst", 2, 64, 64, 64, 64, 4, 2, 1, False, 0),
+    ("ct3s2_128_64_up", 1, 24, 40, 128, 64, 3, 2, 1, True, 1),
+    ("k7x1_head_big", 2, 70, 64, 64, 64, (7, 1), 1, 0, False, 0),
+    ("k3s1_256_256_64x64", 2, 64, 64, 256, 256, 3, 1, 1, False, 0),
 ]
 
 
