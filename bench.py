@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--topology", default="flat5", choices=["flat5", "default"],
                     help="train workload: flat5 = BASELINE configs[3]; default = the reference's default `deepliif train` "
                          "(4 ResNet-9 + 5 UNet-512 seg cascade, 9 n_layers=4 PatchGANs, BatchNorm, dropout, batch 1)")
+    ap.add_argument("--graph", action="store_true", help="train workload: replay the step from a CUDA graph (training.GraphedStep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-events", action="store_true")
     return ap.parse_args()
@@ -579,8 +580,20 @@ def bench_train(args, rank, world, local, dev, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
-        model.set_input(batches[w % 2]); model.optimize_parameters()
+    stepper = training.GraphedStep(model, warmup=2) if args.graph else None
+
+    def one_step(k):
+        if stepper is not None:
+            stepper(batches[k % 2])
+        else:
+            model.set_input(batches[k % 2]); model.optimize_parameters()
+
+    per_step_launches = 0
+    for w in range(max(args.warmup, 3) if stepper is not None else args.warmup):
+        c0 = ops.LAUNCHES["count"]
+        one_step(w)
+        if w == 0:
+            per_step_launches = ops.LAUNCHES["count"] - c0      # an eager step: what one graph replay re-issues
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = ops.LAUNCHES["count"]
@@ -588,7 +601,7 @@ def bench_train(args, rank, world, local, dev, dist):
     e0.record()
     t_h0 = time.perf_counter()
     for k in range(args.steps):
-        model.set_input(batches[k % 2]); model.optimize_parameters()
+        one_step(k)
     t_host = time.perf_counter() - t_h0
     e1.record()
     barrier()
@@ -613,8 +626,10 @@ def bench_train(args, rank, world, local, dev, dist):
                                                   "n_layers=4, BatchNorm, dropout), batch=%d/GPU" % B) if default_topo else
                                                  ("training: pix2pix L1+GAN, 5x (ResNet-9blocks G + 70x70 PatchGAN D), "
                                                   "batch=%d/GPU, flat-bucket all-reduce" % B), "norm": opt.norm,
-                                     "parallelism": "dp%d" % world, "host_enqueue_ms_per_step": t_host * 1e3 / args.steps},
-                          "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
+                                     "parallelism": "dp%d" % world, "host_enqueue_ms_per_step": t_host * 1e3 / args.steps,
+                                     "cuda_graph": stepper is not None},
+                          "clocks": clocks,
+                          "gpu_launches": per_step_launches * args.steps if stepper is not None else ops.LAUNCHES["count"] - l0,
                           "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")}), flush=True)
     if dist is not None:
         dist.destroy_process_group()

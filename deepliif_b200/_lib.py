@@ -34,13 +34,15 @@ SIGNATURES = {
     "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dlb_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                          _i, _f, C.c_ulonglong, _vp, _sz, _vp]),
+                          _i, _f, C.c_ulonglong, _vp, _vp, _sz, _vp]),
     "dlb_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _i, _f, _vp]),
+    "dlb_adam_hyper": (_i, [_f, _f, _f, _i, _f, C.POINTER(_f)]),
+    "dlb_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, _vp, _f, _f, _f, _vp]),
     "dlb_channel_sum": (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _sz, _vp]),
     "dlb_conv_wgrad_workspace": (_sz, [_cd]),
     "dlb_conv_wgrad": (_i, [_cd, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_head_bwd_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _vp]),
+    "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _vp, _vp]),
     "dlb_stem_window_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dlb_head_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dlb_tile_luma_sums": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -138,6 +138,8 @@ TRAIN_DEFAULTS = dict(
 @click.option("--preprocess", type=str, default="resize_and_crop",
               help="resize_and_crop | crop | scale_width | scale_width_and_crop | none")
 @click.option("--no-flip", is_flag=True, help="if specified, do not flip the images for data augmentation")
+@click.option("--cuda-graph", is_flag=True, help="capture the optimisation step in a CUDA graph and replay it per batch "
+                                                   "(single GPU; removes the per-launch host cost that dominates at batch 1)")
 def train(**kw):
     """General-purpose training script for the DeepLIIF multi-task image-to-image translation model."""
     from . import training

@@ -170,6 +170,7 @@ struct ApplyParams {
   float* out_f32; void* out_hi; void* out_lo;
   int N, H, W, C, pad, pad_mode;
   float drop_p; unsigned long long drop_seed;     // training-time nn.Dropout after the activation (0 = off)
+  const unsigned long long* drop_epoch;           // optional device counter mixed into the seed (CUDA-graph replays)
 };
 
 // grid (x: quads of one padded output row, y: rows n*HP + hp).  One thread = 4 channels of one output pixel;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
           if (p.drop_p > 0.f) {
             const unsigned long long e = (static_cast<unsigned long long>(n) * p.H + h) * p.W * p.C + srcs[u];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] *= dropout_scale(p.drop_seed, e + k, p.drop_p);
+            for (int k = 0; k < 4; ++k) o[k] *= dropout_scale(effective_seed(p.drop_seed, p.drop_epoch), e + k, p.drop_p);
           }
           o[0] += rv[u].x; o[1] += rv[u].y; o[2] += rv[u].z; o[3] += rv[u].w;
           if (frow != nullptr && !border[u])
@@ -386,12 +387,13 @@ extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, 
 
 extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                               float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
-                              int pad_mode, float drop_p, unsigned long long drop_seed, dlb_stream_t stream) {
+                              int pad_mode, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_epoch,
+                              dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_apply: C % 4 != 0");
   if (pad < 0 || (pad_mode == DLB_PAD_REFLECT && (pad >= H || pad >= W))) return set_error("dlb_norm_apply: bad pad");
   if (out_hi == nullptr && out_f32 == nullptr) return set_error("dlb_norm_apply: no output");
   if (drop_p < 0.f || drop_p >= 1.f) return set_error("dlb_norm_apply: dropout p must be in [0, 1)");
-  ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode, drop_p, drop_seed};
+  ApplyParams p{y, scale, shift, act, residual, out_f32, out_hi, out_lo, N, H, W, C, pad, pad_mode, drop_p, drop_seed, drop_epoch};
   const int row_quads = (W + 2 * pad) * (C / 4);
   const int rows = N * (H + 2 * pad);
   int gx = (row_quads + 1023) / 1024; if (gx > 64) gx = 64;

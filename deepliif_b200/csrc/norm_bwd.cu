@@ -32,6 +32,7 @@ struct BwdParams {
   int act, N, HW, C;
   int act2;                 // activation of the branch dout2 flows through (UNet: LeakyReLU down path + ReLU skip path)
   float drop_p; unsigned long long drop_seed;   // dropout that followed the activation on the dout branch (0 = off)
+  const unsigned long long* drop_epoch;
 };
 
 // grid (slices, N), block 256: thread = (pixel lane, channel quad); fixed-order merge over the pixel lanes.
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const BwdParams p,
         float dd[4] = {dv.x, dv.y, dv.z, dv.w};
         if (p.drop_p > 0.f) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(p.drop_seed, static_cast<unsigned long long>(off) + k, p.drop_p);
+          for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(effective_seed(p.drop_seed, p.drop_epoch), static_cast<unsigned long long>(off) + k, p.drop_p);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const BwdParams p, 
     float dd[4] = {dv.x, dv.y, dv.z, dv.w};
     if (p.drop_p > 0.f) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(p.drop_seed, static_cast<unsigned long long>(off) + k, p.drop_p);
+      for (int k = 0; k < 4; ++k) dd[k] *= dropout_scale(effective_seed(p.drop_seed, p.drop_epoch), static_cast<unsigned long long>(off) + k, p.drop_p);
     }
     float o[4];
     if (p.scale != nullptr) {
@@ -316,9 +317,9 @@ extern "C" int dlb_norm_bwd(const float* dout, const float* dout2, const float* 
                             const float* mean, const float* rstd, int act, int act2, int N, int HW, int C, int pooled,
                             float* c1, float* c2, float* dgamma, float* dbeta, int accumulate_param_grads,
                             float* dy_f32, void* dy_hi, void* dy_lo, int fmt, float drop_p, unsigned long long drop_seed,
-                            void* workspace, size_t workspace_bytes, dlb_stream_t stream) {
+                            const unsigned long long* drop_epoch, void* workspace, size_t workspace_bytes, dlb_stream_t stream) {
   if (C % 4 != 0) return set_error("dlb_norm_bwd: C % 4 != 0");
-  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C, act2, drop_p, drop_seed};
+  BwdParams p{dout, dout2, y, scale, shift, mean, rstd, act, N, HW, C, act2, drop_p, drop_seed, drop_epoch};
   if (scale != nullptr) {
     const int c4n = C / 4;
     if ((c4n < 256 && 256 % c4n != 0) || (c4n > 256 && c4n % 256 != 0)) return set_error("dlb_norm_bwd: C/4 must divide 256");

@@ -16,6 +16,12 @@ __host__ __device__ __forceinline__ uint32_t dropout_hash(unsigned long long see
   return static_cast<uint32_t>(z >> 32);
 }
 
+// Seed of one layer invocation: the host-drawn seed, advanced by an optional device-resident step counter so that a
+// captured CUDA graph draws a fresh mask on every replay (the forward and the backward of one replay read the same value).
+__device__ __forceinline__ unsigned long long effective_seed(unsigned long long seed, const unsigned long long* epoch) {
+  return epoch ? seed + __ldg(epoch) * 0xD1B54A32D192ED03ULL : seed;
+}
+
 // keep with probability 1 - p; returns the multiplier (0 or 1/(1-p))
 __host__ __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p) {
   const float u = static_cast<float>(dropout_hash(seed, idx) >> 8) * (1.0f / 16777216.0f);   // [0,1)

@@ -143,6 +143,11 @@ class _NormParams:
             self.beta = sd[key + ".bias"].detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+# Optional device uint64 [1] mixed into every dropout seed (set by training.GraphedStep: a captured CUDA graph bakes the
+# host-drawn seeds, the counter makes each replay draw new masks; forward and backward read the same value).
+DROP_EPOCH = [None]
+
+
 class _EngineBase:
     def __init__(self, norm, norm_mode, prec, backend, device):
         if norm not in ("batch", "instance", "none"):
@@ -166,7 +171,8 @@ class _EngineBase:
                pad_mode=PAD_ZERO, drop=None):
         dp, dseed = drop if drop is not None else (0.0, 0)
         f32, hi, lo = ops.norm_apply(y, scale, shift, act, residual, want_f32, want_split, self.prec.fmt, pad,
-                                     pad_mode, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
+                                     pad_mode, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed,
+                                     drop_epoch=DROP_EPOCH[0] if dp > 0 else None)
         return Act(f32, hi, lo, pad)
 
     def _conv(self, layer, act, N, H, W):

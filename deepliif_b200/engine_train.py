@@ -11,6 +11,7 @@ of csrc/rng.cuh (regenerated in backward from (seed, element index)).  Gradients
 names so the nn.Module containers can store them in ``param.grad``."""
 import torch
 
+from . import engine as _engine
 from . import ops
 from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO, Act, ConvLayer, NLayerDEngine,
                      Precision, ResnetEngine, _EngineBase, _NormParams, _pad_cout32)
@@ -70,7 +71,8 @@ class _TrainOps:
         dp, dseed = rec.extra if rec.extra is not None else (0.0, 0)
         f32, hi, lo = ops.norm_bwd(dout, rec.y, rec.sc, rec.sh, rec.mean, rec.rstd, rec.act, dout2=dout2,
                                    pooled=self._pooled(), dgamma=dg, dbeta=db, want_f32=need_f32, want_split=True,
-                                   fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
+                                   fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed,
+                                   drop_epoch=_engine.DROP_EPOCH[0] if dp > 0 else None)
         if dg is not None:
             grads[rec.nkey + ".weight"], grads[rec.nkey + ".bias"] = dg, db
         grads[rec.wkey + ".weight"] = layer.wgrad(rec.x, hi, lo, N, H, W, rec.pad)
@@ -395,7 +397,8 @@ class UnetTrainEngine(_EngineBase, _TrainOps):
             dp, dseed = ctx["u_drop"][lvl] if ctx["u_drop"][lvl] is not None else (0.0, 0)
             f32, hi, lo = ops.norm_bwd(g_below[lvl], ctx["u_raw"][lvl], sc, sh, mean, rstd, ACT_RELU, pooled=self._pooled(),
                                        dgamma=dg, dbeta=db, want_f32=has_bias and not normed, want_split=True,
-                                       fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed)
+                                       fmt=self.prec.fmt, need_lo=self.prec.split, drop_p=dp, drop_seed=dseed,
+                                   drop_epoch=_engine.DROP_EPOCH[0] if dp > 0 else None)
             if dg is not None:
                 grads[self.unkey[lvl] + ".weight"], grads[self.unkey[lvl] + ".bias"] = dg, db
             if has_bias:

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "adam_hyper", "adam_step_dev", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -157,7 +157,7 @@ def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=Fals
 
 def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE, dout2=None, act2=None, pooled=False,
              dgamma=None, dbeta=None, accumulate=False, want_f32=False, want_split=True, fmt=FMT_BF16, need_lo=True,
-             drop_p=0.0, drop_seed=0):
+             drop_p=0.0, drop_seed=0, drop_epoch=None):
     """Backward of norm(+affine)+activation: returns (dy_f32 | None, dy_hi | None, dy_lo | None); writes the
     parameter gradients into dgamma/dbeta (fp32 [C]) when given.  scale=None: layer without norm."""
     _need_cuda(dout, dout2, y, scale, shift, mean, rstd, dgamma, dbeta)
@@ -172,12 +172,28 @@ def norm_bwd(dout, y, scale=None, shift=None, mean=None, rstd=None, act=ACT_NONE
     check(_lib.load().dlb_norm_bwd(_p(dout), _p(dout2), _p(y), _p(scale), _p(shift), _p(mean), _p(rstd), act,
                                    act if act2 is None else act2, N, H * W, Cc,
                                    int(pooled), _p(c1), _p(c2), _p(dgamma), _p(dbeta), int(accumulate), _p(f32), _p(hi),
-                                   _p(lo), fmt, float(drop_p), int(drop_seed), _p(ws), ws.numel() * 4, _stream()), "dlb_norm_bwd")
+                                   _p(lo), fmt, float(drop_p), int(drop_seed), _p(drop_epoch), _p(ws), ws.numel() * 4, _stream()),
+          "dlb_norm_bwd")
     LAUNCHES["count"] += 3 if scale is not None else 1
     return f32, hi, lo
 
 
 _WG_CACHE = {}
+
+
+def adam_hyper(lr, beta1, beta2, step, grad_scale=1.0):
+    """The four step-dependent floats of the update, computed by the library (same arithmetic as dlb_adam_step)."""
+    buf = (C.c_float * 4)()
+    check(_lib.load().dlb_adam_hyper(float(lr), float(beta1), float(beta2), int(step), float(grad_scale), buf), "dlb_adam_hyper")
+    return list(buf)
+
+
+def adam_step_dev(p, g, m, v, hyper_dev, beta1, beta2, eps):
+    """Fused Adam with {lr, bc1, sqrt(bc2), grad_scale} read from the device tensor hyper_dev (graph-capturable)."""
+    _need_cuda(p, g, m, v, hyper_dev)
+    check(_lib.load().dlb_adam_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper_dev), float(beta1), float(beta2),
+                                        float(eps), _stream()), "dlb_adam_step_dev")
+    LAUNCHES["count"] += 1
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
@@ -241,7 +257,7 @@ def head_bwd_pack(dzz_nchw, S, fmt=FMT_BF16, need_lo=True):
 
 
 def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=False, want_split=True,
-               fmt=FMT_BF16, pad=0, pad_mode=PAD_ZERO, need_lo=True, drop_p=0.0, drop_seed=0):
+               fmt=FMT_BF16, pad=0, pad_mode=PAD_ZERO, need_lo=True, drop_p=0.0, drop_seed=0, drop_epoch=None):
     """out = act(y*scale+shift) (+ residual) -> (out_f32 | None, hi | None, lo | None)."""
     _need_cuda(y, scale, shift, residual)
     N, H, W, Cc = y.shape
@@ -252,7 +268,8 @@ def norm_apply(y, scale=None, shift=None, act=ACT_NONE, residual=None, want_f32=
         hi = torch.empty(shp, dtype=_dtype(fmt), device=y.device)
         lo = torch.empty(shp, dtype=_dtype(fmt), device=y.device) if need_lo else None
     check(_lib.load().dlb_norm_apply(_p(y), _p(scale), _p(shift), act, _p(residual), _p(f32), _p(hi), _p(lo), fmt,
-                                     N, H, W, Cc, pad, pad_mode, float(drop_p), int(drop_seed), _stream()), "dlb_norm_apply")
+                                     N, H, W, Cc, pad, pad_mode, float(drop_p), int(drop_seed), _p(drop_epoch), _stream()),
+          "dlb_norm_apply")
     LAUNCHES["count"] += 1
     return f32, hi, lo
 

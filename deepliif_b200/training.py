@@ -122,6 +122,7 @@ class FlatAdam(torch.optim.Optimizer):
             off += al(k)
         self.t = 0
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.hyper_dev = None          # set by GraphedStep: device float[4] the captured Adam launch reads
 
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
@@ -134,12 +135,20 @@ class FlatAdam(torch.optim.Optimizer):
         if self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
 
+    def hyper(self):
+        """{lr, 1-beta1^t, sqrt(1-beta2^t), 1/world} of the *next* update (step t+1)."""
+        g = self.param_groups[0]
+        return ops.adam_hyper(g["lr"], g["betas"][0], g["betas"][1], self.t + 1, 1.0 / self.world)
+
     @torch.no_grad()
     def step(self, closure=None):
-        self.t += 1
         g = self.param_groups[0]
-        ops.adam_step(self.flat, self.grad, self.m, self.v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.t,
-                      1.0 / self.world)
+        if self.hyper_dev is not None:       # graph capture / replay: the host refreshes hyper_dev and counts the steps
+            ops.adam_step_dev(self.flat, self.grad, self.m, self.v, self.hyper_dev, g["betas"][0], g["betas"][1], g["eps"])
+        else:
+            self.t += 1
+            ops.adam_step(self.flat, self.grad, self.m, self.v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.t,
+                          1.0 / self.world)
         networks._EngineBacked.GLOBAL_VERSION += 1        # packed weights of every engine are now stale
 
 
@@ -208,6 +217,111 @@ def deepliif_step(model):
     model.optimizer_G.zero_grad()
     _loss_G(model).backward()
     _sync_and_step(model.optimizer_G)
+
+
+class GraphedStep:
+    """One `optimize_parameters()` (forward, D step, G step, both Adam updates) captured in a CUDA graph and replayed per
+    batch.  At batch 1 the reference's default topology issues ~4400 launches per step and the host, not the GPU, sets
+    the pace; a replay costs one launch.
+
+    What varies between steps lives in device memory the graph reads: the input batch (static tensors refreshed by
+    `copy_`), Adam's {lr, bias corrections} (FlatAdam.hyper_dev) and the dropout step counter (engine.DROP_EPOCH).
+    The first `warmup` calls run eagerly (they also size every cache); the next full batch captures; later ones replay.
+    A batch of another size (the ragged last one) runs eagerly against the same device-resident state."""
+    SLOTS = 4          # pinned staging slots for the per-step state: the host may run this many steps ahead of the GPU
+
+    def __init__(self, model, warmup=2):
+        self.model, self.warmup, self.calls = model, warmup, 0
+        self.graph = None
+        self.opts = [model.optimizer_D, model.optimizer_G]
+        if not all(isinstance(o, FlatAdam) for o in self.opts):
+            raise NotImplementedError("GraphedStep needs the flat-bucket Adam optimizers (--optimizer adam)")
+        if self.opts[0].world > 1:
+            raise NotImplementedError("GraphedStep: single-process only (the NCCL all-reduce is not captured yet)")
+        n = 2 + 4 * len(self.opts)                                   # [dropout epoch (int64 as 2 floats) | 4 floats per Adam]
+        self.host = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(self.SLOTS)]
+        self.done = [None] * self.SLOTS
+        self.state_dev = torch.zeros(n, dtype=torch.float32, device=model.device)
+        self.epoch = 0
+        self.static = None
+        # Eager steps run on a side stream: autograd's AccumulateGrad nodes remember the stream they were created on, and
+        # nodes born on the legacy default stream cannot be joined from a capturing stream.
+        self.side = torch.cuda.Stream(device=model.device)
+
+    def _eager(self, data):
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            self.model.set_input(data)
+            self.model.optimize_parameters()
+        cur.wait_stream(self.side)
+
+    def _upload(self):
+        self.epoch += 1
+        k = self.epoch % self.SLOTS
+        if self.done[k] is not None:
+            self.done[k].synchronize()                              # slot still in flight: wait for that copy only
+        h = self.host[k]
+        h[:2].view(torch.int64)[0] = self.epoch
+        for i, o in enumerate(self.opts):
+            h[2 + 4 * i: 6 + 4 * i] = torch.tensor(o.hyper())
+        self.state_dev.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        self.done[k] = ev
+
+    def _bind(self):
+        from . import engine as _engine
+        for i, o in enumerate(self.opts):
+            o.hyper_dev = self.state_dev[2 + 4 * i: 6 + 4 * i]
+        _engine.DROP_EPOCH[0] = self.state_dev[:2].view(torch.int64)
+
+    @staticmethod
+    def _shape_key(data):
+        A = data["A"]
+        return tuple(A[0].shape if isinstance(A, list) else A.shape)
+
+    def __call__(self, data):
+        model = self.model
+        if self.calls < self.warmup:
+            self._eager(data)
+            self.calls += 1
+            return
+        dev = model.device
+        A = [a.to(dev) for a in data["A"]] if isinstance(data["A"], list) else data["A"].to(dev)
+        B = [b.to(dev) for b in data["B"]]
+        paths = data.get("A_paths", [])
+        self._bind()
+        self._upload()
+        if self.static is not None and self._shape_key(data) != self.static_key:
+            self._eager({"A": A, "B": B, "A_paths": paths})         # ragged batch: eager, same device-resident state
+        else:
+            if self.static is None:
+                self.static = {"A": [a.clone() for a in A] if isinstance(A, list) else A.clone(), "B": [b.clone() for b in B]}
+                self.static_key = self._shape_key(data)
+                model.set_input({**self.static, "A_paths": paths})
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    model.optimize_parameters()
+                # the step's result tensors (losses, visuals) are static outputs of the graph: an eager step in between
+                # rebinds the model attributes, so they are put back after every replay
+                self.outputs = {k: v for k, v in vars(model).items()
+                                if torch.is_tensor(v) and k.startswith(("loss_", "fake_B", "real_"))}
+            else:
+                if isinstance(A, list):
+                    for d, s_ in zip(self.static["A"], A):
+                        d.copy_(s_, non_blocking=True)
+                else:
+                    self.static["A"].copy_(A, non_blocking=True)
+                for d, s_ in zip(self.static["B"], B):
+                    d.copy_(s_, non_blocking=True)
+            model.image_paths = paths
+            self.graph.replay()
+            for k, v in self.outputs.items():
+                setattr(model, k, v)
+        for o in self.opts:
+            o.t += 1
+        self.calls += 1
 
 
 def _sync_and_step(optimizer):
@@ -287,6 +401,7 @@ def run_training(params):
     from .models import networks as nw
     model.schedulers = [nw.get_scheduler(o, opt) for o in model.optimizers]
     model.train()
+    stepper = GraphedStep(model) if params.get("cuda_graph") else None
     total_iters = 0
     for epoch in range(opt.epoch_count, opt.n_epochs + opt.n_epochs_decay + 1):
         if sampler is not None:
@@ -294,8 +409,11 @@ def run_training(params):
         t0 = time.time()
         for data in dl:
             total_iters += opt.batch_size
-            model.set_input(data)
-            model.optimize_parameters()
+            if stepper is not None:
+                stepper(data)
+            else:
+                model.set_input(data)
+                model.optimize_parameters()
             if rank == 0 and total_iters % opt.print_freq < opt.batch_size:
                 losses = model.get_current_losses()
                 print("(epoch: %d, iters: %d) " % (epoch, total_iters) + " ".join("%s: %.3f" % kv for kv in losses.items()),

@@ -98,6 +98,7 @@ int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, con
  * dlb_norm_apply: out = act(y*scale + shift) (+ residual), written as fp32 (out_f32) and/or as split
  *   16-bit planes (out_hi/out_lo) for the next tensor-core conv; `pad` > 0 writes the planes into a
  *   [N, H+2pad, W+2pad, C] buffer with a reflected (DLB_PAD_REFLECT) or zero border.
+ *   drop_epoch (device uint64, may be NULL): added into the seed so a captured CUDA graph draws new masks per replay.
  *   drop_p > 0: training-time nn.Dropout(drop_p) right after the activation (networks.py:493-494, 604-605) with the
  *   counter-based mask keep(seed, element index) of csrc/rng.cuh; dlb_norm_bwd regenerates the same mask. */
 size_t dlb_norm_stats_workspace(int N, int HW, int C);
@@ -109,7 +110,8 @@ int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float
                    size_t workspace_bytes, dlb_stream_t stream);
 int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                    float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
-                   int pad_mode, float drop_p, unsigned long long drop_seed, dlb_stream_t stream);
+                   int pad_mode, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_epoch,
+                   dlb_stream_t stream);
 
 /* ---- training: backward of norm + activation -------------------------------------------------------------------
  * Autograd of BatchNorm2d (batch statistics) / InstanceNorm2d + ReLU / LeakyReLU(0.2) (networks.py:25-44, 391-404,
@@ -122,13 +124,19 @@ int dlb_norm_apply(const float* y, const float* scale, const float* shift, int a
 int dlb_norm_bwd(const float* dout, const float* dout2, const float* y, const float* scale, const float* shift,
                  const float* mean, const float* rstd, int act, int act2, int N, int HW, int C, int pooled, float* c1, float* c2,
                  float* dgamma, float* dbeta, int accumulate_param_grads, float* dy_f32, void* dy_hi, void* dy_lo,
-                 int fmt, float drop_p, unsigned long long drop_seed, void* workspace, size_t workspace_bytes,
-                 dlb_stream_t stream);
+                 int fmt, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_epoch, void* workspace,
+                 size_t workspace_bytes, dlb_stream_t stream);
 
 /* Fused Adam on a flat fp32 bucket (torch.optim.Adam semantics, DeepLIIF_model.py:133-146); g is scaled by grad_scale
  * first (1/world_size after a sum all-reduce).  step counts from 1. */
 int dlb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   int step, float grad_scale, dlb_stream_t stream);
+/* CUDA-graph form: the step-dependent scalars {lr, 1-beta1^t, sqrt(1-beta2^t), grad_scale} are read from device memory
+ * (hyper4_dev), so one captured launch serves every replay; dlb_adam_hyper fills the same four floats on the host with
+ * the arithmetic dlb_adam_step uses (bit-identical updates). */
+int dlb_adam_hyper(float lr, float beta1, float beta2, int step, float grad_scale, float* hyper4_host);
+int dlb_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper4_dev, float beta1,
+                      float beta2, float eps, dlb_stream_t stream);
 
 /* Bias gradient: out[c] (+)= sum_rows x[rows][C] (x = dy as fp32 NHWC, rows = N*OH*OW).  workspace >= 1024*C floats. */
 int dlb_channel_sum(const float* x, long long rows, int C, float* out, int accumulate, void* workspace,

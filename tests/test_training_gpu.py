@@ -356,3 +356,61 @@ def test_padding_backward_kernels_match_autograd():
             (xw * dxw).sum().backward()
             got = ops.stem_window_bwd(dxw.cuda(), C, p, S, mode)
             assert (got.cpu() - x.grad).abs().max().item() < 1e-5, (mode, N, C, H, W)
+
+
+def _tiny_model(tmp_path, no_dropout, seg_gen=False):
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.models import create_model
+    p = dict(TRAIN_DEFAULTS, dataroot=str(tmp_path), checkpoints_dir=str(tmp_path), name="t", gpu_ids=(0,), modalities_no=2,
+             seg_gen=seg_gen, norm="batch", no_dropout=no_dropout, padding="zero", net_g="resnet_2blocks", net_gs="unet_128",
+             batch_size=2)
+    opt = training.build_options(p)
+    torch.manual_seed(0)
+    model = create_model(opt)
+    training.make_optimizers(model)
+    model.train()
+    return model
+
+
+def test_cuda_graph_step_is_bit_identical_to_eager(tmp_path):
+    """GraphedStep (capture once, replay per batch; Adam scalars and the batch read from device memory) must walk the
+    same weights as the eager loop, bit for bit, including a ragged batch in the middle and an lr change."""
+    from deepliif_b200 import training
+    batches = [{"A": _rand((2, 3, 64, 64), 300 + i), "B": [_rand((2, 3, 64, 64), 400 + 10 * i + j) for j in range(2)],
+                "A_paths": []} for i in range(7)]
+    batches[4] = {"A": batches[4]["A"][:1], "B": [b[:1] for b in batches[4]["B"]], "A_paths": []}      # ragged
+    flats = []
+    for graphed in (False, True):
+        model = _tiny_model(tmp_path, no_dropout=True)
+        stepper = training.GraphedStep(model, warmup=2) if graphed else None
+        for i, b in enumerate(batches):
+            if i == 5:
+                for o in (model.optimizer_G, model.optimizer_D):
+                    o.param_groups[0]["lr"] = 1e-4
+            if graphed:
+                stepper(b)
+            else:
+                model.set_input(b); model.optimize_parameters()
+        torch.cuda.synchronize()
+        assert model.optimizer_G.t == len(batches) and model.optimizer_D.t == len(batches)
+        flats.append((model.optimizer_G.flat.clone(), model.optimizer_D.flat.clone(), model.get_current_losses()))
+    assert torch.equal(flats[0][0], flats[1][0]) and torch.equal(flats[0][1], flats[1][1])
+    assert flats[0][2] == flats[1][2]
+
+
+def test_cuda_graph_step_redraws_dropout_masks(tmp_path):
+    """With dropout the host-drawn seeds are baked into the graph; the device step counter must still give every replay
+    its own masks (same batch replayed twice -> different generator losses), forward and backward sharing them."""
+    from deepliif_b200 import training
+    model = _tiny_model(tmp_path, no_dropout=False, seg_gen=True)
+    stepper = training.GraphedStep(model, warmup=1)
+    b = {"A": _rand((2, 3, 128, 128), 500), "B": [_rand((2, 3, 128, 128), 501 + j) for j in range(3)], "A_paths": []}
+    seen = []
+    for _ in range(4):
+        stepper(b)
+        torch.cuda.synchronize()
+        losses = model.get_current_losses()
+        assert all(np.isfinite(v) for v in losses.values())
+        seen.append(model.fake_B_1.detach().float().sum().item())
+    assert stepper.graph is not None and len(set(seen[1:])) == 3
