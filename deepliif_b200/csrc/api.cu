@@ -111,6 +111,31 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     }
     if (S_total > L.S_cap) return set_error("dlb_conv_tc_fwd: statistics workspace slice capacity exceeded");
   }
+  // The output-parity phases of a ConvTranspose2d (and of a stride-2 data gradient) are independent launches.  When one
+  // phase cannot fill the GPU (inner UNet levels: a few CTAs streaming megabytes of weights, latency-bound), the
+  // phases run side by side on helper streams forked from and joined back into the caller's stream (plain event
+  // fork/join: also valid inside a stream capture).
+  cudaStream_t main_stream = reinterpret_cast<cudaStream_t>(stream);
+  bool fork = false;
+  if (np > 1) {
+    int nt_eff = n_tile ? n_tile : (d->Cout >= 256 ? 256 : (d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32)));
+    const long long m_tiles = (static_cast<long long>(d->N) * geo[0].OH * geo[0].OW + 127) / 128;
+    fork = m_tiles * ((d->Cout + nt_eff - 1) / nt_eff) < 74;
+  }
+  static thread_local cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  if (fork) {
+    if (aux[0] == nullptr) {
+      for (int i = 0; i < 3; ++i) {
+        if (cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming) != cudaSuccess) return set_cuda_error("phase streams");
+      }
+      if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return set_cuda_error("phase streams");
+    }
+    if (cudaEventRecord(ev_fork, main_stream) != cudaSuccess) return set_cuda_error("cudaEventRecord(fork)");
+    for (int i = 1; i < np; ++i)
+      if (cudaStreamWaitEvent(aux[i - 1], ev_fork, 0) != cudaSuccess) return set_cuda_error("cudaStreamWaitEvent(fork)");
+  }
   for (int i = 0; i < np; ++i) {
     if (geo[i].ntaps > 16) return set_error("dlb_conv_tc_fwd: more than 16 taps per phase");
     TcPhase ph;
@@ -124,8 +149,14 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
       ph.st_partial = sp.partial; ph.st_cnt = sp.cnt; ph.st_S = sp.S; ph.st_S_cap = sp.S_cap;
       ph.st_slice_base = slice_base[i]; ph.st_S_total = S_total;
     }
-    const int rc = launch_conv_tc_phase(ph, reinterpret_cast<cudaStream_t>(stream));
+    const int rc = launch_conv_tc_phase(ph, (fork && i > 0) ? aux[i - 1] : main_stream);
     if (rc != 0) return rc;
+  }
+  if (fork) {
+    for (int i = 1; i < np; ++i) {
+      if (cudaEventRecord(ev_join[i - 1], aux[i - 1]) != cudaSuccess) return set_cuda_error("cudaEventRecord(join)");
+      if (cudaStreamWaitEvent(main_stream, ev_join[i - 1], 0) != cudaSuccess) return set_cuda_error("cudaStreamWaitEvent(join)");
+    }
   }
   return 0;
 }

@@ -394,10 +394,21 @@ bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank,
 // 128 output pixels per CTA tile = tile_n x tile_h x tile_w (shared with api.cu for the statistics slices).
 // Returns 1 when the phase runs in vertical-strip mode (see TcParams::vs): R x 1 filter, stride 1, one source,
 // all output channels in one N tile, resident weights + two A strips fit in shared memory.
+// UMMA N when the caller leaves it open.  Large layers take the widest tile (A is read once per 256 output channels).
+// Layers with at most a few hundred output pixels per phase (the inner UNet levels, the PatchGAN tail at small batch)
+// are bound by the latency of streaming the weights through a handful of CTAs: there the tile narrows (down to 64)
+// until the grid covers the SMs — four times the CTAs, each with a quarter of the weights and a deeper TMA ring.
+static int auto_n_tile(int cout, long long out_px) {
+  int n = cout >= 256 ? 256 : (cout >= 128 ? 128 : (cout > 32 ? 64 : 32));
+  const long long m_tiles = (out_px + 127) / 128;
+  while (n > 64 && m_tiles <= 4 && m_tiles * ((cout + n - 1) / n) < 148) n >>= 1;
+  return n;
+}
+
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
                   int* tile_h, int* tile_n, int* n_tile_out) {
   int n_tile = n_tile_req;
-  if (n_tile == 0) n_tile = cout >= 256 ? 256 : (cout >= 128 ? 128 : (cout > 32 ? 64 : 32));
+  if (n_tile == 0) n_tile = auto_n_tile(cout, static_cast<long long>(g.N) * g.OH * g.OW);
   *n_tile_out = n_tile;
   int tw = g.OW >= 128 ? 128 : pow2_ceil(g.OW);
   int th = 128 / tw; { int hp = pow2_ceil(g.OH); if (th > hp) th = hp; }
@@ -421,7 +432,7 @@ int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int sp
 // One phase of a convolution on the tensor cores.  See internal.h for the argument contract.
 static void tc_plan_tiles_novs(const TcPhase& ph, int* tile_w, int* tile_h, int* tile_n, int* n_tile_out) {
   int n_tile = ph.n_tile;
-  if (n_tile == 0) n_tile = ph.cout >= 256 ? 256 : (ph.cout >= 128 ? 128 : (ph.cout > 32 ? 64 : 32));
+  if (n_tile == 0) n_tile = auto_n_tile(ph.cout, static_cast<long long>(ph.N) * ph.OH * ph.OW);
   *n_tile_out = n_tile;
   int tw = ph.OW >= 128 ? 128 : pow2_ceil(ph.OW);
   int th = 128 / tw; { int hp = pow2_ceil(ph.OH); if (th > hp) th = hp; }
