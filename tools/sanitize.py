@@ -12,7 +12,11 @@ sd = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "batch", False, 
 x = rnd((1, 3, 64, 64), 1).cuda()
 eng = engine_train.ResnetTrainEngine(sd, n_blocks=1, norm="batch", use_dropout=False, padding_type="zero", norm_mode="batch")
 y, ctx = eng.forward_train(x)
-g = eng.backward(ctx, rnd((1, 3, 64, 64), 2).cuda())
+g, dx0 = eng.backward(ctx, rnd((1, 3, 64, 64), 2).cuda(), need_dx=True)
+sdq = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "batch", True, "reflect"), 8, "stress")
+engq = engine_train.ResnetTrainEngine(sdq, n_blocks=1, norm="batch", use_dropout=True, padding_type="reflect", norm_mode="batch")
+yq, cq = engq.forward_train(x)
+gq, dxq = engq.backward(cq, rnd((1, 3, 64, 64), 9).cuda(), need_dx=True)
 sdu = nets.make_state_dict(nets.unet_param_shapes(5, 64, 3, 3, "batch"), 4, "stress")
 u = engine_train.UnetTrainEngine(sdu, num_downs=5, norm="batch", norm_mode="batch")
 yu, cu = u.forward_train(rnd((1, 3, 32, 32), 3).cuda())
@@ -25,5 +29,12 @@ sdr = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "instance", Fal
 yr = engine.ResnetEngine(sdr, n_blocks=1, norm="instance", padding_type="reflect").forward(x)
 _, u8, mask = ops.seg_finish([yr], [1.0])
 t = ops.u8_to_f32(u8)
+# cell post-processing (union-find labelling, statistics, classification, boundaries)
+from oracle import cells
+from deepliif_b200 import postprocessing
+orig, seg, marker = cells.synth_case(70, 93, 3)
+ov, rf, sc = postprocessing.compute_final_results(orig, seg, marker, "40x", marker_thresh="default")
+ov2, rf2, sc2 = postprocessing.compute_final_results(orig, seg, None, "40x", od_thresh_lower=20, od_thresh_upper=330, size_thresh=None)
 torch.cuda.synchronize()
+print("cells", sc, sc2)
 print("sanitize run ok", float(y.abs().sum()), float(yu.abs().sum()), float(yd.abs().sum()), int(mask.sum()))
