@@ -94,7 +94,7 @@ def _seg_weights(opt, seg_weights):
     return [1 / (opt.modalities_no + 1)] * (opt.modalities_no + 1)
 
 
-def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=4, n_streams=2):
+def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3):
     """uint8 tiles [T,ts,ts,3] (numpy) -> dict[name -> uint8 [T,ts,ts,3]] with the reference's result keys
     (G1.., G{S}, and per-modality seg G{S}k), skipping empty tiles exactly like run_wrapper (:399-443)."""
     gens, segs = _names(opt)

@@ -17,7 +17,7 @@ from . import ops
 
 
 class TilePipeline:
-    def __init__(self, gens, segs=None, seg_weights=None, micro_batch=4, thresh=120, n_streams=1):
+    def __init__(self, gens, segs=None, seg_weights=None, micro_batch=8, thresh=120, n_streams=3):
         """gens: list of callables fp32 NCHW -> fp32 NCHW (modalities).  segs: None (flat: last of `gens` is the
         seg head) or list of len(gens)+1 seg generators (cascade)."""
         self.gens, self.segs = list(gens), (list(segs) if segs is not None else None)
