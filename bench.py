@@ -311,7 +311,7 @@ def main():
                     "peak_kind": f"{peak_kind} cuBLAS bf16 sustained; bf16x3 executes 3 MMAs per algorithmic MAC "
                                  f"(ceiling = 1/3)" if args.precision.endswith("x3") else peak_kind}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU leg is a single-GPU-run item (rank 0, N=1 only)
             v, s_per, cores = cpu_flat5_tiles_per_s(args.norm, 1, 1)
             cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
                    "sample": "1 tile x 5 ResNet-9 generators, N=1 per call, torch fp32 CPU (oracle port), best of {16,32,64,all} threads, 1 warm-up", "host_cores": os.cpu_count()}
@@ -459,7 +459,7 @@ def bench_postprocess(args, rank, world, local, dev, dist):
                              "frac": alg_bytes / (dev_ms / 1e3) / 1e9 / pk[1], "peak_source": pk[2], "traffic": None,
                              "note": "whole device pipeline (all kernels of the function; host threshold step excluded); "
                                      "algorithmic bytes = 15 B/pixel"}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             t0 = time.perf_counter()
             C.compute_final_results(o, s_, m, "40x", **kw)
             dt = time.perf_counter() - t0

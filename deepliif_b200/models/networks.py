@@ -318,11 +318,12 @@ def get_scheduler(optimizer, opt):
 class GANLoss(nn.Module):
     """vanilla -> BCEWithLogits, lsgan -> MSE against a constant label map (networks.py:244-317)."""
 
-    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0):
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0, label_smoothing=0.0):
         super().__init__()
         self.register_buffer("real_label", torch.tensor(target_real_label))
         self.register_buffer("fake_label", torch.tensor(target_fake_label))
         self.gan_mode = gan_mode
+        self.label_smoothing = label_smoothing
         if gan_mode == "lsgan":
             self.loss = nn.MSELoss()
         elif gan_mode == "vanilla":
@@ -333,7 +334,11 @@ class GANLoss(nn.Module):
             raise NotImplementedError("gan mode %s not implemented" % gan_mode)
 
     def get_target_tensor(self, prediction, target_is_real):
-        return (self.real_label if target_is_real else self.fake_label).expand_as(prediction)
+        # networks.py:278-292: real labels are scaled by (1 - s), fake labels by s (with the default labels 1 / 0 the
+        # fake target therefore stays 0 — kept as the reference has it)
+        if target_is_real:
+            return self.real_label.expand_as(prediction) * (1 - self.label_smoothing)
+        return self.fake_label.expand_as(prediction) * self.label_smoothing
 
     def __call__(self, prediction, target_is_real):
         if self.gan_mode in ("lsgan", "vanilla"):
