@@ -155,39 +155,63 @@ def _round_div_half_even(num, den):
 
 
 class CellTable:
-    """The reference's cellsinfo list (7-tuples: count, positive, marker, x0, y0, cx, cy) held as columns."""
-    __slots__ = ("count", "positive", "marker", "x0", "y0", "cx", "cy")
+    """The reference's cellsinfo list (7-tuples: count, positive, marker, x0, y0, cx, cy) held as columns.  The
+    centroids are only materialised when the list is asked for (compute_final_results never reads them)."""
+    __slots__ = ("count", "positive", "marker", "x0", "y0", "sum_x", "sum_y")
 
     def __len__(self):
         return int(self.count.shape[0])
+
+    @property
+    def cx(self):
+        return _round_div_half_even(self.sum_x, self.count)
+
+    @property
+    def cy(self):
+        return _round_div_half_even(self.sum_y, self.count)
 
     def as_tuples(self):
         return list(zip(self.count.tolist(), self.positive.tolist(), self.marker.tolist(), self.x0.tolist(),
                         self.y0.tolist(), self.cx.tolist(), self.cy.tolist()))
 
 
-def create_kde(values, count, bandwidth=1.0):
-    """postprocessing.py:365-403: Gaussian KDE of `values` on `count` bins (float64 sums stored as float32).  Cell
+def _kde_bins(uniq, mult, n, step, b0, b1, bandwidth=1.0):
+    """Bins b0..b1-1 of the reference's Gaussian KDE (postprocessing.py:365-403; float64 sums stored as float32).  Cell
     sizes repeat, so the kernel is evaluated once per distinct value and weighted by its multiplicity."""
     c = 1 / math.sqrt(2 * math.pi)
-    step = (float(values.max()) + 1) / count
-    n = values.shape[0]
-    uniq, mult = np.unique(values, return_counts=True)
-    x = (np.arange(count, dtype=np.float64) * step)[:, None]
+    x = (np.arange(b0, b1, dtype=np.float64) * step)[:, None]
     val = (x - uniq[None, :]) * (1 / bandwidth)
-    total = (np.exp(-(val * val / 2)) * c) @ mult.astype(np.float64)
-    return (total / (n * bandwidth)).astype(np.float32), step
+    total = (np.exp(-(val * val / 2)) * c) @ mult
+    return (total / (n * bandwidth)).astype(np.float32)
+
+
+def create_kde(values, count, bandwidth=1.0):
+    """postprocessing.py:365-403 -> (kde float32 [count], step)."""
+    step = (float(values.max()) + 1) / count
+    uniq, mult = np.unique(values, return_counts=True)
+    return _kde_bins(uniq, mult.astype(np.float64), values.shape[0], step, 0, count, bandwidth), step
 
 
 def calculate_default_size_threshold(cell_sizes, resolution="40x"):
-    """postprocessing.py:406-447."""
+    """postprocessing.py:406-447.  Only the first interior local minimum of the KDE is used, so the bins are evaluated in
+    blocks from the left and the evaluation stops at the block that contains it (same index as scanning the full KDE)."""
     cell_sizes = np.asarray(cell_sizes, dtype=np.int64)
     if cell_sizes.shape[0] <= 1:
         return 0
-    kde, step = create_kde(np.sqrt(cell_sizes), 500)
-    interior = (kde[1:-1] < kde[:-2]) & (kde[1:-1] < kde[2:])
-    hits = np.flatnonzero(interior)
-    idx = int(hits[0]) + 1 if hits.size else 1
+    values = np.sqrt(cell_sizes)
+    count = 500
+    step = (float(values.max()) + 1) / count
+    uniq, mult = np.unique(values, return_counts=True)
+    mult = mult.astype(np.float64)
+    idx, kde, block = 1, np.zeros(0, np.float32), 64
+    for b0 in range(0, count, block):
+        kde = np.concatenate([kde, _kde_bins(uniq, mult, values.shape[0], step, b0, min(count, b0 + block))])
+        m = kde.shape[0]                                   # interior bins 1 .. m-2 are decidable now
+        interior = (kde[1:m - 1] < kde[:m - 2]) & (kde[1:m - 1] < kde[2:m])
+        hits = np.flatnonzero(interior)
+        if hits.size:
+            idx = int(hits[0]) + 1
+            break
     thresh_sqrt = (idx - 1) * step
     lo, default, hi = {"20x": (3, 4, 6), "10x": (2, 2, 3)}.get(resolution, (4, 7, 10))
     if thresh_sqrt < lo:
@@ -287,7 +311,7 @@ def _cells_device(seg_d, marker_d, resolution, noise_thresh, seg_thresh, large_n
     cells.count, cells.positive = cnt, t[:, 1] >= t[:, 2]
     cells.marker = _round_div_half_even(t[:, 3], cnt) if use_od else t[:, 3]
     cells.x0, cells.y0 = t[:, 4], t[:, 5]
-    cells.cx, cells.cy = _round_div_half_even(t[:, 6], cnt), _round_div_half_even(t[:, 7], cnt)
+    cells.sum_x, cells.sum_y = t[:, 6], t[:, 7]
     defaults = {"size_thresh": calculate_default_size_threshold(cells.count, resolution)}
     if marker_d is not None and not use_od:
         defaults["marker_thresh"] = calculate_default_marker_threshold_from_hist(hist.cpu().numpy())

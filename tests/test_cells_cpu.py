@@ -87,7 +87,7 @@ def test_host_threshold_logic_matches_oracle():
         n = int(rng.integers(0, 400))
         tab = P.CellTable()
         tab.count = rng.integers(1, 500, n); tab.positive = rng.random(n) < 0.5; tab.marker = rng.integers(0, 400, n)
-        tab.x0 = tab.y0 = tab.cx = tab.cy = np.zeros(n, np.int64)
+        tab.x0 = tab.y0 = tab.sum_x = tab.sum_y = np.zeros(n, np.int64)
         kept = np.sort(rng.choice(2 * n + 1, n, replace=False)) if n else np.zeros(0, np.int64)
         kw = [dict(), dict(marker_thresh=200), dict(size_thresh_upper=300), dict(od_thresh_lower=50, od_thresh_upper=350),
               dict(od_thresh_upper=100, marker_thresh=20)][t % 5]
