@@ -14,7 +14,7 @@ import torch
 from . import engine as _engine
 from . import ops
 from .engine import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, PAD_REFLECT, PAD_ZERO, Act, ConvLayer, NLayerDEngine,
-                     Precision, ResnetEngine, _EngineBase, _NormParams, _pad_cout32)
+                     Precision, ResnetEngine, _EngineBase, _NormParams)
 
 
 class _Rec:

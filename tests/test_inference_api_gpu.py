@@ -178,7 +178,6 @@ class _Stub(torch.nn.Module):
 def test_legacy_names_and_serialized_pt_dirs_load_identically(tmp_path):
     """(i) legacy Zenodo naming latest_net_G51..G55 and (ii) a `deepliif serialize` directory of
     TorchScript archives G1.pt.. give the same images as the S-named .pth directory with the same weights."""
-    import shutil
     from deepliif_b200.models import infer_modalities, init_nets
     mdir, sds = _write_model_dir(tmp_path, net_g="resnet_2blocks", net_gs="unet_128", n_blocks=2)
     # _write_model_dir builds 9-block / unet_512 shapes: rewrite the files for the small topology
