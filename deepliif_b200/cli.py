@@ -101,7 +101,12 @@ TRAIN_DEFAULTS = dict(
     save_by_iter=False, continue_train=False, epoch_count=1, phase="train", lr_policy="linear", n_epochs=100,
     n_epochs_decay=100, optimizer="adam", beta1=0.5, lr_g=0.0002, lr_d=0.0002, lr_decay_iters=50, gan_mode="vanilla",
     gan_mode_s="lsgan", pool_size=50, seed=None, modalities_no=4, seg_gen=True, print_freq=100, dataset_mode="aligned",
-    input_no=1, scale_size=512, with_val=False, precision="bf16x3")
+    input_no=1, scale_size=512, with_val=False, precision="bf16x3",
+    # written to train_opt.txt with the reference's defaults so that the reference can read a directory trained here
+    # (its BaseModel reads opt.remote_transfer_cmd, base_model.py:49); the visdom / html ones are inert in this package
+    label_smoothing=0.0, display_freq=400, display_ncols=4, display_id=1, display_server="http://localhost", display_env="main",
+    display_port=8097, update_html_freq=1000, no_html=False, remote=False, remote_transfer_cmd=None, model_dir_teacher="",
+    net_ds="n_layers", local_rank=None, debug=False, debug_data_size=10, monitor_image=None)
 
 
 @cli.command()

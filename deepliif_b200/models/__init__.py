@@ -157,8 +157,8 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
         opt = get_opt(model_path)
     for k, v in opt_args.items():
         setattr(opt, k, v)
-    if seg_weights is None and hasattr(opt, "seg_weights"):
-        seg_weights = opt.seg_weights
+    # seg_weights=None means equal weights 1/(modalities_no+1), as in the reference's run_dask (:299-306): only the
+    # `deepliif test` command passes opt.seg_weights down (cli.py:878, 906), a direct API call does not read them
     nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
     grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
     tiles = grid.tiles()

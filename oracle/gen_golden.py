@@ -149,7 +149,65 @@ def dataset_fixture():
     save("aligned_dataset", **arrs)
 
 
+E2E_IMAGE = (600, 700, 31)          # H, W, seed of the synthetic IHC region (2 x 2 tiles of 512 with overlap 32)
+
+
+def e2e_image():
+    """Seeded, smooth-ish synthetic RGB region (low-pass noise: tiles are far from is_empty())."""
+    H, W, seed = E2E_IMAGE
+    rng = np.random.default_rng(seed)
+    small = rng.integers(0, 256, size=(H // 8 + 2, W // 8 + 2, 3)).astype(np.float32)
+    img = np.kron(small, np.ones((8, 8, 1), np.float32))[:H, :W]
+    img = 0.75 * img + 0.25 * rng.integers(0, 256, size=(H, W, 3)).astype(np.float32)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def e2e_state_dicts():
+    """The nine generators of the default topology with the seeds tests/test_inference_api_gpu.py::_write_model_dir uses."""
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, 9, "batch", True, "zero")
+    s_shapes = nets.unet_param_shapes(9, 64, 3, 3, "batch")
+    sds = {f"G{i}": nets.make_state_dict(g_shapes, 50 + i, "stress") for i in range(1, 5)}
+    sds.update({f"GS{i}": nets.make_state_dict(s_shapes, 60 + i, "stress") for i in range(5)})
+    return sds
+
+
+def e2e_fixture():
+    """End-to-end pin: the reference's own `infer_modalities` (deepliif/models/__init__.py:613-660: InferenceTiler, run_dask
+    per tile, stitching, output naming, postprocess) on a seeded 600 x 700 region with a model directory whose
+    train_opt.txt was written by deepliif_b200.options (format interchange) and whose nine .pth files hold the seeded
+    state_dicts above.  Stored: per output image a subsample + checksums, and the scoring dict."""
+    import tempfile
+    from PIL import Image
+    import_reference()
+    import deepliif.models as RM
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.options import print_options
+    root = tempfile.mkdtemp()
+    # exactly what `python -m deepliif_b200.cli train` writes (CLI defaults), read back below by the reference
+    p = dict(TRAIN_DEFAULTS, dataroot=root, checkpoints_dir=root, name="m", gpu_ids=(0,),
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25])
+    print_options(training.build_options(p), save=True)
+    mdir = os.path.join(root, "m")
+    for k, sd in e2e_state_dicts().items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    img = Image.fromarray(e2e_image())
+    torch.set_num_threads(os.cpu_count())
+    images, scoring = RM.infer_modalities(img, 512, mdir, eager_mode=True, return_seg_intermediate=True)
+    arrs = {"names": np.frombuffer(json.dumps(sorted(images)).encode(), dtype=np.uint8),
+            "scoring": np.frombuffer(json.dumps(scoring, sort_keys=True).encode(), dtype=np.uint8)}
+    for k, im in images.items():
+        a = np.asarray(im)
+        arrs[f"{k}__sub"] = a[::7, ::5].copy()
+        arrs[f"{k}__sum"] = checksum(a)
+        arrs[f"{k}__shape"] = np.array(a.shape)
+    print("e2e outputs:", sorted(images), scoring)
+    save("e2e_infer_modalities", **arrs)
+
+
 def main():
+    if "e2e" in sys.argv[1:]:
+        return e2e_fixture()
     if "cells" in sys.argv[1:]:
         return cells_fixture()
     if "dataset" in sys.argv[1:]:
@@ -276,6 +334,7 @@ def main():
     save("tiler", **arrs)
     cells_fixture()
     dataset_fixture()
+    e2e_fixture()
     print("all fixtures written to", OUT)
 
 

@@ -37,7 +37,7 @@ def _write_model_dir(root, net_g="resnet_9blocks", net_gs="unet_512", n_blocks=9
     return mdir, sds
 
 
-def _oracle_cascade(x, sds, net_gs):
+def _oracle_cascade(x, sds, net_gs, weights=(0.2, 0.2, 0.2, 0.2, 0.2)):
     torch.set_num_threads(min(32, os.cpu_count()))
     cfg = dict(n_blocks=9, norm="batch", use_dropout=True, padding_type="zero", norm_mode="sample")
     with torch.no_grad():
@@ -47,7 +47,7 @@ def _oracle_cascade(x, sds, net_gs):
         else:
             run_s = lambda t, sd: nets.resnet_forward(t, sd, **{**cfg, "padding_type": "reflect"})
         return nets.deepliif_forward(x, [sds[f"G{i}"] for i in range(1, 5)], [sds[f"GS{i}"] for i in range(5)],
-                                     [0.25, 0.15, 0.25, 0.1, 0.25], run_g, run_s)
+                                     list(weights), run_g, run_s)
 
 
 def test_infer_modalities_matches_oracle_cascade(tmp_path):
@@ -79,6 +79,13 @@ def test_infer_modalities_matches_oracle_cascade(tmp_path):
     mism = int((mask_ref != mask_got).sum())
     print(f"posneg mask pixel mismatches vs oracle-from-fp32: {mism} of {mask_ref.size}")
     assert mism <= 0.005 * mask_ref.size
+    # explicit seg_weights (what `deepliif test` passes down from train_opt.txt, cli.py:878): same parts, other weights
+    w2 = [0.25, 0.15, 0.25, 0.1, 0.25]
+    images2, _ = infer_modalities(Image.fromarray(img), 512, mdir, seg_weights=w2)
+    seg2 = pixel.seg_aggregate([p.numpy() for p in parts], w2)
+    d2 = np.abs(np.asarray(images2["Seg"]).astype(np.int32) - pixel.tensor2im(seg2).astype(np.int32))
+    assert d2.max() <= 1 and float((d2 > 0).mean()) < 0.02
+    assert np.abs(np.asarray(images2["Seg"]).astype(np.int32) - np.asarray(images["Seg"]).astype(np.int32)).max() > 1
     # postprocess (models/__init__.py:582-591): integer work on the stitched uint8 images -> bit-exact vs the oracle
     from oracle import cells
     ov, rf, sc = cells.compute_final_results(img, np.asarray(images["Seg"]), np.asarray(images["mod4-Marker"]), "40x")
@@ -206,3 +213,32 @@ def test_legacy_names_and_serialized_pt_dirs_load_identically(tmp_path):
         assert set(got) == set(base)
         for k in base:
             assert np.array_equal(np.asarray(got[k]), np.asarray(base[k])), (d, k)
+
+
+def test_infer_modalities_matches_reference_end_to_end_golden(tmp_path):
+    """tests/golden/e2e_infer_modalities.npz = the reference's own infer_modalities (tiling, per-tile cascade, stitching,
+    naming, postprocess) on a seeded 600 x 700 region, reading a model directory written by this package's trainer
+    options.  Same directory + image here: names, shapes and the scoring dict must be equal, every uint8 image within
+    1 LSB (fp32 outputs agree to ~1e-4, so a pixel can straddle a quantisation step)."""
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.models import infer_modalities
+    from deepliif_b200.options import print_options
+    from oracle.gen_golden import e2e_image, e2e_state_dicts
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "e2e_infer_modalities.npz"))
+    p = dict(TRAIN_DEFAULTS, dataroot=str(tmp_path), checkpoints_dir=str(tmp_path), name="m", gpu_ids=(0,),
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25])
+    print_options(training.build_options(p), save=True)
+    mdir = os.path.join(str(tmp_path), "m")
+    for k, sd in e2e_state_dicts().items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    images, scoring = infer_modalities(Image.fromarray(e2e_image()), 512, mdir, return_seg_intermediate=True)
+    assert sorted(images) == json.loads(bytes(gold["names"]).decode())
+    assert json.dumps(scoring, sort_keys=True) == bytes(gold["scoring"]).decode()
+    for k, im in images.items():
+        a = np.asarray(im)
+        assert list(a.shape) == gold[f"{k}__shape"].tolist(), k
+        d = np.abs(a[::7, ::5].astype(np.int32) - gold[f"{k}__sub"].astype(np.int32))
+        frac = float((d > 0).mean())
+        print(f"{k}: max |d| {d.max()} LSB, {100 * frac:.3f}% of the sampled bytes differ")
+        assert d.max() <= 1 and frac < 0.02, k
