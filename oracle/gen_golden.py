@@ -205,7 +205,74 @@ def e2e_fixture():
     save("e2e_infer_modalities", **arrs)
 
 
+TRAIN_CASE = dict(modalities_no=2, seg_gen=True, net_g="resnet_2blocks", net_gs="unet_128", norm="batch", no_dropout=True,
+                  padding="zero", batch_size=1, hw=128)
+
+
+def train_state_dicts(case=TRAIN_CASE):
+    """Seeded state_dicts for every network of the small training topology (names as DeepLIIF_model.py:72-113)."""
+    n, norm = case["modalities_no"], case["norm"]
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, 2, norm, not case["no_dropout"], case["padding"])
+    s_shapes = nets.unet_param_shapes(7, 64, 3, 3, norm)
+    d_shapes = nets.nlayer_d_param_shapes(4, 64, 6, norm)
+    sds = {}
+    for i in range(n):
+        sds[f"G{i + 1}"] = nets.make_state_dict(g_shapes, 700 + i, "reference")
+        sds[f"D{i + 1}"] = nets.make_state_dict(d_shapes, 720 + i, "reference")
+    for i in range(n + 1):
+        sds[f"GS{i}"] = nets.make_state_dict(s_shapes, 740 + i, "reference")
+        sds[f"DS{i}"] = nets.make_state_dict(d_shapes, 760 + i, "reference")
+    return sds
+
+
+def train_batch(case=TRAIN_CASE):
+    hw, B, n = case["hw"], case["batch_size"], case["modalities_no"]
+    return {"A": seeded_input(800, B, 3, hw, hw), "B": [seeded_input(801 + i, B, 3, hw, hw) for i in range(n + 1)],
+            "A_paths": ["synthetic"] * B}
+
+
+def train_params(root, case=TRAIN_CASE):
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    return dict(TRAIN_DEFAULTS, dataroot=root, checkpoints_dir=root, name="t", gpu_ids=(),
+                **{k: v for k, v in case.items() if k != "hw"})
+
+
+def train_step_fixture():
+    """One `optimize_parameters()` of the reference's own DeepLIIFModel (DeepLIIF_model.py:431-467) on CPU: seeded weights
+    in all ten networks (2 ResNet G, 3 UNet seg G, 5 PatchGAN D), a seeded batch, VGG term patched to zero (it needs a
+    downloaded VGG19; lambda_feat is not part of the north star).  Stored: the 14 losses and the post-step values of two
+    small weight tensors per optimizer."""
+    import tempfile
+    import_reference()
+    N = reference_networks()
+    import deepliif.models as RM
+    from deepliif_b200 import training
+
+    class NoVGG(torch.nn.Module):
+        def forward(self, x, y):
+            return torch.zeros((), device=x.device)
+    N.VGGLoss = lambda *a, **k: NoVGG()
+    root = tempfile.mkdtemp()
+    opt = training.build_options(train_params(root))
+    opt.gpu_ids = []
+    torch.manual_seed(0)
+    model = RM.create_model(opt)
+    model.setup(opt)
+    for name, sd in train_state_dicts().items():
+        getattr(model, "net" + name).load_state_dict(sd)
+    model.set_input(train_batch())
+    model.optimize_parameters()
+    losses = {k: float(v) for k, v in model.get_current_losses().items()}
+    print("reference losses:", losses)
+    arrs = {"losses": np.frombuffer(json.dumps(losses, sort_keys=True).encode(), dtype=np.uint8)}
+    for name, key in (("G1", "model.1.weight"), ("GS0", "model.model.0.weight"), ("D1", "model.0.weight"), ("DS2", "model.0.weight")):
+        arrs[f"{name}__{key}"] = getattr(model, "net" + name).state_dict()[key].detach().numpy().copy()
+    save("train_step", **arrs)
+
+
 def main():
+    if "train" in sys.argv[1:]:
+        return train_step_fixture()
     if "e2e" in sys.argv[1:]:
         return e2e_fixture()
     if "cells" in sys.argv[1:]:
@@ -335,6 +402,7 @@ def main():
     cells_fixture()
     dataset_fixture()
     e2e_fixture()
+    train_step_fixture()
     print("all fixtures written to", OUT)
 
 
