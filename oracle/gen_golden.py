@@ -270,7 +270,38 @@ def train_step_fixture():
     save("train_step", **arrs)
 
 
+SCHED_CASES = [dict(lr_policy="linear", n_epochs=3, n_epochs_decay=4, epoch_count=1, lr_decay_iters=50),
+               dict(lr_policy="linear", n_epochs=100, n_epochs_decay=100, epoch_count=98, lr_decay_iters=50),
+               dict(lr_policy="step", n_epochs=3, n_epochs_decay=4, epoch_count=1, lr_decay_iters=2),
+               dict(lr_policy="cosine", n_epochs=5, n_epochs_decay=4, epoch_count=1, lr_decay_iters=50)]
+
+
+def lr_sequence(get_scheduler, case, epochs=9, lr=2e-4):
+    class O:
+        pass
+    o = O()
+    for k, v in case.items():
+        setattr(o, k, v)
+    w = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([w], lr=lr)
+    sch = get_scheduler(opt, o)
+    out = [opt.param_groups[0]["lr"]]
+    for _ in range(epochs):
+        opt.step(); sch.step()
+        out.append(opt.param_groups[0]["lr"])
+    return np.asarray(out, dtype=np.float64)
+
+
+def scheduler_fixture():
+    """Learning-rate sequences of the reference's get_scheduler (networks.py:55-81), stepped once per epoch as
+    BaseModel.update_learning_rate does (base_model.py:132-141)."""
+    N = reference_networks()
+    save("schedulers", **{f"c{i}": lr_sequence(N.get_scheduler, c) for i, c in enumerate(SCHED_CASES)})
+
+
 def main():
+    if "sched" in sys.argv[1:]:
+        return scheduler_fixture()
     if "train" in sys.argv[1:]:
         return train_step_fixture()
     if "e2e" in sys.argv[1:]:
@@ -403,6 +434,7 @@ def main():
     dataset_fixture()
     e2e_fixture()
     train_step_fixture()
+    scheduler_fixture()
     print("all fixtures written to", OUT)
 
 

@@ -174,3 +174,12 @@ def test_unknown_names_raise_like_the_reference():
         networks.define_D(6, 64, "nonsense")
     with pytest.raises(NotImplementedError):
         networks.get_norm_layer("nonsense")
+
+
+def test_lr_schedulers_match_reference_golden():
+    """get_scheduler (networks.py:55-81) stepped per epoch: linear / step / cosine sequences equal the reference's."""
+    from deepliif_b200.models.networks import get_scheduler
+    from oracle.gen_golden import SCHED_CASES, lr_sequence
+    z = np.load(os.path.join(GOLD, "schedulers.npz"))
+    for i, case in enumerate(SCHED_CASES):
+        assert np.array_equal(lr_sequence(get_scheduler, case), z[f"c{i}"]), case
