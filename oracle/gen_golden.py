@@ -270,6 +270,36 @@ def train_step_fixture():
     save("train_step", **arrs)
 
 
+INIT_CASES = [("G", "resnet_9blocks", "batch", True), ("G", "unet_512", "batch", True), ("G", "resnet_6blocks", "instance", False),
+              ("D", "n_layers", "batch", 4), ("D", "basic", "instance", 3)]
+
+
+def init_signature(networks_module, case, seed=3):
+    """Per-tensor (sum, sum of |.|, first element) of a freshly initialised network under torch.manual_seed(seed)."""
+    kind, arch, norm, extra = case
+    torch.manual_seed(seed)
+    if kind == "G":
+        net = networks_module.define_G(3, 3, 64, arch, norm, extra, "normal", 0.02, [], "zero")
+    else:
+        net = networks_module.define_D(6, 64, arch, extra, norm, "normal", 0.02, [])
+    sd = net.state_dict()
+    keys = list(sd)
+    sig = np.array([[float(v.double().sum()), float(v.double().abs().sum()), float(v.reshape(-1)[0])] if v.numel() else [0, 0, 0]
+                    for v in sd.values()], dtype=np.float64)
+    return keys, sig
+
+
+def init_fixture():
+    """define_G / define_D + init_weights (networks.py:84-238): same seed -> the same initial weights, tensor by tensor."""
+    N = reference_networks()
+    arrs = {}
+    for i, case in enumerate(INIT_CASES):
+        keys, sig = init_signature(N, case)
+        arrs[f"c{i}_keys"] = np.frombuffer(json.dumps(keys).encode(), dtype=np.uint8)
+        arrs[f"c{i}_sig"] = sig
+    save("init_weights", **arrs)
+
+
 SCHED_CASES = [dict(lr_policy="linear", n_epochs=3, n_epochs_decay=4, epoch_count=1, lr_decay_iters=50),
                dict(lr_policy="linear", n_epochs=100, n_epochs_decay=100, epoch_count=98, lr_decay_iters=50),
                dict(lr_policy="step", n_epochs=3, n_epochs_decay=4, epoch_count=1, lr_decay_iters=2),
@@ -300,6 +330,8 @@ def scheduler_fixture():
 
 
 def main():
+    if "init" in sys.argv[1:]:
+        return init_fixture()
     if "sched" in sys.argv[1:]:
         return scheduler_fixture()
     if "train" in sys.argv[1:]:
@@ -435,6 +467,7 @@ def main():
     e2e_fixture()
     train_step_fixture()
     scheduler_fixture()
+    init_fixture()
     print("all fixtures written to", OUT)
 
 

@@ -183,3 +183,16 @@ def test_lr_schedulers_match_reference_golden():
     z = np.load(os.path.join(GOLD, "schedulers.npz"))
     for i, case in enumerate(SCHED_CASES):
         assert np.array_equal(lr_sequence(get_scheduler, case), z[f"c{i}"]), case
+
+
+def test_same_seed_gives_the_reference_initial_weights():
+    """define_G / define_D + init_weights consume torch's RNG exactly as the reference does (networks.py:84-238): under
+    the same seed every tensor of a fresh network equals the reference's (keys, order and values)."""
+    import json
+    from deepliif_b200.models import networks
+    from oracle.gen_golden import INIT_CASES, init_signature
+    z = np.load(os.path.join(GOLD, "init_weights.npz"))
+    for i, case in enumerate(INIT_CASES):
+        keys, sig = init_signature(networks, case)
+        assert keys == json.loads(bytes(z[f"c{i}_keys"]).decode()), case
+        assert np.array_equal(sig, z[f"c{i}_sig"]), case
