@@ -270,6 +270,43 @@ def train_step_fixture():
     save("train_step", **arrs)
 
 
+def options_model_dir(root, legacy=False):
+    """A model directory as `deepliif_b200.cli train` leaves it (train_opt.txt from the CLI defaults + empty checkpoint
+    files: only their names matter for Options(mode='test'))."""
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.options import print_options
+    p = dict(TRAIN_DEFAULTS, dataroot=root, checkpoints_dir=root, name="m", gpu_ids=(0,),
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25])
+    print_options(training.build_options(p), save=True)
+    mdir = os.path.join(root, "m")
+    names = ["G1", "G2", "G3", "G4"] + ([f"G5{i}" for i in range(1, 6)] if legacy else [f"GS{i}" for i in range(5)])
+    for k in names:
+        open(os.path.join(mdir, f"latest_net_{k}.pth"), "wb").close()
+    return mdir
+
+
+def options_as_json(opt, root):
+    d = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(opt).items() if k not in ("checkpoints_dir", "dataroot")}
+    return json.dumps(d, sort_keys=True, default=str).replace(root, "<root>")
+
+
+def options_fixture():
+    """Options(path_file=train_opt.txt, mode='test') (deepliif/options/__init__.py:76-217): every attribute the reference
+    derives for inference (scale_size, mod_id_seg / input_id from the checkpoint names, modalities_names, seg_weights,
+    is_train/phase overrides ...) for a new-style (GS0..) and a legacy (G51..) directory."""
+    import tempfile
+    import_reference()
+    from deepliif.options import Options as RefOptions
+    arrs = {}
+    for tag, legacy in (("new", False), ("legacy", True)):
+        root = tempfile.mkdtemp()
+        mdir = options_model_dir(root, legacy)
+        arrs[tag] = np.frombuffer(options_as_json(RefOptions(path_file=os.path.join(mdir, "train_opt.txt"), mode="test"), root).encode(),
+                                  dtype=np.uint8)
+    save("options_test_mode", **arrs)
+
+
 INIT_CASES = [("G", "resnet_9blocks", "batch", True), ("G", "unet_512", "batch", True), ("G", "resnet_6blocks", "instance", False),
               ("D", "n_layers", "batch", 4), ("D", "basic", "instance", 3)]
 
@@ -330,6 +367,8 @@ def scheduler_fixture():
 
 
 def main():
+    if "options" in sys.argv[1:]:
+        return options_fixture()
     if "init" in sys.argv[1:]:
         return init_fixture()
     if "sched" in sys.argv[1:]:
@@ -468,6 +507,7 @@ def main():
     train_step_fixture()
     scheduler_fixture()
     init_fixture()
+    options_fixture()
     print("all fixtures written to", OUT)
 
 

@@ -196,3 +196,19 @@ def test_same_seed_gives_the_reference_initial_weights():
         keys, sig = init_signature(networks, case)
         assert keys == json.loads(bytes(z[f"c{i}_keys"]).decode()), case
         assert np.array_equal(sig, z[f"c{i}_sig"]), case
+
+
+def test_test_mode_options_equal_the_reference(tmp_path):
+    """Options(path_file, mode='test') on a directory written by this package's trainer: every attribute equals what the
+    reference's Options derives from the same files (new GS0.. naming and legacy G51.. naming)."""
+    import json
+    from deepliif_b200.options import Options
+    from oracle.gen_golden import options_as_json, options_model_dir
+    z = np.load(os.path.join(GOLD, "options_test_mode.npz"))
+    for tag, legacy in (("new", False), ("legacy", True)):
+        root = str(tmp_path / tag)
+        os.makedirs(root)
+        mdir = options_model_dir(root, legacy)
+        got = json.loads(options_as_json(Options(path_file=os.path.join(mdir, "train_opt.txt"), mode="test"), root))
+        want = json.loads(bytes(z[tag]).decode())
+        assert got == want, {k: (got.get(k), want.get(k)) for k in set(got) | set(want) if got.get(k) != want.get(k)}
