@@ -109,48 +109,67 @@ TRAIN_DEFAULTS = dict(
     net_ds="n_layers", local_rank=None, debug=False, debug_data_size=10, monitor_image=None)
 
 
+# `deepliif train`: every option of the reference command (cli.py:72-193), same names and defaults.  Options that only
+# drive the visdom / html dashboards are accepted and written to train_opt.txt but have no effect here.
+_TRAIN_OPTIONS = [
+    # name, kwargs
+    ("--dataroot", dict(required=True, type=str, help="path to images (must have the subfolder train)")),
+    ("--name", dict(default="experiment_name")),
+    ("--gpu-ids", dict(type=int, multiple=True, help="one GPU per process; several GPUs: trainlaunch / torchrun")),
+    ("--checkpoints-dir", dict(default="./checkpoints")),
+    ("--modalities-no", dict(default=4, type=int)),
+    ("--modalities-names", dict(default="", type=str, help="comma-separated names of the input and target modalities")),
+    ("--model", dict(default="DeepLIIF", type=str)),
+    ("--model-dir-teacher", dict(default="", type=str)),
+    ("--seg-weights", dict(default="", type=str, help="comma-separated weights of the seg generators' outputs")),
+    ("--loss-weights-g", dict(default="", type=str)),
+    ("--loss-weights-d", dict(default="", type=str)),
+    ("--input-nc", dict(default=3)), ("--output-nc", dict(default=3)), ("--ngf", dict(default=64)), ("--ndf", dict(default=64)),
+    ("--net-d", dict(default="n_layers")), ("--net-g", dict(default="resnet_9blocks")), ("--n-layers-d", dict(default=4)),
+    ("--norm", dict(default="batch")), ("--init-type", dict(default="normal")), ("--init-gain", dict(default=0.02)),
+    ("--no-dropout", dict(is_flag=True)), ("--upsample", dict(default="convtranspose")),
+    ("--label-smoothing", dict(type=float, default=0.0)), ("--direction", dict(default="AtoB")),
+    ("--serial-batches", dict(is_flag=True)), ("--num-threads", dict(default=4)), ("--batch-size", dict(default=1)),
+    ("--load-size", dict(default=512)), ("--crop-size", dict(default=512)), ("--max-dataset-size", dict(type=int, default=None)),
+    ("--preprocess", dict(type=str, default=None, help="resize_and_crop | crop | scale_width | scale_width_and_crop | none")),
+    ("--no-flip", dict(is_flag=True)), ("--display-winsize", dict(default=512)), ("--epoch", dict(default="latest")),
+    ("--load-iter", dict(default=0)), ("--verbose", dict(is_flag=True)), ("--lambda-L1", dict(default=100.0)),
+    ("--is-train", dict(is_flag=True, default=True)), ("--continue-train", dict(is_flag=True)), ("--epoch-count", dict(type=int, default=0)),
+    ("--phase", dict(default="train")), ("--n-epochs", dict(type=int, default=100)), ("--n-epochs-decay", dict(type=int, default=100)),
+    ("--optimizer", dict(type=str, default="adam")), ("--beta1", dict(default=0.5)), ("--lr-g", dict(default=0.0002)),
+    ("--lr-d", dict(default=0.0002)), ("--lr-policy", dict(default="linear")), ("--lr-decay-iters", dict(type=int, default=50)),
+    ("--seed", dict(type=int, default=None)), ("--display-freq", dict(default=400)), ("--display-ncols", dict(default=4)),
+    ("--display-id", dict(default=1)), ("--display-server", dict(default="http://localhost")), ("--display-env", dict(default="main")),
+    ("--display-port", dict(default=8097)), ("--update-html-freq", dict(default=1000)), ("--print-freq", dict(default=100)),
+    ("--no-html", dict(is_flag=True)), ("--save-latest-freq", dict(default=500)), ("--save-epoch-freq", dict(default=100)),
+    ("--save-by-iter", dict(is_flag=True)), ("--remote", dict(type=bool, default=False)),
+    ("--remote-transfer-cmd", dict(type=str, default=None)), ("--dataset-mode", dict(type=str, default="aligned")),
+    ("--padding", dict(type=str, default="zero")), ("--seg-gen", dict(type=bool, default=True)),
+    ("--net-ds", dict(type=str, default="n_layers")), ("--net-gs", dict(type=str, default="unet_512")),
+    ("--gan-mode", dict(type=str, default="vanilla")), ("--gan-mode-s", dict(type=str, default="lsgan")),
+    ("--local-rank", dict(type=int, default=None)), ("--with-val", dict(is_flag=True)), ("--debug", dict(is_flag=True)),
+    ("--debug-data-size", dict(default=10, type=int)), ("--monitor-image", dict(default=None)),
+    # additions of this package
+    ("--precision", dict(default="bf16x3", help="bf16x3 (fp32-parity split operands) | bf16 (single pass)")),
+    ("--cuda-graph", dict(is_flag=True, help="capture the optimisation step in a CUDA graph and replay it per batch "
+                                             "(single GPU; removes the per-launch host cost that dominates at batch 1)")),
+]
+
+
+def _with_options(specs):
+    def deco(f):
+        for name, kw in reversed(specs):
+            f = click.option(name, **kw)(f)
+        return f
+    return deco
+
+
 @cli.command()
-@click.option("--dataroot", required=True, help="path to images (should have subfolders train, val)")
-@click.option("--name", default="experiment_name")
-@click.option("--checkpoints-dir", default="./checkpoints")
-@click.option("--gpu-ids", type=int, multiple=True)
-@click.option("--batch-size", default=1)
-@click.option("--modalities-no", default=4, type=int)
-@click.option("--seg-gen", type=bool, default=True)
-@click.option("--net-g", default="resnet_9blocks")
-@click.option("--net-gs", default="unet_512")
-@click.option("--net-d", default="n_layers")
-@click.option("--norm", default="batch")
-@click.option("--no-dropout", is_flag=True)
-@click.option("--padding", default="zero")
-@click.option("--n-epochs", default=100)
-@click.option("--n-epochs-decay", default=100)
-@click.option("--lr-g", default=0.0002)
-@click.option("--lr-d", default=0.0002)
-@click.option("--optimizer", default="adam")
-@click.option("--gan-mode", default="vanilla")
-@click.option("--gan-mode-s", default="lsgan")
-@click.option("--seed", type=int, default=None)
-@click.option("--save-epoch-freq", default=100)
-@click.option("--print-freq", default=100)
-@click.option("--continue-train", is_flag=True)
-@click.option("--epoch", default="latest")
-@click.option("--num-threads", default=4)
-@click.option("--max-dataset-size", type=int, default=None)
-@click.option("--serial-batches", is_flag=True, help="take images in order to make batches, otherwise at random")
-@click.option("--load-size", default=512, help="scale images to this size")
-@click.option("--crop-size", default=512, help="then crop to this size")
-@click.option("--preprocess", type=str, default="resize_and_crop",
-              help="resize_and_crop | crop | scale_width | scale_width_and_crop | none")
-@click.option("--no-flip", is_flag=True, help="if specified, do not flip the images for data augmentation")
-@click.option("--cuda-graph", is_flag=True, help="capture the optimisation step in a CUDA graph and replay it per batch "
-                                                   "(single GPU; removes the per-launch host cost that dominates at batch 1)")
+@_with_options(_TRAIN_OPTIONS)
 def train(**kw):
     """General-purpose training script for the DeepLIIF multi-task image-to-image translation model."""
     from . import training
-    params = dict(TRAIN_DEFAULTS)
-    params.update({k: v for k, v in kw.items() if v is not None})
-    training.run_training(params)
+    training.run_training(training.prepare_train_params(kw))
 
 
 @cli.command(context_settings=dict(ignore_unknown_options=True, allow_extra_args=True))

@@ -147,23 +147,27 @@ __global__ void __launch_bounds__(256) head_bwd_pack_kernel(const float* __restr
   }
 }
 
-// is_empty() support (deepliif/models/__init__.py:391-396, util/__init__.py:478-485): per-tile sums of the PIL 'L' luma
-// L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 and of L^2, as exact 64-bit integers (order-independent, so the
-// atomics are deterministic); the host turns them into the variance.  grid (blocks_per_tile, N), block 256.
+// is_empty() support (deepliif/models/__init__.py:391-396, util/__init__.py:478-485): per tile, over the pixels whose
+// PIL 'L' luma L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 is neither 0 nor 255 (the reference drops saturated black /
+// white before taking the variance): their count, sum of L and sum of L^2 as exact 64-bit integers (order-independent,
+// so the atomics are deterministic); the host turns them into the variance.  grid (blocks_per_tile, N), block 256.
 __global__ void __launch_bounds__(256) tile_luma_sums_kernel(const uint8_t* __restrict__ img, int HW,
                                                              unsigned long long* __restrict__ sums) {
   const int n = blockIdx.y;
-  unsigned long long s1 = 0, s2 = 0;
+  unsigned long long s0 = 0, s1 = 0, s2 = 0;
   for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < HW; px += gridDim.x * blockDim.x) {
     const uint8_t* q = img + (static_cast<long long>(n) * HW + px) * 3;
     const unsigned int L = (19595u * q[0] + 38470u * q[1] + 7471u * q[2] + 0x8000u) >> 16;
-    s1 += L; s2 += L * L;
+    if (L != 0u && L != 255u) { s0 += 1; s1 += L; s2 += L * L; }
   }
   for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, o);
     s1 += __shfl_down_sync(0xffffffffu, s1, o);
     s2 += __shfl_down_sync(0xffffffffu, s2, o);
   }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[n * 2], s1); atomicAdd(&sums[n * 2 + 1], s2); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[n * 3], s0); atomicAdd(&sums[n * 3 + 1], s1); atomicAdd(&sums[n * 3 + 2], s2);
+  }
 }
 
 int grid1d(long long total) {
@@ -224,10 +228,10 @@ extern "C" int dlb_head_bwd_pack(const float* dzz_nchw, int N, int H, int W, int
   return 0;
 }
 
-// sums: uint64 [N][2] (sum L, sum L^2), zeroed by this call.
+// sums: uint64 [N][3] (count, sum L, sum L^2 over the pixels with 0 < L < 255), zeroed by this call.
 extern "C" int dlb_tile_luma_sums(const uint8_t* img_nhwc, int N, int H, int W, unsigned long long* sums,
                                   dlb_stream_t stream) {
-  if (cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 2 * N, stream) != cudaSuccess) return set_cuda_error("memset");
+  if (cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 3 * N, stream) != cudaSuccess) return set_cuda_error("memset");
   int bx = (H * W + 255) / 256; if (bx > 64) bx = 64;
   tile_luma_sums_kernel<<<dim3(bx, N), 256, 0, stream>>>(img_nhwc, H * W, sums);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("tile_luma_sums_kernel launch");

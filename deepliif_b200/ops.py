@@ -322,15 +322,18 @@ def head_finish(z, bias, W, S, CO, act=ACT_TANH):
 
 
 def tile_gray_variance(img_nhwc):
-    """uint8 [N,H,W,3] on device -> float64 numpy [N]: population variance of the PIL 'L' luma of every tile."""
+    """uint8 [N,H,W,3] on device -> float64 numpy [N]: population variance of the PIL 'L' luma of every tile over its
+    pixels with 0 < L < 255 (0.0 when there is none), the statistic of the reference's is_empty()."""
     _need_cuda(img_nhwc)
     N, H, W, _ = img_nhwc.shape
-    sums = torch.empty((N, 2), dtype=torch.int64, device=img_nhwc.device)
+    sums = torch.empty((N, 3), dtype=torch.int64, device=img_nhwc.device)
     check(_lib.load().dlb_tile_luma_sums(_p(img_nhwc), N, H, W, _p(sums), _stream()), "dlb_tile_luma_sums")
     LAUNCHES["count"] += 1
     s = sums.cpu().numpy().astype("float64")
-    n = float(H * W)
-    return s[:, 1] / n - (s[:, 0] / n) ** 2
+    n = s[:, 0].clip(min=1.0)
+    var = s[:, 2] / n - (s[:, 1] / n) ** 2
+    var[s[:, 0] == 0] = 0.0
+    return var
 
 
 def u8_to_f32(img_nhwc):

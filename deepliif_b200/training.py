@@ -335,6 +335,84 @@ def _sync_and_step(optimizer):
 # -------------------------------------------------------------------------------------------------------------------
 # `deepliif train`
 # -------------------------------------------------------------------------------------------------------------------
+def default_weights(model, modalities_no, default):
+    """cli.py:349-355: the 4-modality DeepLIIF model has hand-set defaults, every other size gets equal weights."""
+    if model in ("DeepLIIF", "DeepLIIFKD") and modalities_no == 4:
+        return list(default)
+    if model in ("DeepLIIF", "DeepLIIFKD"):
+        return [1 / (modalities_no + 1)] * (modalities_no + 1)
+    return [1 / modalities_no] * modalities_no
+
+
+def _weights_arg(v, model, n, default):
+    if v is None or (isinstance(v, str) and len(v) == 0):
+        return default_weights(model, n, default)
+    return [float(x) for x in v.split(",")] if isinstance(v, str) else [float(x) for x in v]
+
+
+def prepare_train_params(kw):
+    """The option prologue of the reference's `deepliif train` (cli.py:213-380), same rules in the same order: seg_no from
+    seg_gen, validation only with a seg generator, zero padding when a seed asks for determinism, input_no / scale_size
+    read off the first training image, modalities names, background colours of empty tiles, one architecture per
+    generator, seg / loss weights (defaults, comma-separated strings, sanity checks) -> the dict Options() is built from."""
+    from PIL import Image
+    from .util import infer_background_colors
+    d = dict(kw)
+    model, n = d["model"], d["modalities_no"]
+    if model not in ("DeepLIIF",):
+        raise NotImplementedError(f"model class {model} is outside the B200 hot-path scope (only DeepLIIF is built)")
+    d["seg_no"] = 1 if d["seg_gen"] else 0
+    if not d["seg_gen"]:
+        d["with_val"] = False
+    if d.get("optimizer", "adam") != "adam":
+        print(f"Optimizer torch.optim.{d['optimizer']} is not tested. Be careful about the parameters of the optimizer.")
+    gpu_ids = tuple(d.get("gpu_ids") or ())
+    if gpu_ids and gpu_ids[0] == -1:
+        raise SystemExit("deepliif_b200 has no CPU path: --gpu-ids -1 is not available")
+    if d.get("seed") is not None:
+        d["padding"] = "zero"
+        print("padding type is forced to zero padding, because neither refection pad2d or replication pad2d has a "
+              "deterministic implementation")
+    dir_train = os.path.join(d["dataroot"], "train")
+    fns = sorted(x for x in os.listdir(dir_train) if x.endswith(".png"))
+    print(f"{len(fns)} images found")
+    img = Image.open(os.path.join(dir_train, fns[0]))
+    print("image shape:", img.size)
+    num_img = img.size[0] / img.size[1]
+    assert int(num_img) == num_img, f"img size {img.size[0]} / {img.size[1]} = {num_img} is not an integer"
+    input_no = int(num_img) - n - d["seg_no"]
+    assert input_no > 0, (f"inferred number of input images is {input_no} (modalities_no {n}, seg_no {d['seg_no']}); "
+                          "should be greater than 0")
+    names = d.get("modalities_names") or ""
+    names = [x.strip() for x in names.split(",") if len(x) > 0] if isinstance(names, str) else list(names)
+    assert len(names) == 0 or len(names) == input_no + n, \
+        f"--modalities-names has {len(names)} entries ({names}), expecting 0 or {input_no + n} entries"
+    d.update(input_no=input_no, modalities_names=names, scale_size=img.size[1], gpu_ids=gpu_ids, lambda_identity=0, pool_size=0)
+    if d["seg_gen"]:
+        colors = infer_background_colors(dir_train, sample_size=10, input_no=input_no, modalities_no=n, seg_no=d["seg_no"],
+                                         tile_size=32, return_list=True)
+        if colors is not None:
+            d["background_colors"] = colors
+    net_g = d["net_g"].split(",") if isinstance(d["net_g"], str) else list(d["net_g"])
+    assert len(net_g) in (1, n), ("net_g should contain either 1 architecture for all translation generators or the same "
+                                  f"number of architectures as the number of translation generators ({n})")
+    net_gs = d["net_gs"].split(",") if isinstance(d["net_gs"], str) else list(d["net_gs"])
+    assert len(net_gs) in (1, d["seg_no"]), ("net_gs should contain either 1 architecture for all segmentation generators "
+                                             f"or the same number of architectures as the number of segmentation generators ({d['seg_no']})")
+    d["net_g"] = net_g * n if len(net_g) == 1 else net_g
+    d["net_gs"] = net_gs * (n + d["seg_no"]) if len(net_gs) == 1 else net_gs
+    seg_w = _weights_arg(d.get("seg_weights"), model, n, [0.25, 0.15, 0.25, 0.1, 0.25])
+    lw_g = _weights_arg(d.pop("loss_weights_g", None), model, n, [0.2] * 5)
+    lw_d = _weights_arg(d.pop("loss_weights_d", None), model, n, [0.2] * 5)
+    assert sum(seg_w) == 1, "seg weights should add up to 1"
+    assert sum(lw_g) == 1, "loss weights g should add up to 1"
+    assert sum(lw_d) == 1, "loss weights d should add up to 1"
+    for name, w in (("seg weights", seg_w), ("loss weights g", lw_g), ("loss weights d", lw_d)):
+        assert len(w) == n + 1, f"{name} should have the same number of elements as number of modalities to be generated"
+    d.update(seg_weights=seg_w, loss_G_weights=lw_g, loss_D_weights=lw_d)
+    return d
+
+
 def build_options(params):
     from .options import Options
     p = dict(params)
@@ -342,8 +420,8 @@ def build_options(params):
     targets = n + (1 if p["seg_gen"] else 0)
     p.setdefault("seg_no", 1 if p["seg_gen"] else 0)
     p["seg_weights"] = p.get("seg_weights") or [1 / (n + 1)] * (n + 1)
-    p["loss_G_weights"] = p.pop("loss_weights_g", None) or [1 / targets] * targets
-    p["loss_D_weights"] = p.pop("loss_weights_d", None) or [1 / targets] * targets
+    p["loss_G_weights"] = p.pop("loss_weights_g", None) or p.get("loss_G_weights") or [1 / targets] * targets
+    p["loss_D_weights"] = p.pop("loss_weights_d", None) or p.get("loss_D_weights") or [1 / targets] * targets
     p.setdefault("modalities_names", [f"mod{i}" for i in range(n + 1)])
     opt = Options(d_params=p, mode="train")
     opt.gpu_ids = list(p.get("gpu_ids") or [int(os.environ.get("LOCAL_RANK", "0"))])
@@ -399,26 +477,61 @@ def run_training(params):
     model.schedulers = [nw.get_scheduler(o, opt) for o in model.optimizers]
     model.train()
     stepper = GraphedStep(model) if params.get("cuda_graph") else None
+    # ---- the reference's loop (cli.py:404-572): epochs epoch_count .. n_epochs + n_epochs_decay inclusive, counters in
+    # images, `latest` every save_latest_freq images, an epoch checkpoint every save_epoch_freq epochs, lr step per epoch.
+    # Validation (--with-val) and the visdom / html dashboards are not part of this package.
+    if getattr(opt, "with_val", False) and rank == 0:
+        print("--with-val: validation metrics need the reference's dashboard stack and are skipped here")
     total_iters = 0
-    for epoch in range(opt.epoch_count, opt.n_epochs + opt.n_epochs_decay + 1):
-        if sampler is not None:
+    epoch_base = 0
+    if getattr(opt, "continue_train", False):
+        try:
+            epoch_base = int(opt.epoch)
+        except (TypeError, ValueError):
+            epoch_base = 0
+    log_name = os.path.join(opt.checkpoints_dir, opt.name, "loss_log.txt")
+    if rank == 0:
+        os.makedirs(os.path.dirname(log_name), exist_ok=True)
+        with open(log_name, "a") as f:
+            f.write("================ Training Loss (%s) ================\n" % time.strftime("%c"))
+    last_epoch = opt.n_epochs + opt.n_epochs_decay
+    for epoch in range(opt.epoch_count, last_epoch + 1):
+        if sampler is not None and not opt.serial_batches:
             sampler.set_epoch(epoch)
-        t0 = time.time()
+        t0 = iter_data_time = time.time()
+        epoch_iter, t_data = 0, 0.0
         for data in dl:
+            iter_start_time = time.time()
+            if total_iters % opt.print_freq == 0:
+                t_data = iter_start_time - iter_data_time
             total_iters += opt.batch_size
+            epoch_iter += opt.batch_size
             if stepper is not None:
                 stepper(data)
             else:
                 model.set_input(data)
                 model.optimize_parameters()
-            if rank == 0 and total_iters % opt.print_freq < opt.batch_size:
+            if rank == 0 and total_iters % opt.print_freq == 0:
                 losses = model.get_current_losses()
-                print("(epoch: %d, iters: %d) " % (epoch, total_iters) + " ".join("%s: %.3f" % kv for kv in losses.items()),
-                      flush=True)
-        if rank == 0 and (epoch % opt.save_epoch_freq == 0 or epoch == opt.n_epochs + opt.n_epochs_decay):
-            model.save_networks("latest"); model.save_networks(epoch)
+                t_comp = (time.time() - iter_start_time) / opt.batch_size
+                message = "(epoch: %d, iters: %d, time: %.3f, data: %.3f) " % (epoch, epoch_iter, t_comp, t_data)
+                message += "".join("%s: %.3f " % kv for kv in losses.items())
+                print(message, flush=True)
+                with open(log_name, "a") as f:
+                    f.write("%s\n" % message)
+            if rank == 0 and total_iters % opt.save_latest_freq == 0:
+                print("saving the latest model (epoch %d, total_iters %d)" % (epoch, total_iters))
+                model.save_networks("iter_%d" % total_iters if opt.save_by_iter else "latest")
+            iter_data_time = time.time()
+            if getattr(opt, "debug", False) and epoch_iter >= opt.debug_data_size:
+                print(f"debug mode, epoch {epoch} stopped at epoch iter {epoch_iter} (>= {opt.debug_data_size})")
+                break
+        if rank == 0 and epoch % opt.save_epoch_freq == 0 and not (getattr(opt, "continue_train", False) and epoch == 0):
+            print("saving the model at the end of epoch %d, iters %d" % (epoch, total_iters))
+            model.save_networks("latest")
+            model.save_networks(epoch + epoch_base)
         if rank == 0:
-            print("End of epoch %d / %d \t Time Taken: %d sec" % (epoch, opt.n_epochs + opt.n_epochs_decay, time.time() - t0))
+            print("End of epoch %d / %d \t Time Taken: %d sec" % (epoch, last_epoch, time.time() - t0))
         model.update_learning_rate()
     if world > 1:
         dist.barrier()

@@ -2,6 +2,8 @@
 
 ``TileGrid`` restates ``InferenceTiler``'s geometry on arrays so that all tiles of an image are produced as one
 uint8 batch (for TilePipeline) and stitched back with the same centre-crop + border-strip rule."""
+import os
+
 import numpy as np
 import torch
 
@@ -31,10 +33,83 @@ def enable_batchnorm_tracking_stats(model):
 
 
 def image_variance_gray(img_u8_hwc):
-    """Variance of the ITU-R 601 luma (PIL 'L' conversion) of an RGB tile (util/__init__.py:478-485)."""
+    """Variance of the ITU-R 601 luma (PIL 'L' conversion) of an RGB tile over the pixels that are neither saturated
+    white (255) nor black (0); 0 when no such pixel exists (util/__init__.py:478-485)."""
     a = np.asarray(img_u8_hwc).astype(np.int64)
-    gray = (a[..., 0] * 19595 + a[..., 1] * 38470 + a[..., 2] * 7471 + 0x8000) >> 16
-    return float(np.var(gray.astype(np.uint8)))
+    gray = ((a[..., 0] * 19595 + a[..., 1] * 38470 + a[..., 2] * 7471 + 0x8000) >> 16).astype(np.uint8)
+    val = gray[(gray != 255) & (gray != 0)]
+    return float(np.var(val)) if val.shape[0] else 0.0
+
+
+def is_empty(tile):
+    """models/__init__.py:391-396: a tile (or every tile of a list) whose unsaturated gray variance is below 9."""
+    if isinstance(tile, list):
+        return all(image_variance_gray(t) < 9 for t in tile)
+    return image_variance_gray(tile) < 9
+
+
+def _pad_cols(mod, tile_size):
+    w = mod.shape[1]
+    return np.pad(mod, ((0, 0), (0, tile_size - w % tile_size), (0, 0))) if w % tile_size else mod
+
+
+def infer_background_colors_for_img(img, input_no=1, modalities_no=4, seg_no=1, tile_size=32):
+    """util/__init__.py:421-470.  `img` = one training row (input | modalities | seg), uint8 [h, num_img*h, 3].  Boxes of
+    the seg image(s) that are empty (is_empty) mark background; the mean colour of the same boxes in every modality image
+    is that modality's background colour.  None when the row has no empty box."""
+    a = np.asarray(img)
+    h = a.shape[0]
+    num_img = int(a.shape[1] / h)
+    if h % tile_size:                      # PIL's crop pads boxes that stick out of the image with black
+        a = np.pad(a, ((0, tile_size - h % tile_size), (0, 0), (0, 0)))
+    boxes_per_seg = []
+    for i in range(num_img - seg_no, num_img):
+        mod = _pad_cols(a[:, h * i:h * (i + 1)], tile_size)
+        boxes = []
+        for x in range(0, h, tile_size):
+            for y in range(0, h, tile_size):
+                if is_empty(mod[y:y + tile_size, x:x + tile_size]):
+                    boxes.append((x, y))
+        boxes_per_seg.append(boxes)
+    if len(boxes_per_seg) > 1:
+        final = set()                      # the reference intersects with an empty set here: no box survives
+        for b in boxes_per_seg:
+            final = final & set(b)
+        final = list(final)
+    else:
+        final = boxes_per_seg[0]
+    if len(final) == 0:
+        return None
+    colors = {}
+    for i in range(input_no, modalities_no + input_no):
+        mod = _pad_cols(a[:, h * i:h * (i + 1)], tile_size)
+        tiles = np.stack([mod[y:y + tile_size, x:x + tile_size] for x, y in final], axis=0)
+        img_avg = np.mean(tiles, axis=0)
+        colors[i] = np.mean(img_avg, axis=(0, 1)).astype(np.uint8)
+    return colors
+
+
+def infer_background_colors(dir_data, sample_size=5, input_no=1, modalities_no=4, seg_no=1, tile_size=32, return_list=False):
+    """util/__init__.py:380-418: average the per-image background colours of the first `sample_size` training rows that
+    have empty boxes (files are taken in sorted order here; the reference takes os.listdir order)."""
+    from PIL import Image
+    fns = sorted(x for x in os.listdir(dir_data) if x.endswith(".png"))
+    sample_size = min(sample_size, len(fns))
+    acc, count = {}, 0
+    while count < sample_size and len(fns) > 0:
+        fn = fns.pop(0)
+        img = np.asarray(Image.open(os.path.join(dir_data, fn)).convert("RGB"))
+        c = infer_background_colors_for_img(img, input_no, modalities_no, seg_no, tile_size)
+        if c is not None:
+            count += 1
+            for k, v in c.items():
+                acc.setdefault(k, []).append(v)
+    if count == 0:
+        print("None of the images have empty tiles for estimating averge background color. Try with a proper tile size.")
+        return None
+    print(f"Calculating average color for empty tiles from {count} images..")
+    out = {k: np.mean(v, axis=0).astype(np.uint8) for k, v in acc.items()}
+    return [tuple(int(x) for x in e) for e in out.values()] if return_list else out
 
 
 class TileGrid:

@@ -182,8 +182,9 @@ int dlb_head_bwd_pack(const float* dzz_nchw, int N, int H, int W, int S, int CO,
  *   (util/util.py:130-135) + create_posneg_mask (postprocessing.py:163-190) in one pass:
  *   seg = sum_k w_k * segs[k] (fp32, list order); u8 = trunc((seg+1)/2*255); mask from u8.
  *   segs: nseg device pointers to fp32 NCHW [N,3,H,W]; seg_f32 / seg_u8 (NHWC) / mask may be NULL. */
-/* is_empty() support (models/__init__.py:391-396): exact per-tile integer sums of the PIL 'L' luma and its square,
- * sums = uint64 [N][2]; variance = s2/n - (s1/n)^2 on the host (tiles below 9 skip the networks). */
+/* is_empty() support (models/__init__.py:391-396, util/__init__.py:478-485): per tile, over the pixels whose PIL 'L' luma
+ * is neither 0 nor 255 (the reference drops saturated pixels first): sums = uint64 [N][3] = count n, sum, sum of squares
+ * (exact integers); variance = s2/n - (s1/n)^2 on the host, 0 when n = 0 (tiles below 9 skip the networks). */
 int dlb_tile_luma_sums(const uint8_t* img_nhwc, int N, int H, int W, unsigned long long* sums, dlb_stream_t stream);
 int dlb_u8_to_f32(const uint8_t* img_nhwc, float* out_nchw, int N, int H, int W, dlb_stream_t stream);
 int dlb_f32_to_u8(const float* x_nchw, uint8_t* out_nhwc, int N, int H, int W, dlb_stream_t stream);

@@ -307,6 +307,33 @@ def options_fixture():
     save("options_test_mode", **arrs)
 
 
+def variance_images():
+    """Tiles that exercise is_empty()'s rule of dropping saturated luma (0 / 255) before the variance: pure white, white
+    with a dark speck, light grey with black dots, half black / half white, near-white noise, plain noise, one grey level."""
+    rng = np.random.default_rng(17)
+    t = []
+    t.append(np.full((32, 32, 3), 255, np.uint8))
+    a = np.full((32, 32, 3), 255, np.uint8); a[:4, :4] = rng.integers(90, 110, (4, 4, 3)); t.append(a)
+    b = np.full((32, 32, 3), 240, np.uint8); b[::7, ::5] = 0; t.append(b)
+    c = np.zeros((32, 32, 3), np.uint8); c[:, 16:] = 255; t.append(c)
+    t.append(rng.integers(250, 256, (32, 32, 3)).astype(np.uint8))
+    t.append(rng.integers(0, 256, (32, 32, 3)).astype(np.uint8))
+    t.append(np.full((32, 32, 3), 128, np.uint8))
+    d = rng.integers(0, 256, (32, 32, 3)).astype(np.uint8); d[rng.random((32, 32)) < 0.3] = 255; d[rng.random((32, 32)) < 0.2] = 0; t.append(d)
+    return np.stack(t)
+
+
+def variance_fixture():
+    """image_variance_gray (deepliif/util/__init__.py:478-485) and is_empty (models/__init__.py:391-396) of those tiles."""
+    from PIL import Image
+    import_reference()
+    from deepliif.util import image_variance_gray as ref_var
+    from deepliif.models import is_empty
+    imgs = variance_images()
+    save("variance", imgs=imgs, var=np.array([float(ref_var(Image.fromarray(v))) for v in imgs]),
+         empty=np.array([bool(is_empty(Image.fromarray(v))) for v in imgs]))
+
+
 INIT_CASES = [("G", "resnet_9blocks", "batch", True), ("G", "unet_512", "batch", True), ("G", "resnet_6blocks", "instance", False),
               ("D", "n_layers", "batch", 4), ("D", "basic", "instance", 3)]
 
@@ -366,7 +393,80 @@ def scheduler_fixture():
     save("schedulers", **{f"c{i}": lr_sequence(N.get_scheduler, c) for i, c in enumerate(SCHED_CASES)})
 
 
+TRAIN_CLI_CASES = [
+    # (dataset: tile size, tiles per row, number of rows), CLI overrides
+    (dict(tile=64, k=6, rows=3), dict()),
+    (dict(tile=64, k=6, rows=3), dict(seg_weights="0.3,0.1,0.2,0.1,0.3", loss_weights_g="0.1,0.2,0.3,0.2,0.2", seed=7, padding="reflect",
+                                     modalities_names="IHC, Hema,DAPI,Lap2,Marker", net_g="resnet_9blocks", preprocess="resize_and_crop",
+                                     load_size=72, crop_size=64, epoch_count=1, no_flip=True)),
+    (dict(tile=32, k=5, rows=2), dict(modalities_no=2, net_g="resnet_6blocks,resnet_9blocks", net_gs="unet_256", batch_size=3)),
+    (dict(tile=32, k=5, rows=2), dict(modalities_no=4, seg_gen=False, net_d="basic", norm="instance", no_dropout=True)),
+]
+
+
+def train_cli_dataset(root, tile, k, rows, seed=5):
+    """Row images for the CLI prologue: the seg tile (last one) is black with a bright square, so that the background colour
+    estimate finds empty 32 x 32 boxes; the other tiles are smooth colour fields plus noise."""
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "train"), exist_ok=True)
+    for r in range(rows):
+        row = np.zeros((tile, tile * k, 3), np.uint8)
+        for j in range(k - 1):
+            base = rng.integers(40, 220, size=3)
+            row[:, j * tile:(j + 1) * tile] = np.clip(base + rng.integers(-12, 13, size=(tile, tile, 3)), 0, 255)
+        seg = np.zeros((tile, tile, 3), np.uint8)
+        seg[tile // 2:, tile // 2:] = rng.integers(60, 250, size=(tile - tile // 2, tile - tile // 2, 3))
+        row[:, (k - 1) * tile:] = seg
+        Image.fromarray(row).save(os.path.join(root, "train", f"r{r}.png"))
+
+
+def options_snapshot(opt, root):
+    skip = ("checkpoints_dir", "dataroot", "local_rank", "precision", "cuda_graph")
+    d = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(opt).items() if k not in skip}
+    def conv(o):
+        if isinstance(o, np.integer):
+            return int(o)
+        return [int(x) for x in o] if hasattr(o, "__iter__") else str(o)
+    return json.dumps(d, sort_keys=True, default=conv).replace(root, "<root>")
+
+
+def train_cli_fixture():
+    """The option prologue of the reference's `deepliif train` (cli.py:213-386): the command's callback runs with its click
+    defaults + the overrides above on a synthetic dataroot until it calls print_options(opt, save=True); the attributes of
+    that Options object are the fixture."""
+    import importlib
+    import tempfile
+    import_reference()
+    sys.path.insert(0, "/root/reference")
+    rcli = importlib.import_module("cli")
+
+    class Captured(Exception):
+        pass
+
+    def capture(opt, save=False):
+        raise Captured(opt)
+    rcli.print_options = capture
+    arrs = {}
+    for ci, (ds, over) in enumerate(TRAIN_CLI_CASES):
+        root = tempfile.mkdtemp()
+        train_cli_dataset(root, **ds)
+        kw = {p.name: (p.default if not callable(p.default) else p.default()) for p in rcli.cli.commands["train"].params}
+        kw.update(dataroot=root, checkpoints_dir=root, name="exp", gpu_ids=())
+        kw.update(over)
+        try:
+            rcli.cli.commands["train"].callback(**kw)
+            raise RuntimeError("print_options was not reached")
+        except Captured as c:
+            arrs[f"c{ci}"] = np.frombuffer(options_snapshot(c.args[0], root).encode(), dtype=np.uint8)
+    save("train_cli_options", **arrs)
+
+
 def main():
+    if "traincli" in sys.argv[1:]:
+        return train_cli_fixture()
+    if "variance" in sys.argv[1:]:
+        return variance_fixture()
     if "options" in sys.argv[1:]:
         return options_fixture()
     if "init" in sys.argv[1:]:
@@ -508,6 +608,8 @@ def main():
     scheduler_fixture()
     init_fixture()
     options_fixture()
+    variance_fixture()
+    train_cli_fixture()
     print("all fixtures written to", OUT)
 
 

@@ -124,20 +124,23 @@ def test_cli_train_then_test_round_trip(tmp_path):
     root = tmp_path / "data"
     (root / "train").mkdir(parents=True)
     rng = np.random.default_rng(3)
-    for i in range(2):       # row of 6 tiles: IHC | Hema | DAPI | Lap2 | Marker | Seg
-        Image.fromarray((rng.random((128, 6 * 128, 3)) * 255).astype(np.uint8)).save(root / "train" / f"s{i}.png")
+    for i in range(2):       # row of 6 tiles: IHC | Hema | DAPI | Lap2 | Marker | Seg (512 high: scale_size is read off it)
+        Image.fromarray((rng.random((512, 6 * 512, 3)) * 255).astype(np.uint8)).save(root / "train" / f"s{i}.png")
     ck = tmp_path / "ck"
     r = CliRunner().invoke(cli, ["train", "--dataroot", str(root), "--name", "exp", "--checkpoints-dir", str(ck), "--gpu-ids", "0",
                                  "--batch-size", "2", "--net-g", "resnet_2blocks", "--net-gs", "unet_128", "--n-epochs", "1",
                                  "--n-epochs-decay", "0", "--save-epoch-freq", "1", "--print-freq", "1", "--num-threads", "0",
-                                 "--load-size", "144", "--crop-size", "128",
+                                 "--preprocess", "resize_and_crop", "--load-size", "144", "--crop-size", "128",
                                  "--seed", "0"])
     assert r.exit_code == 0, r.output[-3000:]
     files = set(os.listdir(ck / "exp"))
     for k in ["G1", "G4", "GS0", "GS4", "D1", "DS4"]:
         assert f"latest_net_{k}.pth" in files, files
-    assert "train_opt.txt" in files
+    assert "train_opt.txt" in files and "loss_log.txt" in files and "1_net_G1.pth" in files
     assert "G_L1_1" in r.output and "D_real_S" in r.output
+    from deepliif_b200.options import Options
+    topt = Options(path_file=str(ck / "exp" / "train_opt.txt"), mode="test")
+    assert topt.scale_size == 512 and topt.input_no == 1 and topt.seg_weights == [0.25, 0.15, 0.25, 0.1, 0.25]
     inp, out = tmp_path / "in", tmp_path / "out"
     inp.mkdir()
     Image.fromarray((rng.random((200, 300, 3)) * 255).astype(np.uint8)).save(inp / "roi.png")

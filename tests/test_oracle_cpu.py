@@ -212,3 +212,13 @@ def test_test_mode_options_equal_the_reference(tmp_path):
         got = json.loads(options_as_json(Options(path_file=os.path.join(mdir, "train_opt.txt"), mode="test"), root))
         want = json.loads(bytes(z[tag]).decode())
         assert got == want, {k: (got.get(k), want.get(k)) for k in set(got) | set(want) if got.get(k) != want.get(k)}
+
+
+def test_image_variance_gray_drops_saturated_pixels_like_the_reference():
+    """is_empty()'s statistic: the variance is taken over the luma values that are neither 0 nor 255 (0 if none)."""
+    from deepliif_b200.util import image_variance_gray
+    z = np.load(os.path.join(GOLD, "variance.npz"))
+    for im, v, e in zip(z["imgs"], z["var"], z["empty"]):
+        got = image_variance_gray(im)
+        assert abs(got - float(v)) < 1e-9 * max(1.0, abs(float(v)))
+        assert (got < 9) == bool(e)

@@ -55,3 +55,13 @@ def test_tile_gray_variance_matches_reference_golden(ops):
     v = ops.tile_gray_variance(torch.from_numpy(z["var_imgs"]).cuda())
     assert np.abs(v - z["var_vals"]).max() < 1e-6
     assert v[1] == 0.0 and (v[1] < 9) and (v[0] >= 9)      # constant tile is "empty", random tile is not
+
+
+def test_tile_gray_variance_drops_saturated_pixels(ops):
+    """Device statistic of is_empty() on tiles with luma 0 / 255 pixels (tests/golden/variance.npz, recorded from the
+    reference): exact integer sums over the unsaturated pixels only."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "variance.npz"))
+    v = ops.tile_gray_variance(torch.from_numpy(z["imgs"]).cuda())
+    assert np.allclose(v, z["var"], rtol=1e-9, atol=1e-9)
+    assert ((v < 9) == z["empty"]).all()
