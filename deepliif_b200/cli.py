@@ -43,8 +43,9 @@ def cli():
 @click.option("--mod-only", is_flag=True, help="save only the translated modality images")
 @click.option("--color-dapi", is_flag=True)
 @click.option("--color-marker", is_flag=True)
+@click.option("--BtoA", "btoa", is_flag=True, help="CycleGAN models only (load generator B): accepted, unused by the DeepLIIF model")
 def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids, eager_mode, epoch, seg_intermediate,
-         seg_only, mod_only, color_dapi, color_marker):
+         seg_only, mod_only, color_dapi, color_marker, btoa=False):
     """Test trained models"""
     output_dir = output_dir or input_dir
     os.makedirs(output_dir, exist_ok=True)
