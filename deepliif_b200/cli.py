@@ -20,8 +20,7 @@ from PIL import Image
 
 from .models import infer_modalities
 from .options import Options, print_options
-
-IMG_EXT = (".png", ".jpg", ".jpeg", ".tif", ".tiff", ".bmp")
+from .util import allowed_file
 
 
 @click.group()
@@ -54,8 +53,10 @@ def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids,
     elif seg_only:
         seg_intermediate = False
     if filename_pattern == "*":
-        image_files = sorted(fn for fn in os.listdir(input_dir) if fn.lower().endswith(IMG_EXT))
+        print("use all alowed files")
+        image_files = sorted(fn for fn in os.listdir(input_dir) if allowed_file(fn))
     else:
+        print("match files using filename pattern", filename_pattern)
         image_files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(input_dir, filename_pattern)))
     print(len(image_files), "image files")
     assert "train_opt.txt" in os.listdir(model_dir), f"file train_opt.txt is missing from model directory {model_dir}"

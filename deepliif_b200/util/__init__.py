@@ -8,6 +8,17 @@ import numpy as np
 import torch
 
 
+# names a result image ends with (`<stem>_<name>.png`): results written next to the inputs are not inputs of the next run
+excluding_names = ["Hema", "DAPI", "DAPILap2", "Ki67", "Seg", "Marked", "SegRefined", "SegOverlaid", "Marker", "Lap2"]
+image_extensions = [".png", ".jpg", ".tif", ".jpeg"]
+
+
+def allowed_file(filename):
+    """util/__init__.py:38-48: an image extension, and not one of this tool's own result files."""
+    name, extension = os.path.splitext(filename)
+    return extension in image_extensions and name.split("_")[-1] not in excluding_names
+
+
 def chunker(iterable, size):
     for i in range(size):
         yield iterable[i::size]
