@@ -157,6 +157,9 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
         opt = get_opt(model_path)
     for k, v in opt_args.items():
         setattr(opt, k, v)
+    if getattr(opt, "seg_gen", True) is False and (seg_only or return_seg_intermediate):      # models/__init__.py:478-482
+        seg_only = return_seg_intermediate = False
+        print("option seg_gen is False, disabled seg_only and return_seg_intermediate")
     # seg_weights=None means equal weights 1/(modalities_no+1), as in the reference's run_dask (:299-306): only the
     # `deepliif test` command passes opt.seg_weights down (cli.py:878, 906), a direct API call does not read them
     nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
