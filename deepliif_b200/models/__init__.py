@@ -162,6 +162,9 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
         print("option seg_gen is False, disabled seg_only and return_seg_intermediate")
     # seg_weights=None means equal weights 1/(modalities_no+1), as in the reference's run_dask (:299-306): only the
     # `deepliif test` command passes opt.seg_weights down (cli.py:878, 906), a direct API call does not read them
+    if getattr(opt, "input_no", 1) > 1:
+        raise NotImplementedError("inference(): models with several input images side by side (input_no > 1, SDG-style) are "
+                                  "outside the B200 hot-path scope")
     nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
     grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
     tiles = grid.tiles()
