@@ -472,6 +472,9 @@ def run_training(params):
     dl = DeviceBatches(loader, torch.device("cuda", local), input_no=getattr(opt, "input_no", 1))
     model = create_model(opt)
     model.setup(opt)
+    if getattr(opt, "precision", "bf16x3") != "bf16x3":           # --precision bf16: single-pass operands (not fp32-parity)
+        for nm in model.model_names:
+            model._unwrap(model._net(nm)).precision = opt.precision
     make_optimizers(model)
     from .models import networks as nw
     model.schedulers = [nw.get_scheduler(o, opt) for o in model.optimizers]
