@@ -188,5 +188,19 @@ def trainlaunch(ctx, use_torchrun):
     sys.exit(subprocess.run(cmd).returncode)
 
 
+@cli.command()
+@click.option("--model-dir", required=True, help="reads models from here")
+@click.option("--output-dir", help="saves serialized models here")
+@click.option("--device", default="cpu", type=str)
+@click.option("--epoch", default="latest", type=str)
+@click.option("--verbose", default=0, type=int)
+def serialize(model_dir, output_dir, device, epoch, verbose):
+    """Not needed here: the reference traces its cuDNN graphs to TorchScript to speed up loading (cli.py:760-830); this
+    package always builds its sm_100a engines from the state_dicts.  Directories the reference serialized (G1.pt ...) are
+    read directly by `test` / init_nets (the weights are extracted)."""
+    raise click.UsageError("deepliif_b200 has no TorchScript export: its engines are built from the .pth state_dicts at load "
+                           "time; `test` reads both .pth directories and directories serialized by the reference")
+
+
 if __name__ == "__main__":
     cli()
