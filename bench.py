@@ -47,13 +47,15 @@ def parse():
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--trunk-n-tile", type=int, default=0, help="UMMA N of the ResNet-block convs (0 = 256)")
     ap.add_argument("--norm", default="batch", help="batch (CLI default of the reference) | instance")
-    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade", "postprocess"],
+    ap.add_argument("--workload", default="inference", choices=["inference", "train", "unet256", "cascade", "postprocess", "wsi"],
                     help="inference = BASELINE configs[1] (the headline); train = configs[3] (pix2pix step, batch 8/GPU); "
                          "unet256 = configs[4] (UNet-256 seg head, single-pass bf16, batch 64)")
     ap.add_argument("--topology", default="flat5", choices=["flat5", "default"],
                     help="train workload: flat5 = BASELINE configs[3]; default = the reference's default `deepliif train` "
                          "(4 ResNet-9 + 5 UNet-512 seg cascade, 9 n_layers=4 PatchGANs, BatchNorm, dropout, batch 1)")
     ap.add_argument("--graph", action="store_true", help="train workload: replay the step from a CUDA graph (training.GraphedStep)")
+    ap.add_argument("--no-graph", action="store_true", help="inference: issue every launch from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="inference: skip the configs.{train,unet256,wsi} sub-records and the library baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-events", action="store_true")
     return ap.parse_args()
@@ -154,7 +156,7 @@ def cpu_flat5_tiles_per_s(norm, steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
     v, s_per_step, cores = cpu_flat5_tiles_per_s(args.norm, steps, warmup)
     sample = ("1 tile (512x512x3) x 5 ResNet-9 generators per step, N=1 per call, torch fp32 CPU (oracle port), "
               "best of {16,32,64,all} threads of %d host cores" % os.cpu_count())
@@ -188,14 +190,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.workload == "train":
-        return bench_train(args, rank, world, local, dev, dist)
-    if args.workload == "unet256":
-        return bench_unet256(args, rank, world, local, dev, dist)
-    if args.workload == "cascade":
-        return bench_cascade(args, rank, world, local, dev, dist)
-    if args.workload == "postprocess":
-        return bench_postprocess(args, rank, world, local, dev, dist)
+    other = {"train": bench_train, "unet256": bench_unet256, "cascade": bench_cascade, "postprocess": bench_postprocess,
+             "wsi": bench_wsi}
+    if args.workload in other:
+        rec = other[args.workload](args, rank, world, local, dev, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+        return
     from deepliif_b200 import engine as eng_mod
     from deepliif_b200 import ops
     from deepliif_b200.models import networks
@@ -211,7 +215,10 @@ def main():
         g.to(dev).eval()
         gens.append(g)
     engines = [g.engine() for g in gens]
-    pipe = TilePipeline([e.forward for e in engines], micro_batch=args.micro_batch, n_streams=args.streams)
+    use_graph = not args.no_graph
+    pipe = TilePipeline([e.forward for e in engines], micro_batch=args.micro_batch, n_streams=args.streams, use_graph=use_graph)
+    # with the graph path the first call of a shape runs eagerly (fills the caches), the second captures, later ones replay
+    n_warm = max(args.warmup, 3) if use_graph else args.warmup
 
     B = args.batch
     # rotate over distinct input batches so the inputs of consecutive steps never sit in the 126 MB L2
@@ -226,12 +233,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident metric ---------------------------------------------------------------------
-    for w in range(args.warmup):
+    for w in range(n_warm):
         pipe.forward_device(xs[w % n_rot])
     barrier()
-    roof_pairs = []
-    if not args.no_roofline_events:
-        eng_mod.BLOCK_CONV_EVENTS = roof_pairs        # engine records (start, end) around block-conv launches
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.LAUNCHES["count"]
@@ -244,23 +248,28 @@ def main():
     e1.record()
     barrier()
     launches = ops.LAUNCHES["count"] - l0
-    eng_mod.BLOCK_CONV_EVENTS = None
     t_ms = e0.elapsed_time(e1)
-    # ---- roofline pass: the same steps on ONE stream, so the block-conv launches are timed without co-running
-    # kernels of other chains (in the headline region above the chains overlap on several streams, which inflates
-    # every individual launch while raising whole-job throughput) -------------------------------------------------------
-    roof_solo = []
-    if not args.no_roofline_events and args.streams > 1:
-        solo = TilePipeline([e.forward for e in engines], micro_batch=args.micro_batch, n_streams=1)
-        solo.forward_device(xs[0])
-        barrier()
-        eng_mod.BLOCK_CONV_EVENTS = roof_solo
-        for k in range(max(1, args.steps - 1)):
-            solo.forward_device(xs[k % n_rot])
-        barrier()
-        eng_mod.BLOCK_CONV_EVENTS = None
+    # ---- roofline passes: the same step issued eagerly with CUDA events around every ResNet-block conv launch (events
+    # cannot sit inside the replayed graph).  (a) in-region: the same stream layout as the headline, so the kernel is timed
+    # while the other chains' kernels co-run; (b) isolated: ONE stream, nothing co-running ------------------------------
+    roof_pairs, roof_solo = [], []
+    if not args.no_roofline_events:
+        for n_st, sink in ((args.streams, roof_pairs), (1, roof_solo)):
+            if n_st == 1 and args.streams == 1:
+                roof_solo = roof_pairs
+                break
+            rp = TilePipeline([e.forward for e in engines], micro_batch=args.micro_batch, n_streams=n_st)
+            rp.forward_device(xs[0])
+            barrier()
+            eng_mod.BLOCK_CONV_EVENTS = sink
+            for k in range(2):
+                rp.forward_device(xs[k % n_rot])
+            barrier()
+            eng_mod.BLOCK_CONV_EVENTS = None
     # ---- end-to-end metric (host uint8 in, host uint8 out) ------------------------------------------------
-    out_host = pipe.infer_u8(u8s[0])
+    out_host = None
+    for w in range(3 if use_graph else 1):
+        out_host = pipe.infer_u8(u8s[w % n_rot], out_host)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -280,36 +289,72 @@ def main():
     tiles = B * world * args.steps
     value = tiles / (t_ms / 1e3)
     e2e = tiles / (t2_ms / 1e3)
-    if dist is not None:            # all ranks leave the group before rank 0 spends tens of seconds on the CPU baseline
+
+    # ---- sub-records for the other BASELINE configs (same launch, same ranks): configs[3] training with the NCCL
+    # gradient all-reduce, configs[4] UNet-256 bf16, configs[2] the WSI tile -> infer -> stitch sweep ------------------------
+    extras = {}
+    if not args.no_extras:
+        del pipe, engines, gens, xs, u8s, out_host
+        rp = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        import copy
+        for name, fn, over in (("train", bench_train, dict(batch=8, steps=3, warmup=2, graph=False, topology="flat5")),
+                               ("unet256", bench_unet256, dict(batch=64, steps=10, warmup=3)),
+                               ("wsi", bench_wsi, dict(steps=1, warmup=1))):
+            a2 = copy.copy(args)
+            for k_, v_ in over.items():
+                setattr(a2, k_, v_)
+            a2.no_cpu_baseline = True
+            try:
+                rec = fn(a2, rank, world, local, dev, dist)
+            except Exception as e:                      # a failing sub-record must not lose the headline
+                rec = {"error": repr(e)[:300]}
+            if rank == 0 and rec is not None:
+                extras[name] = _compact(rec)
+            gc.collect()
+            torch.cuda.empty_cache()
+    if dist is not None:            # all ranks leave the group before rank 0 spends tens of seconds on the baselines
         dist.barrier()
         dist.destroy_process_group()
         dist = None
 
     if rank == 0:
         peak_tf, peak_hbm, peak_kind = peaks()
+        whole_tf = value / world * N_HEADS * RESNET_GFLOP / 1e3            # per GPU
         roof = None
-        in_pipe = None
-        if roof_pairs and roof_solo:
-            per = [a.elapsed_time(b) for a, b, _ in roof_pairs]
+
+        def _kernel_rate(pairs):
+            per = [a.elapsed_time(b) for a, b, _ in pairs]
             avg = sum(per) / len(per)
-            a_ = BLOCK_CONV_FLOP * roof_pairs[0][2] / (avg * 1e-3) / 1e12
-            in_pipe = {"achieved": a_, "frac": a_ / peak_tf, "launch_ms": avg, "launches_timed": len(per),
-                       "note": "same kernel inside the %d-stream headline region (co-running kernels share the SMs)" % args.streams}
-            roof_pairs = roof_solo
+            return BLOCK_CONV_FLOP * pairs[0][2] / (avg * 1e-3) / 1e12, avg, len(per), pairs[0][2]
         if roof_pairs:
-            per = [a.elapsed_time(b) for a, b, _ in roof_pairs]
-            ntile = roof_pairs[0][2]
-            avg_ms = sum(per) / len(per)
-            ach = BLOCK_CONV_FLOP * ntile / (avg_ms * 1e-3) / 1e12
+            ach, avg_ms, n_timed, ntile = _kernel_rate(roof_pairs)
+            iso = None
+            if roof_solo and roof_solo is not roof_pairs:
+                a_, ms_, n_, _ = _kernel_rate(roof_solo)
+                iso = {"achieved": a_, "frac": a_ / peak_tf, "launch_ms": ms_, "launches_timed": n_,
+                       "note": "same kernel on ONE stream (nothing co-running)"}
             traffic = None
             tp = os.path.join(ROOT, "profiles", "block_conv_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "traffic": traffic, "kernel": "conv_tc_kernel (ResNet block conv 256->256 3x3 @128x128)",
-                    "launch_ms": avg_ms, "tiles_per_launch": ntile, "launches_timed": len(per), "in_pipeline": in_pipe,
-                    "peak_kind": f"{peak_kind} cuBLAS bf16 sustained; bf16x3 executes 3 MMAs per algorithmic MAC "
-                                 f"(ceiling = 1/3)" if args.precision.endswith("x3") else peak_kind}
+                    "launch_ms": avg_ms, "tiles_per_launch": ntile, "launches_timed": n_timed,
+                    "region": "in-region: the headline step's %d-stream layout issued eagerly with CUDA events around every "
+                              "block-conv launch (other chains' kernels co-run)" % args.streams,
+                    "isolated": iso,
+                    "whole_step_frac": whole_tf / peak_tf, "whole_step_tflops": whole_tf,
+                    "peak_kind": (f"{peak_kind} cuBLAS bf16 sustained; bf16x3 executes 3 MMAs per algorithmic MAC (ceiling = 1/3)"
+                                  if args.precision.endswith("x3") else peak_kind)}
+        lib = None
+        if not args.no_extras:
+            try:
+                lib = library_baseline(args, dev)
+            except Exception as e:
+                lib = {"error": repr(e)[:300]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:          # the CPU leg is a single-GPU-run item (rank 0, N=1 only)
             v, s_per, cores = cpu_flat5_tiles_per_s(args.norm, 1, 1)
@@ -317,26 +362,173 @@ def main():
                    "sample": "1 tile x 5 ResNet-9 generators, N=1 per call, torch fp32 CPU (oracle port), best of {16,32,64,all} threads, 1 warm-up", "host_cores": os.cpu_count()}
         line = {
             "metric": "512x512 IHC tiles/sec (flat-5 ResNet-9 generators)", "value": value, "unit": "tiles/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": t_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 result via %s tensor-core operands, fp32 accumulate" % args.precision, "data": "synthetic",
             "config": {"workload": "inference: 5x ResNet-9blocks generators, batch=%d/GPU, 512x512 synthetic tiles"
                                    % B, "norm": args.norm, "padding": "zero", "micro_batch": args.micro_batch, "streams": args.streams,
+                       "cuda_graph": use_graph,
                        "host_enqueue_ms_per_step": t_host * 1e3 / args.steps,
                        "parallelism": "tile-sharded dp%d, no collective" % world,
-                       "l2": "3 rotating input batches (%.0f MB each) + multi-GB activations per step >> 126 MB L2"
-                             % (xs[0].numel() * 4 / 1e6),
+                       "l2": "3 rotating input batches (%.0f MB each) + multi-GB activations per step >> 126 MB L2" % (B * 3 * HW * HW * 4 / 1e6),
                        "algorithmic_gflop_per_tile": N_HEADS * RESNET_GFLOP},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t2_ms / args.steps},
             "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib,
             "algorithmic_tflops": value * N_HEADS * RESNET_GFLOP / 1e3,
+            "configs": extras or None,
         }
         print(json.dumps(line), flush=True)
+
+
+def _compact(rec):
+    """Sub-record of the headline line: the numbers, not the prose."""
+    if rec is None or "error" in rec:
+        return rec
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "gpu_launches",
+            "algorithmic_tflops", "e2e", "roofline", "cuda_graph", "sweep", "loss_G_L1_1")
+    out = {k: rec[k] for k in keep if k in rec}
+    out["workload"] = rec.get("config", {}).get("workload")
+    for k in ("host_enqueue_ms_per_step", "parallelism", "allreduce"):
+        if k in rec.get("config", {}):
+            out[k] = rec["config"][k]
+    return out
+
+
+def library_baseline(args, dev):
+    """The "library bar" (SURVEY.md 8d): the same five ResNet-9 generators as plain torch.nn.functional calls on THIS GPU —
+    eager PyTorch over cuDNN, which is what the reference's modules execute (networks.py:448-450) — batch 32, fp32 inputs
+    resident in HBM, (a) with TF32 convolutions allowed (the reference default, cli.py:1059-1063) and (b) strict fp32.
+    Also reports each variant's max-abs error against the CPU fp32 oracle on one tile (the 1e-3 parity gate)."""
+    from oracle import nets
+    cfg = dict(n_blocks=9, norm=args.norm, use_dropout=False, padding_type="zero")
+    shapes = nets.resnet_param_shapes(3, 3, 64, 9, args.norm, False, "zero")
+    sds_cpu = [nets.make_state_dict(shapes, 100 + i) for i in range(N_HEADS)]
+    sds = [{k: v.to(dev) for k, v in sd.items()} for sd in sds_cpu]
+    B = args.batch
+    g = torch.Generator().manual_seed(77)
+    x_cpu = torch.rand((B, 3, HW, HW), generator=g) * 2 - 1
+    x = x_cpu.to(dev)
+    with torch.no_grad():
+        torch.set_num_threads(min(32, os.cpu_count()))
+        y_ref = nets.resnet_forward(x_cpu[:1], sds_cpu[0], norm_mode="sample", **cfg)
+    out = {"what": "oracle/nets.resnet_forward on cuda (eager PyTorch, cuDNN convolutions, F.instance_norm), 5 generators, "
+                   "batch %d in micro-batches of %d, device-resident fp32 input" % (B, args.micro_batch), "unit": "tiles/s"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for label, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def step():
+                with torch.no_grad():
+                    for sd in sds:
+                        for s0 in range(0, B, args.micro_batch):
+                            nets.resnet_forward(x[s0:s0 + args.micro_batch], sd, norm_mode="sample", **cfg)
+            step(); step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            with torch.no_grad():
+                y = nets.resnet_forward(x[:1], sds[0], norm_mode="sample", **cfg).cpu()
+            err = float((y - y_ref).abs().max())
+            out[label] = {"value": B / (ms / 1e3), "ms_per_step": ms, "max_abs_vs_cpu_oracle": err, "passes_1e-3": err <= 1e-3}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return out
+
+
+# ROI sizes (W, H) of the reference's Sample_Large_Tissues/ PNGs (the images themselves cannot travel to the GPU box)
+WSI_ROIS = [(1381, 949), (1404, 1179), (2167, 1520), (2662, 2207), (1250, 995)]
+
+
+def bench_wsi(args, rank, world, local, dev, dist):
+    """BASELINE configs[2]: the WSI sweep — five Sample_Large_Tissues-sized ROIs through models.infer_tiles (the body of
+    inference(), models/__init__.py:464-579): InferenceTiler geometry at tile_size=512 overlap=56 (102 tiles), tiles sharded
+    rank::world, the default cascade (4 ResNet-9 + 5 UNet-512) on every rank, uint8 results gathered to rank 0 (one NCCL
+    gather per ROI) and stitched there.  Timed end to end with the host work inside (tiling, pinning, H2D, D2H, gather,
+    stitching): wall clock between barriers, max over ranks."""
+    import numpy as np
+    from PIL import Image
+    from deepliif_b200 import ops
+    from deepliif_b200.models import infer_tiles, networks
+    from deepliif_b200.options import Options
+    opt = Options(d_params=dict(model="DeepLIIF", name="bench", checkpoints_dir="/tmp", gpu_ids=(local,), input_nc=3, output_nc=3,
+                                ngf=64, ndf=64, net_g="resnet_9blocks", net_gs="unet_512", net_d="n_layers", norm=args.norm,
+                                no_dropout=False, padding="zero", init_type="normal", init_gain=0.02, modalities_no=4, seg_gen=True,
+                                input_no=1, scale_size=512, phase="test", modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"],
+                                seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25], loss_G_weights=[0.2] * 5, loss_D_weights=[0.2] * 5,
+                                mod_id_seg="S", background_colors=[[255, 255, 255]] * 4), mode="train")
+    opt.input_id = "0"
+    nets = {}
+    for i in range(1, 5):
+        torch.manual_seed(i)
+        nets[f"G{i}"] = networks.define_G(3, 3, 64, "resnet_9blocks", args.norm, True, "normal", 0.02, [], "zero").to(dev).eval()
+    for i in range(5):
+        torch.manual_seed(10 + i)
+        nets[f"GS{i}"] = networks.define_G(3, 3, 64, "unet_512", args.norm, True, "normal", 0.02, []).to(dev).eval()
+    rng = np.random.default_rng(7)          # same images on every rank
+    rois = []
+    for (W_, H_) in WSI_ROIS:
+        small = rng.integers(0, 256, size=(H_ // 8 + 2, W_ // 8 + 2, 3)).astype(np.float32)
+        img = np.kron(small, np.ones((8, 8, 1), np.float32))[:H_, :W_]
+        img = 0.75 * img + 0.25 * rng.integers(0, 256, size=(H_, W_, 3)).astype(np.float32)
+        rois.append(Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def sweep():
+        n_tiles, outs = 0, None
+        for im in rois:
+            outs = infer_tiles(im, 512, 56, nets, opt, seg_weights=opt.seg_weights)
+            from deepliif_b200.util import TileGrid
+            n_tiles += len(TileGrid(np.asarray(im), 512, 56).tiles()) if rank == 0 else 0
+        return n_tiles, outs
+
+    for _ in range(max(1, args.warmup) + 1):     # first sweep: eager (fills caches); second: captures the per-shape graphs
+        sweep()
+    barrier()
+    l0 = ops.LAUNCHES["count"]
+    sampler = ClockSampler(local); sampler.start()
+    t0 = time.perf_counter()
+    n_tiles = 0
+    for _ in range(args.steps):
+        n, outs = sweep()
+        n_tiles += n
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if dist is not None:
-        dist.destroy_process_group()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        v = n_tiles / dt
+        return {"metric": "WSI sweep tiles/sec (5 ROIs, tile 512 overlap 56, default cascade), end to end incl. tiling + stitch", "value": v,
+                "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup) + 1, "ms_per_step": dt * 1e3 / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 via %s" % args.precision,
+                "data": "synthetic", "config": {"workload": "WSI sweep: 5 ROIs sized like Sample_Large_Tissues (%s), tile_size=512 "
+                                                            "overlap=56 -> %d tiles per sweep, tiles sharded over %d GPU(s), rank-0 stitch"
+                                                            % (", ".join("%dx%d" % r for r in WSI_ROIS), n_tiles // max(1, args.steps), world),
+                                                "norm": args.norm, "parallelism": "tile-sharded dp%d + 1 gather per ROI" % world},
+                "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
+                "sweep": {"seconds": dt / args.steps, "tiles": n_tiles // max(1, args.steps), "rois": len(rois),
+                          "outputs_per_roi": sorted(outs.keys()) if outs else None},
+                "e2e": {"value": v, "unit": "tiles/s",
+                        "h2d_bytes_per_step": n_tiles // max(1, args.steps) * 512 * 512 * 3,
+                        "d2h_bytes_per_step": n_tiles // max(1, args.steps) * 512 * 512 * 3 * 10}}
+    return None
 
 
 def bench_cascade(args, rank, world, local, dev, dist):
@@ -382,16 +574,15 @@ def bench_cascade(args, rank, world, local, dev, dist):
     t_ms = float(t.item())
     if rank == 0:
         v = B * world * args.steps / (t_ms / 1e3)
-        print(json.dumps({"metric": "512x512 IHC tiles/sec (default cascade: 4 ResNet-9 + 5 UNet-512), end to end", "value": v,
+        return ({"metric": "512x512 IHC tiles/sec (default cascade: 4 ResNet-9 + 5 UNet-512), end to end", "value": v,
                           "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32 via %s" % args.precision, "data": "synthetic",
                           "config": {"workload": "inference: DeepLIIF default cascade, batch=%d/GPU, host uint8 in/out" % B,
                                      "norm": args.norm, "micro_batch": args.micro_batch, "streams": args.streams},
                           "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
-                          "algorithmic_tflops": v * 1827.8 / 1e3}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+                          "algorithmic_tflops": v * 1827.8 / 1e3})
+    return None
 
 
 def bench_postprocess(args, rank, world, local, dev, dist):
@@ -465,9 +656,8 @@ def bench_postprocess(args, rank, world, local, dev, dist):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": T * T / 1e6 / dt, "unit": "Mpixel/s", "cores": 1, "kind": "port",
                                     "sample": "one %dx%d tile of the region through oracle/cells.py (numpy/scipy)" % (T, T)}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def bench_unet256(args, rank, world, local, dev, dist):
@@ -539,14 +729,17 @@ def bench_unet256(args, rank, world, local, dev, dist):
         ops.LAUNCHES["count"] = l0 + (ops.LAUNCHES["count"] - c0) * args.steps
     if rank == 0:
         v = B * world * args.steps / (t_ms / 1e3)
-        print(json.dumps({"metric": "256x256 tiles/sec (UNet-256 seg head)", "cuda_graph": graph is not None, "value": v, "unit": "tiles/s", "n_gpus": world,
+        pk = peaks()
+        return ({"metric": "256x256 tiles/sec (UNet-256 seg head)", "cuda_graph": graph is not None, "value": v, "unit": "tiles/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
                           "config": {"workload": "UNet-256 generator, %s, batch=%d/GPU, seg head only, 256x256" % (prec, B),
                                      "norm": args.norm}, "clocks": clocks, "gpu_launches": ops.LAUNCHES["count"] - l0,
-                          "algorithmic_tflops": v * 12.10 / 1e3}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+                          "algorithmic_tflops": v * 12.10 / 1e3,
+                          "roofline": {"bound": "tensor", "achieved": v / world * 12.10 / 1e3, "peak": pk[0], "unit": "TFLOP/s",
+                                       "frac": v / world * 12.10 / 1e3 / pk[0], "traffic": None,
+                                       "note": "whole network (single-pass bf16: ceiling 1.0), algorithmic 12.10 GFLOP/tile"}})
+    return None
 
 
 def bench_train(args, rank, world, local, dev, dist):
@@ -616,7 +809,7 @@ def bench_train(args, rank, world, local, dev, dist):
         gflop = (N_HEADS * (3 * RESNET_GFLOP + (3 + 2 * 2 + 1) * 26.11) if not default_topo else
                  3 * (4 * RESNET_GFLOP + 5 * 48.44) + 9 * (3 + 2 * 2 + 1) * 21.77)
         v = B * world * args.steps / (t_ms / 1e3)
-        print(json.dumps({"metric": ("512x512 training tiles/sec (DeepLIIF default step: 4 ResNet-9 + 5 UNet-512 G, 9 PatchGAN D)"
+        return ({"metric": ("512x512 training tiles/sec (DeepLIIF default step: 4 ResNet-9 + 5 UNet-512 G, 9 PatchGAN D)"
                                      if default_topo else
                                      "512x512 training tiles/sec (pix2pix step, 5x ResNet-9 G + PatchGAN D)"), "value": v,
                           "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -630,9 +823,8 @@ def bench_train(args, rank, world, local, dev, dist):
                                      "cuda_graph": stepper is not None},
                           "clocks": clocks,
                           "gpu_launches": per_step_launches * args.steps if stepper is not None else ops.LAUNCHES["count"] - l0,
-                          "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+                          "algorithmic_tflops": v * gflop / 1e3, "loss_G_L1_1": losses.get("G_L1_1")})
+    return None
 
 
 if __name__ == "__main__":

@@ -17,6 +17,12 @@ class ConvDesc(C.Structure):
                 ("transposed", C.c_int), ("output_padding", C.c_int), ("pad_mode", C.c_int)]
 
 
+class FusedSrc(C.Structure):
+    """dlb_fused_src: one K-source of dlb_conv_tc_fwd_fused (raw fp32 producer output + norm/act/residual)."""
+    _fields_ = [("x", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int), ("residual", C.c_void_p),
+                ("out", C.c_void_p), ("border", C.c_int), ("border_mode", C.c_int)]
+
+
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _cd = C.POINTER(ConvDesc)
 _vpp = C.POINTER(C.c_void_p)
@@ -29,10 +35,14 @@ SIGNATURES = {
     "dlb_pack_weights_tc": (_i, [_cd, _vp, _i, _vp, _vp, _vp]),
     "dlb_pack_weights_direct": (_i, [_cd, _vp, _vp, _vp]),
     "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dlb_conv_tc_fused_mode": (_i, [_cd, _i, _i]),
+    "dlb_conv_tc_fwd_fused": (_i, [_cd, C.POINTER(FusedSrc), _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_direct_fwd": (_i, [_cd, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
     "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dlb_norm_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dlb_norm_finalize_bn": (_i, [_vp, _sz, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    "dlb_norm_stats_bn": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _sz, _vp]),
     "dlb_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                           _i, _f, C.c_ulonglong, _vp, _vp, _sz, _vp]),
     "dlb_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _i, _f, _vp]),

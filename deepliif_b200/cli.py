@@ -65,7 +65,8 @@ def test(input_dir, output_dir, tile_size, model_dir, filename_pattern, gpu_ids,
     if not torch.cuda.is_available():
         raise click.UsageError("deepliif_b200 needs a CUDA (sm_100a) device")
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:       # torchrun: one process per GPU, tiles are sharded across ranks, rank 0 stitches and writes
+    if world > 1 or "LOCAL_RANK" in os.environ:   # torchrun (also --nproc-per-node 1): one process per GPU, tiles are
+        # sharded across ranks, rank 0 stitches and writes
         import torch.distributed as dist
         torch.cuda.set_device(local)
         gpu_ids = (local,)

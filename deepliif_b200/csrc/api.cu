@@ -83,12 +83,12 @@ extern "C" int dlb_version(void) { return 100; }
 
 extern "C" int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW) { return out_shape(d, OH, OW); }
 
-extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
-                               const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split,
-                               int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
+static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
+                            const dlb_fused_src* fsrc, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                            int fmt, int split, int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
   int OH, OW;
   if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
-  if (d->pad_mode != DLB_PAD_ZERO) return set_error("dlb_conv_tc_fwd: zero padding only (reflect border comes from dlb_norm_apply)");
+  if (d->pad_mode != DLB_PAD_ZERO) return set_error("dlb_conv_tc_fwd: zero padding only (reflect border comes from dlb_norm_apply / dlb_fused_src.border)");
   if (d->nsrc < 1 || d->nsrc > 2) return set_error("dlb_conv_tc_fwd: nsrc must be 1 or 2");
   if (fmt != DLB_FMT_BF16 && fmt != DLB_FMT_FP16) return set_error("dlb_conv_tc_fwd: bad fmt");
   PhaseGeom geo[4];
@@ -104,7 +104,7 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     sp = stats_ptrs(stats_ws, L);
     for (int i = 0; i < np; ++i) {
       int tw, th, tn, nt;
-      tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt);
+      tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, fsrc != nullptr);
       if (tn != 1) return set_error("dlb_conv_tc_fwd: fused statistics need OH*OW >= 128 per phase (use dlb_norm_stats)");
       slice_base[i] = S_total;
       S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw) * 4;
@@ -142,7 +142,18 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     memset(&ph, 0, sizeof(ph));
     static_cast<PhaseGeom&>(ph) = geo[i];
     ph.nsrc = d->nsrc;
-    for (int s = 0; s < d->nsrc; ++s) { ph.cin[s] = d->Cin[s]; ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; }
+    for (int s = 0; s < d->nsrc; ++s) {
+      ph.cin[s] = d->Cin[s];
+      if (fsrc == nullptr) { ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; continue; }
+      ph.fa = 1;
+      ph.fa_x[s] = fsrc[s].x; ph.fa_scale[s] = fsrc[s].scale; ph.fa_shift[s] = fsrc[s].shift; ph.fa_res[s] = fsrc[s].residual;
+      ph.fa_out[s] = fsrc[s].out; ph.fa_act[s] = fsrc[s].act;
+      ph.fa_border = fsrc[0].border; ph.fa_border_mode = fsrc[0].border_mode;
+      if (fsrc[s].border != fsrc[0].border || fsrc[s].border_mode != fsrc[0].border_mode)
+        return set_error("dlb_conv_tc_fwd_fused: every source needs the same border");
+      if (fsrc[s].act != DLB_ACT_NONE && fsrc[s].act != DLB_ACT_RELU && fsrc[s].act != DLB_ACT_LRELU02)
+        return set_error("dlb_conv_tc_fwd_fused: act must be none / relu / lrelu0.2");
+    }
     ph.w_hi = w_hi; ph.w_lo = split ? w_lo : nullptr; ph.bias = bias; ph.y = y;
     ph.fmt = fmt; ph.split = split ? 1 : 0; ph.n_tile = n_tile;
     if (stats_ws != nullptr) {
@@ -159,6 +170,38 @@ extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, 
     }
   }
   return 0;
+}
+
+extern "C" int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_tile) {
+  int OH, OW;
+  if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
+  if (d->nsrc < 1 || d->nsrc > 2) return set_error("dlb_conv_tc_fused_mode: nsrc must be 1 or 2");
+  PhaseGeom geo[4];
+  const long long C = d->Cout;
+  const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
+  if (np < 0) return np;
+  int worst = 2;
+  for (int i = 0; i < np; ++i) {
+    if (geo[i].ntaps > 16) return 0;
+    int tw, th, tn, nt;
+    const int m = tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, 1);
+    if (m == 0) return 0;
+    worst = m < worst ? m : worst;
+  }
+  return worst;
+}
+
+extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
+                               const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split,
+                               int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
+  return conv_tc_fwd_impl(d, x_hi, x_lo, nullptr, w_hi, w_lo, bias, y, fmt, split, n_tile, stats_ws, stats_ws_bytes, stream);
+}
+
+extern "C" int dlb_conv_tc_fwd_fused(const dlb_conv_desc* d, const dlb_fused_src* src, const void* w_hi, const void* w_lo,
+                                     const float* bias, float* y, int fmt, int split, int n_tile, void* stats_ws,
+                                     size_t stats_ws_bytes, dlb_stream_t stream) {
+  if (src == nullptr) return set_error("dlb_conv_tc_fwd_fused: src is null");
+  return conv_tc_fwd_impl(d, nullptr, nullptr, src, w_hi, w_lo, bias, y, fmt, split, n_tile, stats_ws, stats_ws_bytes, stream);
 }
 
 extern "C" int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, const float* in_scale,

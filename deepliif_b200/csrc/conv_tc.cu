@@ -24,6 +24,9 @@
 // warps read TMEM with tcgen05.ld (one output pixel per thread), add the bias and store fp32 NHWC.
 // The kernel is persistent: grid = min(#tiles, #SMs), static round-robin tile schedule (tiles have
 // identical cost).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -36,6 +39,9 @@ constexpr int kMaxStages = 8;
 constexpr int kKC = 64;                // channels per pipeline stage: 64 x 2 B = one 128 B swizzle row
 constexpr int kABytes = 128 * 128;     // one A plane of a stage: 128 pixels x 128 B
 constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kConvWarps = 8;          // fused-operand mode: warps 6-13 build the A planes from fp32 producer outputs
+constexpr int kThreadsFa = kThreads + 32 * kConvWarps;
+constexpr int kHsMaxPx = 192;          // halo-strip mode: at most this many strip pixels (3x3: 18 x 10 = 180; 2x2 taps: 17 x 9)
 constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
 constexpr int kStaticSmem = 18 * 1024; // barriers + statistics transpose buffers (static __shared__), rounded up
 constexpr int kMaxDynSmem = kSmemLimit - kStaticSmem - 1024;
@@ -69,6 +75,28 @@ struct alignas(64) TcParams {
   // a 1024-byte-aligned window of that strip (tile_w = 8 pixels = one 8-row swizzle atom per image row).
   int vs, vs_rows, vs_dh_min;
   int vs_row_off[kMaxTaps];
+  // "fused operand" mode (fa): there are no operand planes in HBM.  Converter warps read the PRODUCER's raw fp32 output,
+  // apply its normalisation (per-(n,c) scale/shift), activation and residual add, split the result into hi/lo 16-bit
+  // values and write them straight into the 128B-swizzled A stage the MMA reads — the nn.BatchNorm2d/InstanceNorm2d +
+  // nn.ReLU (+ ResnetBlock skip add) between two convolutions (networks.py:490-513) costs no HBM round trip.
+  int fa, fa_is_bf16, fa_wb_tap;
+  const float* fa_x[2];                // fp32 NHWC [N, Hs, Ws, cin[s]] per K-source
+  const float* fa_scale[2];            // [N][cin] or null
+  const float* fa_shift[2];
+  const float* fa_res[2];              // optional fp32 NHWC added after the activation
+  float* fa_out[2];                    // optional: the materialised operand, written once (by the tap that maps 1:1)
+  int fa_act[2];
+  int fa_cin[2];
+  int fa_border, fa_border_mode;       // the conv's input = source behind a zero / reflected border of this width
+  int H, W, Hs, Ws, conv_stride;       // conv input extents (incl. border), source extents
+  int tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  // "halo strip" mode (hs; fused-operand, stride 1): per 64-channel chunk the converters build ONE operand strip of
+  // (tile_h + dh span) x (tile_w + dw span) input pixels — every input value is converted once per tile instead of once
+  // per tap — and each tap's MMAs address their shifted 16 x 8 pixel window of it directly: descriptor start =
+  // strip + ((dh - dh_min) * cols + (dw - dw_min)) * 128 B, group stride (SBO) = cols * 128 B.  Weights stream per
+  // (chunk, tap) through the stage ring as in tap mode.
+  int hs, hs_rows, hs_cols, hs_plane_bytes, hs_dh_min, hs_dw_min;
+  int hs_off[kMaxTaps];
 };
 
 struct TileCoord {
@@ -84,13 +112,59 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ float fa_act1(float v, int act) {
+  if (act == DLB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DLB_ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+
+// 4 fp32 values -> 4 hi + 4 lo 16-bit values (hi = rn16(x), lo = rn16(x - hi)): the arithmetic of norm_apply_kernel.
+__device__ __forceinline__ void fa_split4(const float (&o)[4], int is_bf16, uint2& hi, uint2& lo) {
+  if (is_bf16) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(o[k]); l[k] = __float2bfloat16_rn(o[k] - __bfloat162float(h[k])); }
+    hi = *reinterpret_cast<uint2*>(h); lo = *reinterpret_cast<uint2*>(l);
+  } else {
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { h[k] = __float2half_rn(o[k]); l[k] = __float2half_rn(o[k] - __half2float(h[k])); }
+    hi = *reinterpret_cast<uint2*>(h); lo = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// One operand element group: 4 channels of one input pixel of K-source `src`.  (vh, vw): coordinates in the conv's input
+// (source + border).  Returns the transformed values (zeros outside the input = the conv's own zero padding, or in a zero
+// border) and whether the position is an interior source pixel (eligible for the write-back).
+struct FaPix { long long off; bool ok, interior; int n; };
+
+__device__ __forceinline__ FaPix fa_locate(const TcParams& p, int src, int n, int vh, int vw) {
+  FaPix r;
+  r.n = n;
+  r.ok = (n < p.N) && (vh >= 0) && (vh < p.H) && (vw >= 0) && (vw < p.W);
+  int sh = vh - p.fa_border, sw = vw - p.fa_border;
+  r.interior = r.ok && sh >= 0 && sh < p.Hs && sw >= 0 && sw < p.Ws;
+  if (!r.interior) {
+    if (p.fa_border_mode == DLB_PAD_REFLECT) {
+      if (sh < 0) sh = -sh; if (sh >= p.Hs) sh = 2 * p.Hs - 2 - sh;
+      if (sw < 0) sw = -sw; if (sw >= p.Ws) sw = 2 * p.Ws - 2 - sw;
+    } else {
+      r.ok = false;
+    }
+  }
+  r.off = r.ok ? ((static_cast<long long>(n) * p.Hs + sh) * p.Ws + sw) * p.fa_cin[src] : 0;
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
+  __shared__ __align__(8) uint64_t aready_bar;   // hs mode: operand strip written (converter warps)
+  __shared__ __align__(8) uint64_t afree_bar;    // hs mode: every MMA reading the strip has retired
   __shared__ uint32_t tmem_base_smem;
   __shared__ float tr_smem[4][32][33];   // per-epilogue-warp transpose buffer for the fused column statistics
 
@@ -101,22 +175,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
   const int vs_a_bytes = p.vs_rows * p.tile_w * 128;                 // one plane of an A strip (vs mode)
-  const int stage_bytes = p.vs ? p.planes * vs_a_bytes : p.planes * (kABytes + b_bytes);
+  const int stage_bytes = p.hs ? p.planes * b_bytes : (p.vs ? p.planes * vs_a_bytes : p.planes * (kABytes + b_bytes));
   const int kch0 = p.kchunks[0];
-  const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : 0;
-  uint8_t* const stage_base = smem + bres_bytes;                     // resident weights first, then the stage ring
+  const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : (p.hs ? p.planes * p.hs_plane_bytes : 0);
+  uint8_t* const stage_base = smem + bres_bytes;                     // resident weights / operand strip first, then the stage ring
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nsrc; ++s) {
+    for (int s = 0; s < p.nsrc && !p.fa; ++s) {
       prefetch_tensormap(&p.a_hi[s]);
       if (p.planes == 2) prefetch_tensormap(&p.a_lo[s]);
     }
     prefetch_tensormap(&p.b_hi);
     if (p.planes == 2) prefetch_tensormap(&p.b_lo);
     if (blockIdx.x == 0 && p.st_S != nullptr) *p.st_S = p.st_S_total;
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // a stage is full when the TMA bytes have landed (producer's expect_tx arrival) and, in fused-operand mode, every
+    // converter warp has written its share of the A planes
+    const uint32_t full_count = ((p.fa && p.vs) ? 0u : 1u) + ((p.fa && !p.hs) ? static_cast<uint32_t>(kConvWarps) : 0u);
+    mbar_init(&aready_bar, kConvWarps); mbar_init(&afree_bar, 1);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     mbar_init(&bres_bar, 1);
     fence_barrier_init();
@@ -134,7 +212,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (lane == 0) {
       // ===================== TMA producer =====================
       int s = 0; uint32_t ph = 0;
-      if (p.vs) {
+      if (p.hs) {
+        // weights only: one (chunk, tap) tile per stage, chunk-major so the strip of a chunk serves all its taps
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          for (int src = 0; src < p.nsrc; ++src)
+            for (int kc = 0; kc < p.kchunks[src]; ++kc)
+              for (int tap = 0; tap < p.ntaps; ++tap) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+                uint8_t* sb = stage_base + static_cast<size_t>(s) * stage_bytes;
+                const int kw = p.src_koff[src] + kc * kKC;
+                tma_load_3d(sb, &p.b_hi, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+                if (p.planes == 2) tma_load_3d(sb + b_bytes, &p.b_lo, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+              }
+        }
+      } else if (p.vs) {
         // resident weights: every tap / channel chunk / plane once per CTA
         mbar_arrive_expect_tx(&bres_bar, static_cast<uint32_t>(bres_bytes));
         for (int tap = 0; tap < p.ntaps; ++tap)
@@ -143,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_3d(dst, &p.b_hi, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
             if (p.planes == 2) tma_load_3d(dst + b_bytes, &p.b_lo, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
           }
+        if (!p.fa)
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           const TileCoord tc = decode_tile(p, t);
           for (int kc = 0; kc < kch0; ++kc) {
@@ -168,13 +263,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int src = 0; src < p.nsrc; ++src) {
             for (int kc = 0; kc < p.kchunks[src]; ++kc) {
               mbar_wait(&empty_bar[s], ph ^ 1);
-              mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+              mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(p.fa ? p.planes * b_bytes : stage_bytes));
               int c[5];
 #pragma unroll
               for (int i = 0; i < 5; ++i) c[i] = base[i] + (p.dim_sel[i] == 0 ? kc * kKC : 0);
               uint8_t* st = stage_base + static_cast<size_t>(s) * stage_bytes;
-              tma_load_5d(st, &p.a_hi[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
-              if (p.planes == 2) tma_load_5d(st + kABytes, &p.a_lo[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+              if (!p.fa) {
+                tma_load_5d(st, &p.a_hi[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+                if (p.planes == 2) tma_load_5d(st + kABytes, &p.a_lo[src], &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+              }
               const int kw = p.src_koff[src] + kc * kKC;
               uint8_t* sb = st + p.planes * kABytes;
               tma_load_3d(sb, &p.b_hi, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
@@ -191,7 +288,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
-      if (p.vs) {
+      if (p.hs) {
+        const uint32_t strip_hi = smem_u32(smem), strip_lo = strip_hi + static_cast<uint32_t>(p.hs_plane_bytes);
+        const uint32_t sbo = static_cast<uint32_t>(p.hs_cols) * 128u;
+        uint32_t aph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+          uint32_t accumulate = 0;
+          const int nchunks = p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0);
+          for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait(&aready_bar, aph);                // the converters have written this chunk's strip
+            aph ^= 1;
+            tc_fence_after();
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              mbar_wait(&full_bar[s], ph);              // this tap's weights have landed
+              tc_fence_after();
+              const uint32_t aoff = static_cast<uint32_t>(p.hs_off[tap]);
+              const uint32_t b_hi = smem_u32(stage_base + static_cast<size_t>(s) * stage_bytes);
+              const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+              for (int k = 0; k < kKC / 16; ++k) {
+                const uint64_t da_hi = make_sw128_kmajor_desc_sbo(strip_hi + aoff + k * 32, sbo);
+                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
+                  const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
+                  umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                  umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
+                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+                } else {
+                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                }
+                accumulate = 1;
+              }
+              umma_commit(&empty_bar[s]);
+              if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&afree_bar);                    // strip may be overwritten once these MMAs retire
+          }
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1; if (acc == 0) acc_ph ^= 1;
+        }
+      } else if (p.vs) {
         mbar_wait(&bres_bar, 0);                      // resident weights have landed
         tc_fence_after();
         const uint32_t bres = smem_u32(smem);
@@ -266,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue: TMEM -> registers -> (+bias) -> fp32 NHWC =====================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_ph = 0;
@@ -334,6 +474,215 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
+    }
+  } else if (p.fa) {
+    // ===================== operand converters (fused-operand mode) =====================
+    // 256 threads; thread = (q: one float4 = 4 channels of the 64-channel chunk, pr: pixel row group).  A warp-wide
+    // float4 load covers two pixels x 256 contiguous bytes; each thread writes 8 B of the hi and 8 B of the lo plane at
+    // the swizzled position TMA would have used: row m, 16-byte chunk c -> m*128 + ((c ^ (m & 7)) << 4).
+    const int ct = threadIdx.x - 6 * 32;
+    const int q = ct & 15;
+    const int pr = ct >> 4;                                   // 0..15
+    const uint32_t sub = static_cast<uint32_t>((q & 1) * 8);
+    const int chunk = q >> 1;
+    int s = 0; uint32_t ph = 0;
+    const int lw = 31 - __clz(p.tile_w), lh = 31 - __clz(p.tile_h);
+    if (p.hs) {
+      // Strip units: unit u = (pixel u >> 4 of the strip, float4 q = u & 15); thread owns units ct + 256 * j.  A chunk is
+      // loaded, transformed and packed into registers while the MMAs still read the previous chunk's strip; the shared-
+      // memory burst waits for afree_bar.
+      constexpr int kUnits = kHsMaxPx * 16 / 256;              // units per thread for the largest admissible strip
+      const int npx = p.hs_rows * p.hs_cols;
+      const int nunits = (npx * 16 - ct + 255) / 256;          // units this thread owns
+      uint32_t rc[kUnits];                                     // (row << 16) | col of unit j's pixel
+#pragma unroll
+      for (int j = 0; j < kUnits; ++j) {
+        const int px_i = (ct + 256 * j) >> 4;
+        const int row = px_i / p.hs_cols;
+        rc[j] = (static_cast<uint32_t>(row) << 16) | static_cast<uint32_t>(px_i - row * p.hs_cols);
+      }
+      uint8_t* const strip_hi = smem;
+      uint8_t* const strip_lo = smem + p.hs_plane_bytes;
+      uint32_t fph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int vh0 = tc.h0 + p.hs_dh_min, vw0 = tc.w0 + p.hs_dw_min;
+        for (int src = 0; src < p.nsrc; ++src) {
+          const bool wb = (p.fa_out[src] != nullptr) && (tc.cout0 == 0);
+          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+            const int cbase = kc * kKC + q * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.fa_scale[src] != nullptr && tc.n0 < p.N) {
+              sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
+              sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
+            }
+            uint2 hi[kUnits], lo[kUnits];
+#pragma unroll
+            for (int j0 = 0; j0 < kUnits; j0 += 4) {
+              float4 xv[4], rv[4]; FaPix px[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; px[u].ok = false; px[u].interior = false;
+                if (j < nunits) {
+                  const int row = static_cast<int>(rc[j] >> 16), col = static_cast<int>(rc[j] & 0xffffu);
+                  px[u] = fa_locate(p, src, tc.n0, vh0 + row, vw0 + col);
+                  if (px[u].ok) {
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_x[src] + px[u].off + cbase));
+                    if (p.fa_res[src] != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_res[src] + px[u].off + cbase));
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (px[u].ok) {
+                  o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[src]) + rv[u].x;
+                  o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), p.fa_act[src]) + rv[u].y;
+                  o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), p.fa_act[src]) + rv[u].z;
+                  o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[src]) + rv[u].w;
+                  // write-back of the evaluated operand: the tile's own pixels only (each source pixel belongs to exactly
+                  // one tile), i.e. strip positions whose output pixel (vh - border, vw - border) lies inside this tile
+                  if (wb && px[u].interior && j < nunits) {
+                    const int row = static_cast<int>(rc[j] >> 16), col = static_cast<int>(rc[j] & 0xffffu);
+                    const int oh = vh0 + row - p.fa_border, ow = vw0 + col - p.fa_border;
+                    if (oh >= tc.h0 && oh < tc.h0 + p.tile_h && ow >= tc.w0 && ow < tc.w0 + p.tile_w)
+                      *reinterpret_cast<float4*>(p.fa_out[src] + px[u].off + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+                  }
+                }
+                fa_split4(o, p.fa_is_bf16, hi[j], lo[j]);
+              }
+            }
+            mbar_wait(&afree_bar, fph ^ 1);                    // MMAs of the previous chunk are done with the strip
+            fph ^= 1;
+#pragma unroll
+            for (int j = 0; j < kUnits; ++j) {
+              if (j < nunits) {
+                const uint32_t px_i = static_cast<uint32_t>(ct + 256 * j) >> 4;
+                // absolute-address swizzle: the strip base is 1024 B aligned, so row bits [7,10) of the address = px_i & 7
+                const uint32_t off = px_i * 128u + (static_cast<uint32_t>(chunk ^ (px_i & 7u)) << 4) + sub;
+                *reinterpret_cast<uint2*>(strip_hi + off) = hi[j];
+                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + off) = lo[j];
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aready_bar);
+          }
+        }
+      }
+    } else
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      if (p.vs) {
+        const int npx = p.vs_rows * p.tile_w;                 // tile_w == 8: one image row = one 1024 B swizzle atom
+        const int vw0 = tc.w0 + p.tap_off[0][1], vh0 = tc.h0 + p.vs_dh_min;
+        for (int kc = 0; kc < kch0; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
+          uint8_t* a_lo = a_hi + vs_a_bytes;
+          const int cbase = kc * kKC + q * 4;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.fa_scale[0] != nullptr && tc.n0 < p.N) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
+            sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
+          }
+          for (int base = 0; base < npx; base += 64) {
+            float4 xv[4], rv[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = base + u * 16 + pr;
+              xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; ok[u] = false;
+              if (idx < npx) {
+                const FaPix px = fa_locate(p, 0, tc.n0, vh0 + (idx >> 3), vw0 + (idx & 7));
+                ok[u] = px.ok;
+                if (px.ok) {
+                  xv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_x[0] + px.off + cbase));
+                  if (p.fa_res[0] != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_res[0] + px.off + cbase));
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = base + u * 16 + pr;
+              if (idx >= npx) continue;
+              float o[4] = {0.f, 0.f, 0.f, 0.f};
+              if (ok[u]) {
+                o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[0]) + rv[u].x;
+                o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), p.fa_act[0]) + rv[u].y;
+                o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), p.fa_act[0]) + rv[u].z;
+                o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[0]) + rv[u].w;
+              }
+              uint2 hi, lo;
+              fa_split4(o, p.fa_is_bf16, hi, lo);
+              const uint32_t off = static_cast<uint32_t>(idx) * 128u + (static_cast<uint32_t>(chunk ^ (idx & 7)) << 4) + sub;
+              *reinterpret_cast<uint2*>(a_hi + off) = hi;
+              if (p.planes == 2) *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      } else {
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+          for (int src = 0; src < p.nsrc; ++src) {
+            const bool wb = (p.fa_out[src] != nullptr) && (tap == p.fa_wb_tap) && (tc.cout0 == 0);
+            for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
+              uint8_t* a_lo = a_hi + kABytes;
+              const int cbase = kc * kKC + q * 4;
+              float4 xv[8], rv[8];
+              FaPix px[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = pr + 16 * i;
+                const int w_l = m & (p.tile_w - 1), h_l = (m >> lw) & (p.tile_h - 1), n_l = m >> (lw + lh);
+                px[i] = fa_locate(p, src, tc.n0 + n_l, (tc.h0 + h_l) * p.conv_stride + dh, (tc.w0 + w_l) * p.conv_stride + dw);
+                xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); rv[i] = xv[i];
+                if (px[i].ok) {
+                  xv[i] = __ldg(reinterpret_cast<const float4*>(p.fa_x[src] + px[i].off + cbase));
+                  if (p.fa_res[src] != nullptr) rv[i] = __ldg(reinterpret_cast<const float4*>(p.fa_res[src] + px[i].off + cbase));
+                }
+              }
+              const bool has_ss = p.fa_scale[src] != nullptr;
+              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              int sc_n = -1;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = pr + 16 * i;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (px[i].ok) {
+                  if (has_ss && px[i].n != sc_n) {
+                    sc_n = px[i].n;
+                    sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[src] + static_cast<long long>(sc_n) * p.fa_cin[src] + cbase));
+                    sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[src] + static_cast<long long>(sc_n) * p.fa_cin[src] + cbase));
+                  }
+                  o[0] = fa_act1(fmaf(xv[i].x, sc.x, sh.x), p.fa_act[src]) + rv[i].x;
+                  o[1] = fa_act1(fmaf(xv[i].y, sc.y, sh.y), p.fa_act[src]) + rv[i].y;
+                  o[2] = fa_act1(fmaf(xv[i].z, sc.z, sh.z), p.fa_act[src]) + rv[i].z;
+                  o[3] = fa_act1(fmaf(xv[i].w, sc.w, sh.w), p.fa_act[src]) + rv[i].w;
+                  if (wb && px[i].interior)
+                    *reinterpret_cast<float4*>(p.fa_out[src] + px[i].off + cbase) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                uint2 hi, lo;
+                fa_split4(o, p.fa_is_bf16, hi, lo);
+                const uint32_t off = static_cast<uint32_t>(m) * 128u + (static_cast<uint32_t>(chunk ^ (m & 7)) << 4) + sub;
+                *reinterpret_cast<uint2*>(a_hi + off) = hi;
+                if (p.planes == 2) *reinterpret_cast<uint2*>(a_lo + off) = lo;
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[s]);
+              if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -405,28 +754,47 @@ static int auto_n_tile(int cout, long long out_px) {
   return n;
 }
 
+// Halo-strip eligibility (fused-operand mode only): stride 1, several taps, image at least one 16 x 8 tile, the strip of
+// (16 + dh span) x (8 + dw span) pixels within kHsMaxPx, and room for the strip plus two weight stages.
+static bool hs_eligible(const PhaseGeom& g, int split, int n_tile) {
+  if (g.stride != 1 || g.ntaps < 1 || g.ntaps > kMaxTaps || g.OW < 8 || g.OH < 16) return false;
+  int dh0 = g.tap_dh[0], dh1 = g.tap_dh[0], dw0 = g.tap_dw[0], dw1 = g.tap_dw[0];
+  for (int t = 0; t < g.ntaps; ++t) {
+    dh0 = min(dh0, g.tap_dh[t]); dh1 = max(dh1, g.tap_dh[t]); dw0 = min(dw0, g.tap_dw[t]); dw1 = max(dw1, g.tap_dw[t]);
+  }
+  const int rows = 16 + dh1 - dh0, cols = 8 + dw1 - dw0;
+  if (rows * cols > kHsMaxPx) return false;
+  const int planes = split ? 2 : 1;
+  const long long strip = static_cast<long long>(planes) * ((rows * cols * 128 + 1023) / 1024 * 1024);
+  return strip + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem;
+}
+
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
-                  int* tile_h, int* tile_n, int* n_tile_out) {
+                  int* tile_h, int* tile_n, int* n_tile_out, int fa) {
   int n_tile = n_tile_req;
   if (n_tile == 0) n_tile = auto_n_tile(cout, static_cast<long long>(g.N) * g.OH * g.OW);
   *n_tile_out = n_tile;
   int tw = g.OW >= 128 ? 128 : pow2_ceil(g.OW);
   int th = 128 / tw; { int hp = pow2_ceil(g.OH); if (th > hp) th = hp; }
   *tile_w = tw; *tile_h = th; *tile_n = 128 / (tw * th);
-  // ---- vertical-strip eligibility ----
-  if (g.stride != 1 || nsrc != 1 || g.ntaps < 2 || g.ntaps > kMaxTaps || g.OW < 8 || g.OH < 16 || cout > n_tile) return 0;
-  int dh_min = g.tap_dh[0], dh_max = g.tap_dh[0];
-  for (int t = 0; t < g.ntaps; ++t) {
-    if (g.tap_dw[t] != g.tap_dw[0]) return 0;
-    dh_min = min(dh_min, g.tap_dh[t]); dh_max = max(dh_max, g.tap_dh[t]);
+  // ---- vertical-strip eligibility: R x 1 filter, one source, all output channels in one N tile, resident weights ----
+  bool vs = !(g.stride != 1 || nsrc != 1 || g.ntaps < 2 || g.ntaps > kMaxTaps || g.OW < 8 || g.OH < 16 || cout > n_tile);
+  if (vs) {
+    int dh_min = g.tap_dh[0], dh_max = g.tap_dh[0];
+    for (int t = 0; t < g.ntaps; ++t) {
+      if (g.tap_dw[t] != g.tap_dw[0]) vs = false;
+      dh_min = min(dh_min, g.tap_dh[t]); dh_max = max(dh_max, g.tap_dh[t]);
+    }
+    const int planes = split ? 2 : 1;
+    const int kch = cin[0] / kKC;
+    const long long resident = static_cast<long long>(g.ntaps) * kch * planes * n_tile * 128;
+    const long long strip = static_cast<long long>(planes) * (16 + dh_max - dh_min) * 8 * 128;
+    if (resident + 2 * strip + 1024 > kMaxDynSmem) vs = false;
   }
-  const int planes = split ? 2 : 1;
-  const int kch = cin[0] / kKC;
-  const long long resident = static_cast<long long>(g.ntaps) * kch * planes * n_tile * 128;
-  const long long strip = static_cast<long long>(planes) * (16 + dh_max - dh_min) * 8 * 128;
-  if (resident + 2 * strip + 1024 > kMaxDynSmem) return 0;
-  *tile_w = 8; *tile_h = 16; *tile_n = 1;
-  return 1;
+  if (vs) { *tile_w = 8; *tile_h = 16; *tile_n = 1; return 1; }
+  // ---- halo strip (fused-operand mode only): any stride-1 tap set whose strip fits ----
+  if (fa && hs_eligible(g, split, n_tile)) { *tile_w = 8; *tile_h = 16; *tile_n = 1; return 2; }
+  return 0;
 }
 
 // One phase of a convolution on the tensor cores.  See internal.h for the argument contract.
@@ -464,8 +832,9 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
 
   // ---- tile shape: 128 output pixels = tile_n x tile_h x tile_w ---------------------------------
   int tile_w, tile_h, tile_n, n_tile_plan;
-  const int use_vs = ph.no_vs ? (tc_plan_tiles_novs(ph, &tile_w, &tile_h, &tile_n, &n_tile_plan), 0)
-                             : tc_plan_tiles(ph, ph.nsrc, ph.cin, ph.cout, ph.split, ph.n_tile, &tile_w, &tile_h, &tile_n, &n_tile_plan);
+  const int mode = ph.no_vs ? (tc_plan_tiles_novs(ph, &tile_w, &tile_h, &tile_n, &n_tile_plan), 0)
+                           : tc_plan_tiles(ph, ph.nsrc, ph.cin, ph.cout, ph.split, ph.n_tile, &tile_w, &tile_h, &tile_n, &n_tile_plan, ph.fa);
+  const int use_vs = mode == 1, use_hs = mode == 2;
   p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n;
   p.tiles_w = (ph.OW + tile_w - 1) / tile_w;
   p.tiles_h = (ph.OH + tile_h - 1) / tile_h;
@@ -507,8 +876,41 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       box[0] = kKC; box[1] = tile_w; box[2] = 1; box[3] = tile_h; box[4] = tile_n;
       p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 4; p.dim_sel[3] = 2; p.dim_sel[4] = 3;
     }
+    if (ph.fa) continue;                       // fused-operand mode: no activation planes, no tensor maps
     if (!encode_tiled_map(&p.a_hi[s], ph.x_hi[s], is_bf16, 5, dims, strides, box)) return -1;
     if (ph.split && !encode_tiled_map(&p.a_lo[s], ph.x_lo[s], is_bf16, 5, dims, strides, box)) return -1;
+  }
+  if (ph.fa) {
+    p.fa = 1; p.fa_is_bf16 = is_bf16; p.fa_wb_tap = -1;
+    p.fa_border = ph.fa_border; p.fa_border_mode = ph.fa_border_mode;
+    p.H = ph.H; p.W = ph.W; p.Hs = ph.H - 2 * ph.fa_border; p.Ws = ph.W - 2 * ph.fa_border; p.conv_stride = ph.stride;
+    if (p.Hs < 1 || p.Ws < 1) return set_error("conv_tc: fused operand border larger than the input");
+    if (ph.fa_border_mode == DLB_PAD_REFLECT && (ph.fa_border >= p.Hs || ph.fa_border >= p.Ws))
+      return set_error("conv_tc: reflect border must be smaller than the source");
+    bool any_out = false;
+    for (int s = 0; s < ph.nsrc; ++s) {
+      p.fa_x[s] = ph.fa_x[s]; p.fa_scale[s] = ph.fa_scale[s]; p.fa_shift[s] = ph.fa_shift[s]; p.fa_res[s] = ph.fa_res[s];
+      p.fa_out[s] = ph.fa_out[s]; p.fa_act[s] = ph.fa_act[s]; p.fa_cin[s] = ph.cin[s];
+      if (ph.fa_x[s] == nullptr) return set_error("conv_tc: fused operand source is null");
+      if ((ph.fa_scale[s] == nullptr) != (ph.fa_shift[s] == nullptr)) return set_error("conv_tc: scale and shift come together");
+      any_out = any_out || ph.fa_out[s] != nullptr;
+    }
+    for (int t = 0; t < ph.ntaps; ++t) {
+      p.tap_dh[t] = ph.tap_dh[t]; p.tap_dw[t] = ph.tap_dw[t];
+      // the tap that reads input pixel (oh + b, ow + b) for output (oh, ow) visits every source pixel exactly once
+      if (ph.stride == 1 && ph.tap_dh[t] == ph.fa_border && ph.tap_dw[t] == ph.fa_border) p.fa_wb_tap = t;
+    }
+    if (any_out && (use_vs || p.fa_wb_tap < 0 || ph.OH != p.Hs || ph.OW != p.Ws))
+      return set_error("conv_tc: operand write-back needs a stride-1 'same' convolution in tap / halo-strip mode");
+    if (use_hs) {
+      int dh0 = ph.tap_dh[0], dh1 = dh0, dw0 = ph.tap_dw[0], dw1 = dw0;
+      for (int t = 0; t < ph.ntaps; ++t) {
+        dh0 = min(dh0, ph.tap_dh[t]); dh1 = max(dh1, ph.tap_dh[t]); dw0 = min(dw0, ph.tap_dw[t]); dw1 = max(dw1, ph.tap_dw[t]);
+      }
+      p.hs = 1; p.hs_rows = tile_h + dh1 - dh0; p.hs_cols = tile_w + dw1 - dw0; p.hs_dh_min = dh0; p.hs_dw_min = dw0;
+      p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
+      for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - dh0) * p.hs_cols + (ph.tap_dw[t] - dw0)) * 128;
+    }
   }
   // ---- weight tensor map: [taps_total][Cout][Cin_total] ---------------------------------------------
   {
@@ -537,8 +939,9 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   }
 
   const int b_bytes = n_tile * 128;
-  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes : 0;
-  const int stage_bytes = use_vs ? p.planes * p.vs_rows * tile_w * 128 : p.planes * (kABytes + b_bytes);
+  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes : (use_hs ? p.planes * p.hs_plane_bytes : 0);
+  const int stage_bytes = use_hs ? p.planes * b_bytes
+                                 : (use_vs ? p.planes * p.vs_rows * tile_w * 128 : p.planes * (kABytes + b_bytes));
   int stages = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;
@@ -553,7 +956,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  conv_tc_kernel<<<grid, ph.fa ? kThreadsFa : kThreads, smem_bytes, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("conv_tc_kernel launch");
   return 0;
 }

@@ -46,14 +46,26 @@ struct TcPhase : PhaseGeom {
   float* st_cnt;
   int* st_S;
   int st_S_cap, st_slice_base, st_S_total;
+  // fused-operand mode (fa != 0): x_hi/x_lo are unused; the kernel builds the operand planes itself from the producer's
+  // raw fp32 output: act(x*scale + shift) + residual, seen behind a zero / reflected border of fa_border pixels
+  // (H, W of the phase are the extents INCLUDING the border; the source tensors are [N, H-2b, W-2b, cin]).
+  int fa;
+  const float* fa_x[2];
+  const float* fa_scale[2];
+  const float* fa_shift[2];
+  const float* fa_res[2];
+  float* fa_out[2];
+  int fa_act[2];
+  int fa_border, fa_border_mode;
 };
 
 // cuTensorMapEncodeTiled (16-bit elements, 128-byte swizzle, zero OOB fill) through the runtime's driver entry point.
 bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box);
 
+// Returns the phase's execution mode: 0 tap mode, 1 vertical strip (resident weights), 2 halo strip (fa only).
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
-                  int* tile_h, int* tile_n, int* n_tile_out);
+                  int* tile_h, int* tile_n, int* n_tile_out, int fa = 0);
 
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream);
 

@@ -92,11 +92,16 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
 //   pass 1: n = sum n_i, mean = sum(sum_i) / n;   pass 2: M2 = sum(M2_i + n_i * (mean_i - mean)^2).
 // Every thread accumulates its slices in index order (fp32), the 32 warps are combined in warp order (fp64):
 // fixed orders -> deterministic.  groups = N (per-sample statistics) or 1 (pooled over the batch).
+struct BnRunning {              // nn.BatchNorm2d(track_running_stats=True) buffers, updated in training (networks.py:34-37)
+  float* mean; float* var; long long* num_batches_tracked; float momentum;
+};
+
 __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int N, int C, int pooled,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps,
                                                               float* __restrict__ scale, float* __restrict__ shift,
-                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                              BnRunning run) {
   __shared__ double sm[32][33];
   __shared__ double sm2[32][33];
   const int S = *ws.S;
@@ -141,6 +146,14 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int 
   const float be = beta ? beta[c] : 0.f;
   const float sc = ga * rstd;
   const float sh = be - mean * sc;
+  if (run.mean != nullptr && pooled) {
+    // torch.nn.functional.batch_norm in training mode: running <- (1 - momentum) * running + momentum * batch statistic,
+    // the variance one being the UNBIASED batch variance (n / (n - 1)); num_batches_tracked += 1 (once per call)
+    const double unbias = tn > 1.0 ? tn / (tn - 1.0) : 1.0;
+    run.mean[c] = (1.f - run.momentum) * run.mean[c] + run.momentum * mean;
+    run.var[c] = (1.f - run.momentum) * run.var[c] + run.momentum * static_cast<float>(var * unbias);
+    if (c == 0 && run.num_batches_tracked != nullptr) *run.num_batches_tracked += 1;
+  }
   for (int n = n_lo; n < n_hi; ++n) {
     scale[n * C + c] = sc; shift[n * C + c] = sh;
     if (mean_out != nullptr) { mean_out[n * C + c] = mean; rstd_out[n * C + c] = rstd; }
@@ -352,11 +365,12 @@ using namespace dlb;
 extern "C" size_t dlb_norm_stats_workspace(int N, int HW, int C) { return stats_layout(N, HW, C).total; }
 
 static int launch_finalize(void* workspace, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
-                           float eps, float* scale, float* shift, float* mean, float* rstd, cudaStream_t stream) {
+                           float eps, float* scale, float* shift, float* mean, float* rstd, cudaStream_t stream,
+                           BnRunning run = BnRunning{nullptr, nullptr, nullptr, 0.f}) {
   const StatsLayout L = stats_layout(N, HW, C);
   const StatsPtrs ws = stats_ptrs(workspace, L);
   dim3 grid(L.cchunks, pooled ? 1 : N);
-  stats_finalize_kernel<<<grid, 1024, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift, mean, rstd);
+  stats_finalize_kernel<<<grid, 1024, 0, stream>>>(ws, N, C, pooled, gamma, beta, eps, scale, shift, mean, rstd, run);
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_finalize_kernel launch");
   return 0;
 }
@@ -383,6 +397,35 @@ extern "C" int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, 
   stats_partial_kernel<<<dim3(slices, N), 256, 0, st>>>(y, HW, C, slices, stats_ptrs(workspace, L));
   if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_partial_kernel launch");
   return launch_finalize(workspace, N, HW, C, pooled, gamma, beta, eps, scale, shift, mean, rstd, st);
+}
+
+extern "C" int dlb_norm_finalize_bn(void* workspace, size_t workspace_bytes, int N, int HW, int C, const float* gamma,
+                                    const float* beta, float eps, float* scale, float* shift, float* mean, float* rstd,
+                                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                                    dlb_stream_t stream) {
+  if (workspace_bytes < stats_layout(N, HW, C).total) return set_error("dlb_norm_finalize_bn: workspace too small");
+  if (running_mean == nullptr || running_var == nullptr) return set_error("dlb_norm_finalize_bn: running buffers are null");
+  return launch_finalize(workspace, N, HW, C, 1, gamma, beta, eps, scale, shift, mean, rstd,
+                         reinterpret_cast<cudaStream_t>(stream), BnRunning{running_mean, running_var, num_batches_tracked, momentum});
+}
+
+extern "C" int dlb_norm_stats_bn(const float* y, int N, int HW, int C, const float* gamma, const float* beta, float eps,
+                                 float* scale, float* shift, float* mean, float* rstd, float* running_mean, float* running_var,
+                                 long long* num_batches_tracked, float momentum, void* workspace, size_t workspace_bytes,
+                                 dlb_stream_t stream) {
+  if (C % 4 != 0) return set_error("dlb_norm_stats_bn: C % 4 != 0");
+  const int c4n = C / 4;
+  if ((c4n < 256 && 256 % c4n != 0) || (c4n > 256 && c4n % 256 != 0))
+    return set_error("dlb_norm_stats_bn: C/4 must divide 256 (or be a multiple of 256)");
+  if (running_mean == nullptr || running_var == nullptr) return set_error("dlb_norm_stats_bn: running buffers are null");
+  const StatsLayout L = stats_layout(N, HW, C);
+  if (workspace_bytes < L.total) return set_error("dlb_norm_stats_bn: workspace too small");
+  const int slices = (HW + kSlicePixels - 1) / kSlicePixels;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  stats_partial_kernel<<<dim3(slices, N), 256, 0, st>>>(y, HW, C, slices, stats_ptrs(workspace, L));
+  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("stats_partial_kernel launch");
+  return launch_finalize(workspace, N, HW, C, 1, gamma, beta, eps, scale, shift, mean, rstd, st,
+                         BnRunning{running_mean, running_var, num_batches_tracked, momentum});
 }
 
 extern "C" int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,

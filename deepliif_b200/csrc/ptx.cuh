@@ -144,6 +144,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Same layout with an explicit stride between 8-row groups (SBO).  The 128B swizzle is a function of the ABSOLUTE shared-
+// memory address bits (chunk bits [4,7) ^= row bits [7,10)), so a descriptor may start at any 128-byte row of a swizzled
+// region and step between row groups by any multiple of 128 B with base_offset = 0 (measured on B200 with
+// tools/umma_window_probe.cu: every start row 0..10 x SBO in {1024, 1280, 2048, 2304} reproduces the reference product).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // kind::f16 instruction descriptor: fp32 accumulate, both operands K-major, no negate/sparsity.
 //   [4,6) c_format=1 (F32)  [7,10) a_format  [10,13) b_format (0 = F16, 1 = BF16)
 //   [17,23) N >> 3          [24,29) M >> 4

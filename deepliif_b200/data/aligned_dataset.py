@@ -100,9 +100,11 @@ class AlignedDataset(torch.utils.data.Dataset):
 
 
 def collate_u8(items):
-    """[B] x ([k,H,W,3] uint8, path) -> ([B,k,H,W,3] uint8 in pinned memory when CUDA is present, paths)."""
+    """[B] x ([k,H,W,3] uint8, path) -> ([B,k,H,W,3] uint8, paths).  Plain pageable memory: this runs inside forked
+    DataLoader workers, which must not touch CUDA (cudaHostAlloc in a forked child fails); the batch is pinned in the
+    main process by DataLoader(pin_memory=True) / DeviceBatches._stage."""
     shape = (len(items),) + tuple(items[0][0].shape)
-    out = torch.empty(shape, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    out = torch.empty(shape, dtype=torch.uint8)
     for i, (t, _) in enumerate(items):
         out[i].copy_(t)
     return out, [p for _, p in items]
@@ -123,6 +125,8 @@ class DeviceBatches:
     def _stage(self, batch):
         from .. import ops
         u8, paths = batch
+        if not u8.is_pinned():                      # loaders built without pin_memory=True: pin here, in the main process
+            u8 = u8.pin_memory()
         with torch.cuda.stream(self.stream):
             d = u8.to(self.device, non_blocking=True)                   # one copy: [B, k, H, W, 3]
             B, k, H, W, _ = d.shape

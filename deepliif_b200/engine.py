@@ -21,18 +21,25 @@ from . import ops
 from .ops import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16, PAD_REFLECT, PAD_ZERO)
 
 
+def _env_flag(name, default):
+    import os
+    v = os.environ.get(name)
+    return default if v is None or v == "" else v not in ("0", "false", "False", "no")
+
+
 # bench.py sets this to a list to collect (start_event, end_event, tiles) around every ResNet-block conv launch
 # (roofline.achieved is measured live on the launching stream); None = no instrumentation.
 BLOCK_CONV_EVENTS = None
 
 
-def _block_conv(cv, acts, N, H, W, pad):
+def _block_conv(cv, acts, N, H, W, pad, fused=False):
+    run = cv.run_fused if fused else cv.run_tc
     ev = BLOCK_CONV_EVENTS
     if ev is None:
-        return cv.run_tc(acts, N, H, W, pad=pad)
+        return run(acts, N, H, W, pad=pad)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    r = cv.run_tc(acts, N, H, W, pad=pad)
+    r = run(acts, N, H, W, pad=pad)
     b.record()
     ev.append((a, b, N))
     return r
@@ -61,6 +68,22 @@ class Act:
     hi: torch.Tensor = None
     lo: torch.Tensor = None
     pad: int = 0
+
+
+@dataclass
+class Lazy:
+    """An activation that is never written to HBM: the producer's raw fp32 conv output plus the normalisation
+    (scale/shift), activation and residual add that the consuming convolution evaluates while it loads its operand
+    (dlb_conv_tc_fwd_fused)."""
+    x: torch.Tensor
+    scale: torch.Tensor = None
+    shift: torch.Tensor = None
+    act: int = ACT_NONE
+    residual: torch.Tensor = None
+
+    def src(self, border=0, border_mode=PAD_ZERO, out=None):
+        return dict(x=self.x, scale=self.scale, shift=self.shift, act=self.act, residual=self.residual, out=out,
+                    border=border, border_mode=border_mode)
 
 
 def _tc_ok(cins, cout):
@@ -107,6 +130,17 @@ class ConvLayer:
                         self.prec.fmt, self.prec.split, self.n_tile, stats_ws=ws)
         return y, ws
 
+    def run_fused(self, srcs, N, H, W, pad=None, fuse_stats=True):
+        """Like run_tc, but the operand is evaluated in-kernel from `srcs` (list of Lazy.src() dicts, one per K-source).
+        H, W: extents of the conv input including the sources' border."""
+        d = self.desc(N, H, W, pad)
+        oh, ow = ops.conv_out_shape(d)
+        per_phase = (oh // self.stride) * (ow // self.stride) if self.transposed else oh * ow
+        ws = ops.stats_workspace(N, oh * ow, self.cout, srcs[0]["x"].device) if (fuse_stats and per_phase >= 128) else None
+        y = ops.conv_tc_fused(d, srcs, self.w_hi, self.w_lo, self.bias, self.prec.fmt, self.prec.split, self.n_tile,
+                              stats_ws=ws)
+        return y, ws
+
     # ---- training ------------------------------------------------------------------------------------------------
     def wgrad(self, x_act, dy_hi, dy_lo, N, H, W, pad=None):
         """dL/dW in the PyTorch weight layout from the forward operand planes and the output-gradient planes."""
@@ -138,9 +172,14 @@ class ConvLayer:
 class _NormParams:
     def __init__(self, sd, key, norm, device):
         self.gamma = self.beta = None
+        self.running = None            # (running_mean, running_var, num_batches_tracked, momentum) of a tracking BatchNorm2d
         if norm == "batch":
             self.gamma = sd[key + ".weight"].detach().to(device=device, dtype=torch.float32).contiguous()
             self.beta = sd[key + ".bias"].detach().to(device=device, dtype=torch.float32).contiguous()
+            rm, rv, nbt = sd.get(key + ".running_mean"), sd.get(key + ".running_var"), sd.get(key + ".num_batches_tracked")
+            # state_dict() hands out the module's own buffer storage: updating these in place IS updating the module
+            if rm is not None and rv is not None and rm.is_cuda and rm.dtype == torch.float32 and rm.is_contiguous():
+                self.running = (rm.detach(), rv.detach(), nbt.detach() if (nbt is not None and nbt.is_cuda) else None, 0.1)
 
 
 # Optional device uint64 [1] mixed into every dropout seed (set by training.GraphedStep: a captured CUDA graph bakes the
@@ -162,10 +201,13 @@ class _EngineBase:
         written by the conv epilogue (then y is not read again)."""
         if self.norm == "none" or np_ is None:
             return (None, None, None, None) if want_stats else (None, None)
+        # training-mode BatchNorm2d (the train engines): the finalize kernel also moves the running statistics
+        running = np_.running if getattr(self, "update_running_stats", False) else None
         if ws is not None:
             N, H, W, C = y.shape
-            return ops.norm_finalize(ws, N, H * W, C, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats)
-        return ops.norm_stats(y, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats)
+            return ops.norm_finalize(ws, N, H * W, C, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats,
+                                     running=running)
+        return ops.norm_stats(y, np_.gamma, np_.beta, self._pooled(), want_stats=want_stats, running=running)
 
     def _apply(self, y, scale, shift, act, *, residual=None, want_f32=False, want_split=True, pad=0,
                pad_mode=PAD_ZERO, drop=None):
@@ -186,9 +228,13 @@ class ResnetEngine(_EngineBase):
     """ResnetGenerator forward (eval semantics: dropout = identity)."""
 
     def __init__(self, sd, *, n_blocks=9, norm="batch", use_dropout=False, padding_type="zero", norm_mode="sample",
-                 precision="bf16x3", backend="tc", device="cuda", n_tile=0, trunk_n_tile=0):
+                 precision="bf16x3", backend="tc", device="cuda", n_tile=0, trunk_n_tile=0, fused=None, fuse_residual=None):
         prec = Precision.parse(precision) if isinstance(precision, str) else precision
         super().__init__(norm, norm_mode, prec, backend, device)
+        # fused operand load (default on the tensor-core backend): norm + activation (+ skip add) are evaluated by the
+        # consuming convolution; fuse_residual also folds the ResnetBlock skip add into the next block's first conv.
+        self.fused = (backend == "tc") and (_env_flag("DLB_FUSED", True) if fused is None else bool(fused))
+        self.fuse_residual = _env_flag("DLB_FUSE_RESIDUAL", True) if fuse_residual is None else bool(fuse_residual)
         if padding_type not in ("zero", "reflect"):
             raise NotImplementedError("padding [%s] is not implemented" % padding_type)
         self.n_blocks, self.padding_type = n_blocks, padding_type
@@ -251,6 +297,8 @@ class ResnetEngine(_EngineBase):
         x = x.contiguous()
         N, _, H, W = x.shape
         tc = self.backend == "tc"
+        if tc and self.fused and self.stem_tc and self.head_tc and H % 4 == 0 and W % 4 == 0:
+            return self._forward_fused(x, taps)
         refl = self.pad_mode == PAD_REFLECT
         want = dict(want_f32=not tc, want_split=tc)
 
@@ -312,6 +360,73 @@ class ResnetEngine(_EngineBase):
             return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
         return self.head.run_direct(y, N, h, w, pad_mode=self.pad_mode, in_scale=sc, in_shift=sh, in_act=ACT_RELU,
                                     out_act=ACT_TANH, out_nchw=True)
+
+    def _consume(self, layer, lazy, N, H, W, *, pad=None, border=0, keep=False, fuse_stats=True, block=False):
+        """Run `layer` on the lazy activation.  Strip-eligible layers evaluate it in-kernel (no HBM pass); the others
+        (stride 2, maps below 16 x 8) get their operand planes from one dlb_norm_apply pass.  keep: also materialise the
+        evaluated activation in fp32 (the ResnetBlock residual stream).  Returns (y, stats_ws, kept fp32 | None)."""
+        Hv, Wv = H + 2 * border, W + 2 * border
+        d = layer.desc(N, Hv, Wv, pad)
+        kept = None
+        if layer.use_tc and ops.conv_tc_fused_mode(d, self.prec.split, layer.n_tile) > 0:
+            if keep:
+                kept = torch.empty_like(lazy.x)
+            srcs = [lazy.src(border, self.pad_mode, out=kept)]
+            y, ws = (_block_conv(layer, srcs, N, Hv, Wv, pad, fused=True) if block
+                     else layer.run_fused(srcs, N, Hv, Wv, pad, fuse_stats=fuse_stats))
+            return y, ws, kept
+        a = self._apply(lazy.x, lazy.scale, lazy.shift, lazy.act, residual=lazy.residual, want_f32=keep, pad=border,
+                        pad_mode=self.pad_mode)
+        y, ws = (_block_conv(layer, [a], N, Hv, Wv, pad) if block else layer.run_tc([a], N, Hv, Wv, pad, fuse_stats=fuse_stats))
+        return y, ws, a.f32
+
+    @torch.no_grad()
+    def _forward_fused(self, x, taps=None):
+        """The same network with (almost) no normalise/split pass between convolutions: a strip-eligible conv reads its
+        producer's raw fp32 output and evaluates norm + ReLU (+ the block's skip add, + the reflect / zero border) while
+        loading; with fuse_residual the skip add of block b is evaluated by the first conv of block b+1, which also
+        writes the fp32 residual stream out once."""
+        N, _, H, W = x.shape
+        refl = self.pad_mode == PAD_REFLECT
+        b = 1 if refl else 0
+        bpad = 0 if refl else 1
+
+        def tap(name, a):
+            if taps is not None:
+                taps[name] = a
+
+        xh, xl = ops.stem_window_pack(x, 3, self.stem_S, self.pad_mode, self.prec.fmt, self.prec.split)
+        y, ws = self.stem.run_tc([Act(None, xh, xl)], N, H + 6, W)
+        tap("stem_conv", y)
+        sc, sh = self._stats(y, self.stem_norm, ws)
+        cur = Lazy(y, sc, sh, ACT_RELU)
+        h, w = H, W
+        for i in range(2):
+            y, ws, _ = self._consume(self.down[i], cur, N, h, w)
+            h, w = h // 2, w // 2
+            sc, sh = self._stats(y, self.down_norm[i], ws)
+            cur = Lazy(y, sc, sh, ACT_RELU)
+        for bi, (cv1, nm1, cv2, nm2) in enumerate(self.blocks):
+            if not self.fuse_residual and (cur.scale is not None or cur.residual is not None):
+                # separate skip-add pass: materialise r_b once, the first conv then loads it unchanged
+                r = self._apply(cur.x, cur.scale, cur.shift, cur.act, residual=cur.residual, want_f32=True, want_split=False).f32
+                cur = Lazy(r)
+            y, ws, r = self._consume(cv1, cur, N, h, w, pad=bpad, border=b, keep=cur.scale is not None or cur.residual is not None,
+                                     block=True)
+            if r is None:
+                r = cur.x
+            sc, sh = self._stats(y, nm1, ws)
+            y, ws, _ = self._consume(cv2, Lazy(y, sc, sh, ACT_RELU), N, h, w, pad=bpad, border=b, block=True)
+            sc, sh = self._stats(y, nm2, ws)
+            cur = Lazy(y, sc, sh, ACT_NONE, residual=r)
+            tap(f"block{bi}", cur)
+        for i in range(2):
+            y, ws, _ = self._consume(self.up[i], cur, N, h, w)
+            h, w = h * 2, w * 2
+            sc, sh = self._stats(y, self.up_norm[i], ws)
+            cur = Lazy(y, sc, sh, ACT_RELU)
+        z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False)
+        return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
 
     __call__ = forward
 

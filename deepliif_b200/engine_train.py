@@ -40,6 +40,9 @@ def _pad_lanes64(w, transposed=False):
 
 class _TrainOps:
     """Shared tape helpers (mixed into the engines below)."""
+    # training forwards of a tracking BatchNorm2d move its running statistics (momentum 0.1, networks.py:34-37):
+    # _EngineBase._stats passes the module's buffers to the finalize kernel when this is set
+    update_running_stats = True
 
     @staticmethod
     def _new_seed():

@@ -94,36 +94,66 @@ def _seg_weights(opt, seg_weights):
     return [1 / (opt.modalities_no + 1)] * (opt.modalities_no + 1)
 
 
-def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3):
+_PIPE_CACHE = {}
+
+
+def _pipeline(nets, gen_keys, seg_keys, weights, micro_batch, n_streams):
+    """One TilePipeline per (networks, pruning, weights): its captured CUDA graphs are reused across images."""
+    key = (tuple(id(nets[k]) if k else None for k in gen_keys), tuple(id(nets[k]) if k else None for k in seg_keys or ()),
+           tuple(weights), micro_batch, n_streams)
+    pipe = _PIPE_CACHE.get(key)
+    if pipe is None:
+        if len(_PIPE_CACHE) > 8:
+            _PIPE_CACHE.clear()
+        pipe = TilePipeline([nets[k] if k else None for k in gen_keys],
+                            [nets[k] if k else None for k in seg_keys] if seg_keys else None, weights,
+                            micro_batch=micro_batch, n_streams=n_streams, use_graph=os.getenv("DLB_NO_GRAPH", "") == "")
+        _PIPE_CACHE[key] = pipe
+    return pipe
+
+
+def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3, seg_only=False):
     """uint8 tiles [T,ts,ts,3] (numpy) -> dict[name -> uint8 [T,ts,ts,3]] with the reference's result keys
-    (G1.., G{S}, and per-modality seg G{S}k), skipping empty tiles exactly like run_wrapper (:399-443)."""
+    (G1.., G{S}, and per-modality seg G{S}k), skipping empty tiles exactly like run_wrapper (:399-443).
+    seg_only: the seg generators whose weight is zero are not run, nor the modality generators that only feed them
+    (models/__init__.py:318-325; the Marker generator always runs) — their keys are then absent from the result."""
     gens, segs = _names(opt)
     T, ts = tiles_u8.shape[0], tiles_u8.shape[1]
     S = opt.mod_id_seg
-    keys = list(gens) + ([f"G{S}"] + segs if (segs and not mod_only) else [])
+    with_seg = bool(segs) and not mod_only
+    w = _seg_weights(opt, seg_weights) if with_seg else None
+    run_gens, run_segs = list(gens), (list(segs) if with_seg else None)
+    if with_seg and seg_only:
+        marker = None
+        if "Marker" in opt.modalities_names:
+            marker = f"G{opt.modalities_names.index('Marker')}"
+        run_segs = [k if w[i] != 0 else None for i, k in enumerate(segs)]
+        run_gens = [k if (run_segs[i + 1] is not None or k == marker) else None for i, k in enumerate(gens)]
+    keys = [k for k in run_gens if k] + ([f"G{S}"] + [k for k in run_segs if k] if with_seg else [])
     out = {k: np.zeros((T, ts, ts, 3), np.uint8) for k in keys}
+    if T == 0:
+        return out
     # is_empty(): gray-level variance per tile, computed on the device from the uint8 batch (exact integer sums)
     var = ops.tile_gray_variance(torch.from_numpy(np.ascontiguousarray(tiles_u8)).cuda())
     live = [i for i in range(T) if var[i] >= EMPTY_TILE_VARIANCE]
     for i in set(range(T)) - set(live):
         for j, k in enumerate(gens):
-            out[k][i] = np.array(opt.background_colors[j], np.uint8)
+            if k in out:
+                out[k][i] = np.array(opt.background_colors[j], np.uint8)
     if live:
         batch = torch.from_numpy(np.ascontiguousarray(tiles_u8[live])).pin_memory()
-        w = _seg_weights(opt, seg_weights)
-        pipe = TilePipeline([nets[k] for k in gens], [nets[k] for k in segs] if (segs and not mod_only) else None,
-                            w, micro_batch=micro_batch, n_streams=n_streams)
-        if segs and not mod_only:
+        pipe = _pipeline(nets, run_gens, run_segs, w, micro_batch, n_streams)
+        if with_seg:
             res = pipe.infer_u8(batch, want_parts=True)
             torch.cuda.synchronize()
             out[f"G{S}"][live] = res["seg"].numpy()
-            for j, k in enumerate(segs):
-                out[k][live] = res["parts"][j].numpy()
+            for j, k in enumerate(pipe.part_index):
+                out[segs[k]][live] = res["parts"][j].numpy()
         else:
             res = pipe.infer_mods_u8(batch)
             torch.cuda.synchronize()
-        for j, k in enumerate(gens):
-            out[k][live] = res["mods"][j].numpy()
+        for j, i in enumerate(pipe.mod_index if with_seg else range(len(gens))):
+            out[gens[i]][live] = res["mods"][j].numpy()
     return out
 
 
@@ -134,7 +164,7 @@ def run_dask(img, model_path=None, nets=None, eager_mode=True, opt=None, seg_onl
     if nets is None:
         nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
     tile = np.asarray(img.resize((opt.scale_size, opt.scale_size)).convert("RGB"))[None]
-    res = run_batch(tile, nets, opt, seg_weights, mod_only)
+    res = run_batch(tile, nets, opt, seg_weights, mod_only, seg_only=seg_only)
     out = {k: Image.fromarray(v[0]) for k, v in res.items()}
     if seg_only:
         keep = [f"G{opt.mod_id_seg}", f"G{opt.modalities_no}"]
@@ -145,6 +175,44 @@ def run_dask(img, model_path=None, nets=None, eager_mode=True, opt=None, seg_onl
 def run_wrapper(tile, run_fn, model_path=None, nets=None, eager_mode=True, opt=None, seg_only=False, mod_only=False,
                 seg_weights=None, use_dask=False, output_tensor=False):
     return run_fn(tile, model_path, nets, eager_mode, opt, seg_only, mod_only, seg_weights)
+
+
+def infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=None, mod_only=False, seg_only=False, micro_batch=8,
+                n_streams=3):
+    """PIL image -> dict[net key -> stitched PIL image] (None on non-zero ranks of a torchrun launch).
+
+    The tile -> infer -> stitch loop of the reference's inference() (models/__init__.py:484-500, InferenceTiler
+    util/__init__.py:129-331).  One process per GPU: every rank tiles the image itself (cheap, deterministic), infers tiles
+    rank, rank+W, ... (tile sharding, no data-path collective; SURVEY.md 8e, BASELINE config 3) and rank 0 receives every
+    rank's uint8 results in ONE gather (all output keys stacked) and stitches."""
+    import torch.distributed as dist
+    from .. import sharding
+    grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
+    tiles = grid.tiles()
+    if tile_size != opt.scale_size:
+        tiles = np.stack([np.asarray(Image.fromarray(t).resize((opt.scale_size, opt.scale_size))) for t in tiles])
+    distributed = dist.is_available() and dist.is_initialized()      # a group of any size (also 1) takes the gather path
+    world = dist.get_world_size() if distributed else 1
+    rank = dist.get_rank() if distributed else 0
+    if distributed:
+        mine = sharding.shard(tiles, rank, world)
+        # an idle rank (fewer tiles than GPUs) still learns the key list from a zero-tile call
+        local = run_batch(mine, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only)
+        keys = sorted(local.keys())
+        stacked = np.stack([local[k] for k in keys], axis=1) if len(mine) else \
+            np.zeros((0, len(keys)) + tuple(tiles.shape[1:]), np.uint8)
+        full = sharding.gather_to_rank0(torch.from_numpy(np.ascontiguousarray(stacked)), len(tiles))
+        if rank != 0:
+            return None
+        res = {k: full[:, j] for j, k in enumerate(keys)}
+    else:
+        res = run_batch(tiles, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only)
+    results = {}
+    for k, v in res.items():
+        if tile_size != opt.scale_size:
+            v = np.stack([np.asarray(Image.fromarray(t).resize((tile_size, tile_size))) for t in v])
+        results[k] = Image.fromarray(grid.stitch(v))
+    return results
 
 
 def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, eager_mode=True, color_dapi=False,
@@ -166,36 +234,9 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
         raise NotImplementedError("inference(): models with several input images side by side (input_no > 1, SDG-style) are "
                                   "outside the B200 hot-path scope")
     nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
-    grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
-    tiles = grid.tiles()
-    if tile_size != opt.scale_size:
-        tiles = np.stack([np.asarray(Image.fromarray(t).resize((opt.scale_size, opt.scale_size))) for t in tiles])
-    # One process per GPU (torchrun): every rank infers tiles rank, rank+W, ... and rank 0 gathers the uint8 results —
-    # tile sharding with no data-path collective (BASELINE config 3).
-    import torch.distributed as dist
-    from .. import sharding
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-    rank = dist.get_rank() if world > 1 else 0
-    if world > 1:
-        local = run_batch(sharding.shard(tiles, rank, world), nets, opt, seg_weights, mod_only) if len(tiles[rank::world]) else None
-        keys = sorted(local.keys()) if local is not None else None
-        klist = [keys]
-        dist.broadcast_object_list(klist, src=0)
-        res = {}
-        for k in klist[0]:
-            part = local[k] if local is not None else np.zeros((0,) + tuple(tiles.shape[1:]), np.uint8)
-            full = sharding.gather_to_rank0(torch.from_numpy(np.ascontiguousarray(part)), len(tiles))
-            if rank == 0:
-                res[k] = full
-        if rank != 0:
-            return {}
-    else:
-        res = run_batch(tiles, nets, opt, seg_weights, mod_only)
-    results = {}
-    for k, v in res.items():
-        if tile_size != opt.scale_size:
-            v = np.stack([np.asarray(Image.fromarray(t).resize((tile_size, tile_size))) for t in v])
-        results[k] = Image.fromarray(grid.stitch(v))
+    results = infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=seg_weights, mod_only=mod_only, seg_only=seg_only)
+    if results is None:
+        return {}
     # ---- the reference's naming (models/__init__.py:502-565) -----------------------------------------------
     n, S = opt.modalities_no, opt.mod_id_seg
     names = opt.modalities_names

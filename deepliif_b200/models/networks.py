@@ -175,7 +175,8 @@ class ResnetGenerator(_EngineBacked):
 
     def _build_engine(self, device):
         return _engine.ResnetEngine(self.state_dict(), device=device, precision=self.precision, backend=self.backend,
-                                    trunk_n_tile=getattr(self, "trunk_n_tile", 0),
+                                    trunk_n_tile=getattr(self, "trunk_n_tile", 0), fused=getattr(self, "fused", None),
+                                    fuse_residual=getattr(self, "fuse_residual", None),
                                     norm_mode="batch" if (self.training and self.cfg["norm"] == "batch") else "sample",
                                     **self.cfg)
 
@@ -215,6 +216,7 @@ class UnetGenerator(_EngineBacked):
     def __init__(self, input_nc, output_nc, num_downs, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False):
         super().__init__()
         self.cfg = dict(num_downs=num_downs, norm=_norm_name(norm_layer))
+        self.use_dropout = bool(use_dropout)        # nn.Dropout(0.5) on the inner ngf*8 blocks in training (networks.py:536)
         blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, norm_layer=norm_layer, innermost=True)
         for _ in range(num_downs - 5):
             blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, submodule=blk, norm_layer=norm_layer, use_dropout=use_dropout)

@@ -9,9 +9,9 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16, PAD_REFLECT, PAD_ZERO,
-                   ConvDesc, check)
+                   ConvDesc, FusedSrc, check)
 
-__all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc",
+__all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc", "conv_tc_fused", "conv_tc_fused_mode",
            "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "adam_hyper", "adam_step_dev", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
@@ -111,6 +111,41 @@ def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_
     return out
 
 
+def conv_tc_fused_mode(d, split=True, n_tile=0):
+    """2 / 1: the fused-operand kernel runs this layer in a strip mode (efficient); 0: it would convert per tap."""
+    m = _lib.load().dlb_conv_tc_fused_mode(C.byref(d), int(split), n_tile)
+    if m < 0:
+        check(m, "dlb_conv_tc_fused_mode")
+    return m
+
+
+def conv_tc_fused(d, srcs, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_tile=0, out=None, stats_ws=None):
+    """Tensor-core conv whose operand is evaluated inside the kernel from the producer's raw fp32 output.
+    srcs: one dict per K-source with keys x (fp32 NHWC), scale, shift ([N,C] or None), act, residual (fp32 NHWC or None),
+    out (fp32 NHWC or None: receives the evaluated operand), border, border_mode.  d.H / d.W include 2*border."""
+    arr = (FusedSrc * 2)()
+    keep = []
+    for i, s_ in enumerate(srcs):
+        x, sc, sh, res, o = s_["x"], s_.get("scale"), s_.get("shift"), s_.get("residual"), s_.get("out")
+        _need_cuda(x, sc, sh, res, o)
+        if x.dtype != torch.float32:
+            raise _lib.DeepliifB200Error("conv_tc_fused: sources are fp32 NHWC tensors")
+        keep += [x, sc, sh, res, o]
+        arr[i] = FusedSrc(x.data_ptr(), sc.data_ptr() if sc is not None else None, sh.data_ptr() if sh is not None else None,
+                          int(s_.get("act", ACT_NONE)), res.data_ptr() if res is not None else None,
+                          o.data_ptr() if o is not None else None, int(s_.get("border", 0)), int(s_.get("border_mode", PAD_ZERO)))
+    _need_cuda(w_hi, w_lo, bias)
+    oh, ow = conv_out_shape(d)
+    if out is None:
+        out = torch.empty((d.N, oh, ow, d.Cout), dtype=torch.float32, device=w_hi.device)
+    check(_lib.load().dlb_conv_tc_fwd_fused(C.byref(d), arr, _p(w_hi), _p(w_lo) if split else None, _p(bias), _p(out), fmt,
+                                            int(split), n_tile, _p(stats_ws),
+                                            stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
+          "dlb_conv_tc_fwd_fused")
+    LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    return out
+
+
 def conv_direct(d, x, w_packed, bias=None, in_nchw=False, in_scale=None, in_shift=None, in_act=ACT_NONE,
                 out_act=ACT_NONE, out_nchw=False, out=None):
     _need_cuda(x, w_packed, bias, in_scale, in_shift)
@@ -125,21 +160,31 @@ def conv_direct(d, x, w_packed, bias=None, in_nchw=False, in_scale=None, in_shif
     return out
 
 
-def norm_finalize(ws, N, HW, Cc, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False):
+def norm_finalize(ws, N, HW, Cc, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False, running=None):
     """Reduce the partial statistics a conv epilogue left in `ws` -> (scale, shift) fp32 [N,C]
-    (+ (mean, rstd) with want_stats, kept for the backward pass)."""
+    (+ (mean, rstd) with want_stats, kept for the backward pass).  running = (running_mean, running_var,
+    num_batches_tracked, momentum): training-mode BatchNorm2d buffers, updated in the same kernel (pooled only)."""
     scale = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
     shift = torch.empty((N, Cc), dtype=torch.float32, device=ws.device)
     mean = torch.empty((N, Cc), dtype=torch.float32, device=ws.device) if want_stats else None
     rstd = torch.empty((N, Cc), dtype=torch.float32, device=ws.device) if want_stats else None
+    if running is not None and pooled:
+        rm, rv, nbt, mom = running
+        _need_cuda(rm, rv, nbt)
+        check(_lib.load().dlb_norm_finalize_bn(_p(ws), ws.numel() * 4, N, HW, Cc, _p(gamma), _p(beta), float(eps), _p(scale),
+                                               _p(shift), _p(mean), _p(rstd), _p(rm), _p(rv), _p(nbt), float(mom), _stream()),
+              "dlb_norm_finalize_bn")
+        LAUNCHES["count"] += 1
+        return (scale, shift, mean, rstd) if want_stats else (scale, shift)
     check(_lib.load().dlb_norm_finalize(_p(ws), ws.numel() * 4, N, HW, Cc, int(pooled), _p(gamma), _p(beta),
                                         float(eps), _p(scale), _p(shift), _p(mean), _p(rstd), _stream()), "dlb_norm_finalize")
     LAUNCHES["count"] += 1
     return (scale, shift, mean, rstd) if want_stats else (scale, shift)
 
 
-def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False):
-    """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift (+ mean, rstd)."""
+def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=False, running=None):
+    """y: fp32 NHWC [N,H,W,C] -> (scale, shift) fp32 [N,C] with norm(y) = y*scale + shift (+ mean, rstd).
+    running: see norm_finalize."""
     _need_cuda(y, gamma, beta)
     N, H, W, Cc = y.shape
     lib = _lib.load()
@@ -149,8 +194,15 @@ def norm_stats(y, gamma=None, beta=None, pooled=False, eps=1e-5, want_stats=Fals
     shift = torch.empty((N, Cc), dtype=torch.float32, device=y.device)
     mean = torch.empty((N, Cc), dtype=torch.float32, device=y.device) if want_stats else None
     rstd = torch.empty((N, Cc), dtype=torch.float32, device=y.device) if want_stats else None
-    check(lib.dlb_norm_stats(_p(y), N, H * W, Cc, int(pooled), _p(gamma), _p(beta), float(eps), _p(scale), _p(shift),
-                             _p(mean), _p(rstd), _p(ws), ws_bytes, _stream()), "dlb_norm_stats")
+    if running is not None and pooled:
+        rm, rv, nbt, mom = running
+        _need_cuda(rm, rv, nbt)
+        check(lib.dlb_norm_stats_bn(_p(y), N, H * W, Cc, _p(gamma), _p(beta), float(eps), _p(scale), _p(shift), _p(mean),
+                                    _p(rstd), _p(rm), _p(rv), _p(nbt), float(mom), _p(ws), ws_bytes, _stream()),
+              "dlb_norm_stats_bn")
+    else:
+        check(lib.dlb_norm_stats(_p(y), N, H * W, Cc, int(pooled), _p(gamma), _p(beta), float(eps), _p(scale), _p(shift),
+                                 _p(mean), _p(rstd), _p(ws), ws_bytes, _stream()), "dlb_norm_stats")
     LAUNCHES["count"] += 2
     return (scale, shift, mean, rstd) if want_stats else (scale, shift)
 
@@ -354,14 +406,19 @@ def f32_to_u8(x_nchw):
     return out
 
 
-def seg_finish(segs, weights, thresh=120, want_f32=True, want_u8=True, want_mask=True):
-    """segs: list of fp32 NCHW [N,3,H,W]; returns (seg_f32 NCHW, seg_u8 NHWC, mask [N,H,W])."""
+def seg_finish(segs, weights, thresh=120, want_f32=True, want_u8=True, want_mask=True, out=None):
+    """segs: list of fp32 NCHW [N,3,H,W]; returns (seg_f32 NCHW, seg_u8 NHWC, mask [N,H,W]).
+    out: optional (f32, u8, mask) contiguous destination tensors (e.g. batch slices) written in place."""
     _need_cuda(*segs)
     N, _, H, W = segs[0].shape
     dev = segs[0].device
-    f32 = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev) if want_f32 else None
-    u8 = torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) if want_u8 else None
-    mask = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    if out is not None:
+        f32, u8, mask = out
+        _need_cuda(f32, u8, mask)
+    else:
+        f32 = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev) if want_f32 else None
+        u8 = torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+        mask = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if want_mask else None
     ptrs = (C.c_void_p * len(segs))(*[s.data_ptr() for s in segs])
     ws = (C.c_float * len(segs))(*[float(w) for w in weights])
     check(_lib.load().dlb_seg_finish(ptrs, ws, len(segs), N, H, W, int(thresh), _p(f32), _p(u8), _p(mask), _stream()),

@@ -1,6 +1,7 @@
 """Options: the attribute bag built from CLI parameters or from ``train_opt.txt`` (reference:
 deepliif/options/__init__.py:8-217).  The text format ('{:>25}: {:<30}' per key, values re-parsed with eval)
 and the train-/test-mode defaults are kept so model directories interchange with the reference."""
+import ast
 import os
 import re
 from pathlib import Path
@@ -9,9 +10,11 @@ from ..util.util import init_input_and_mod_id, mkdirs
 
 
 def _parse(v):
+    """Value of one train_opt.txt line: a Python literal (int / float / tuple / list / bool / None, as save_options wrote
+    it) or, failing that, the string itself.  Literal parsing only: a model directory is data, not code."""
     try:
-        return eval(v)          # ints / floats / tuples / lists / booleans written by save_options
-    except Exception:
+        return ast.literal_eval(v)
+    except (ValueError, SyntaxError, TypeError, MemoryError, RecursionError):
         return v
 
 

@@ -74,7 +74,7 @@ def _train_engine(self):
         elif isinstance(self, networks.UnetGenerator):
             self._tengine = engine_train.UnetTrainEngine(sd, device=dev, precision=self.precision,
                                                         norm_mode="batch" if self.cfg["norm"] == "batch" else "sample",
-                                                        **self.cfg)
+                                                        use_dropout=self.use_dropout, **self.cfg)
         else:
             raise NotImplementedError(f"training path for {type(self).__name__} is not built yet")
         self._tengine_key = key
@@ -121,18 +121,22 @@ class FlatAdam(torch.optim.Optimizer):
             p.grad = self.grad[off:off + k].view_as(p)
             off += al(k)
         self.t = 0
-        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # a process group of ANY size (also world 1: the 1-GPU NCCL self-test) routes the bucket through the collectives
+        self.dist_on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if self.dist_on else 1
         self.hyper_dev = None          # set by GraphedStep: device float[4] the captured Adam launch reads
 
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
 
     def broadcast_from_rank0(self):
-        if self.world > 1:
+        if self.dist_on:
             dist.broadcast(self.flat, src=0)
 
     def all_reduce_grads(self):
-        if self.world > 1:
+        """One NCCL all-reduce (sum) of the whole gradient bucket; the 1/world factor is applied inside the Adam kernel.
+        Enqueued on the current stream, so it is also recorded by a CUDA-graph capture of the step (GraphedStep)."""
+        if self.dist_on:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
 
     def hyper(self):
@@ -236,8 +240,6 @@ class GraphedStep:
         self.opts = [model.optimizer_D, model.optimizer_G]
         if not all(isinstance(o, FlatAdam) for o in self.opts):
             raise NotImplementedError("GraphedStep needs the flat-bucket Adam optimizers (--optimizer adam)")
-        if self.opts[0].world > 1:
-            raise NotImplementedError("GraphedStep: single-process only (the NCCL all-reduce is not captured yet)")
         n = 2 + 4 * len(self.opts)                                   # [dropout epoch (int64 as 2 floats) | 4 floats per Adam]
         self.host = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(self.SLOTS)]
         self.done = [None] * self.SLOTS
@@ -327,6 +329,15 @@ class GraphedStep:
 def _sync_and_step(optimizer):
     if isinstance(optimizer, FlatAdam):
         optimizer.all_reduce_grads()
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # generic torch optimizers (--optimizer other than adam): average every gradient across the ranks, the job
+        # DistributedDataParallel does in the reference (networks.py:131-136)
+        world = dist.get_world_size()
+        for group in optimizer.param_groups:
+            for p_ in group["params"]:
+                if p_.grad is not None:
+                    dist.all_reduce(p_.grad)
+                    p_.grad.div_(world)
     optimizer.step()
     if not isinstance(optimizer, FlatAdam):
         networks._EngineBacked.GLOBAL_VERSION += 1
@@ -435,6 +446,11 @@ def make_optimizers(model):
     """Replace the model's optimizers by flat-bucket fused Adam when --optimizer adam (the default)."""
     opt = model.opt
     if str(opt.optimizer).lower() != "adam":
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for nm in model.model_names:                 # same initial weights on every rank (DDP's constructor broadcast)
+                for t in list(model._net(nm).parameters()) + list(model._net(nm).buffers()):
+                    dist.broadcast(t.data, src=0)
+            networks._EngineBacked.GLOBAL_VERSION += 1
         return
     g = [p for nm in model.model_names_g + model.model_names_gs for p in model._net(nm).parameters()]
     d = [p for nm in model.model_names_d + model.model_names_ds for p in model._net(nm).parameters()]
@@ -453,9 +469,17 @@ def run_training(params):
     rank = int(os.environ.get("RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("deepliif train needs a CUDA (sm_100a) device: there is no CPU fallback")
-    torch.cuda.set_device(local)
+    # reference cli.py:247-256: under torchrun every rank uses gpu_ids[LOCAL_RANK] and then sees it as its only GPU
+    ids = [g for g in (params.get("gpu_ids") or ()) if g is not None and int(g) >= 0]
+    if "LOCAL_RANK" in os.environ and world > 1:
+        dev_index = int(ids[local]) if len(ids) > local else local
+    else:
+        dev_index = int(ids[0]) if ids else local
+    torch.cuda.set_device(dev_index)
+    params = dict(params, gpu_ids=(dev_index,))
+    local = dev_index
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev_index))
     if params.get("seed") is not None:
         torch.manual_seed(params["seed"]); np.random.seed(params["seed"])
     opt = build_options(params)
@@ -468,7 +492,8 @@ def run_training(params):
     ds = AlignedDataset(opt, "train")                 # uint8 tiles; ToTensor + Normalize run on the device
     sampler = torch.utils.data.distributed.DistributedSampler(ds, world, rank, shuffle=True) if world > 1 else None
     loader = torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=sampler is None and not opt.serial_batches,
-                                         sampler=sampler, num_workers=opt.num_threads, collate_fn=collate_u8, drop_last=False)
+                                         sampler=sampler, num_workers=opt.num_threads, collate_fn=collate_u8, drop_last=False,
+                                         pin_memory=True)
     dl = DeviceBatches(loader, torch.device("cuda", local), input_no=getattr(opt, "input_no", 1))
     model = create_model(opt)
     model.setup(opt)

@@ -77,6 +77,39 @@ int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void*
                     const void* w_lo, const float* bias, float* y, int fmt, int split, int n_tile,
                     void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream);
 
+/* Fused operand load: the same convolution, but the input is given as the PRODUCER's raw fp32 output plus the
+ * normalisation / activation / skip-add that sits between the two layers in the reference
+ * (ResnetBlock: Conv -> Norm -> ReLU -> Conv -> Norm -> +x, networks.py:490-513; ResnetGenerator down/up stages :399-436;
+ * the Pad(3) in front of the head :438-444).  Converter warps inside the kernel evaluate
+ *     a[n,h,w,c] = act(x[n,h,w,c] * scale[n,c] + shift[n,c]) + residual[n,h,w,c]
+ * on the fly, split it into hi/lo 16-bit values and write them into the shared-memory operand tile the tensor core
+ * reads — the operand planes never exist in HBM and dlb_norm_apply is not launched.
+ *   x, residual (nullable), out (nullable): fp32 NHWC [N, H-2*border, W-2*border, Cin[s]];
+ *   scale/shift (nullable together): fp32 [N, Cin[s]] from dlb_norm_finalize / dlb_norm_stats;
+ *   border / border_mode: the conv input is the source behind `border` pixels of zeros or reflection
+ *     (nn.ReflectionPad2d(border) + conv padding 0); d->H, d->W are the extents INCLUDING the border;
+ *   out: when given, the evaluated operand `a` is also written there once (fp32) — the ResnetBlock residual stream
+ *     for the next block; needs a stride-1 convolution with OH == H-2*border, OW == W-2*border.
+ * One dlb_fused_src per K-source (d->nsrc).  Everything else as dlb_conv_tc_fwd. */
+typedef struct dlb_fused_src {
+  const float* x;
+  const float* scale;
+  const float* shift;
+  int act;
+  const float* residual;
+  float* out;
+  int border;
+  int border_mode;
+} dlb_fused_src;
+/* How dlb_conv_tc_fwd_fused would run this layer: 2 = every phase in halo-strip mode (each input value converted once per
+ * output tile; the efficient case: stride-1 layers on maps of at least 16 x 8), 1 = vertical-strip mode with resident
+ * weights (R x 1 filters: the head), 0 = at least one phase would fall back to per-tap conversion (stride-2 layers, tiny
+ * maps) — still correct, but slower than dlb_norm_apply + dlb_conv_tc_fwd; callers use this to choose. */
+int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_tile);
+int dlb_conv_tc_fwd_fused(const dlb_conv_desc* d, const dlb_fused_src* src, const void* w_hi, const void* w_lo,
+                          const float* bias, float* y, int fmt, int split, int n_tile, void* stats_ws,
+                          size_t stats_ws_bytes, dlb_stream_t stream);
+
 /* fp32 CUDA-core convolution for the layers tensor cores cannot tile (Cin = 3 stem, networks.py:386-397;
  * Cout = 3 head + Tanh, :438-444; PatchGAN first/last convs, :638, :659).  Fuses the producer's
  * normalisation + activation on the input side: x' = act_in(x * in_scale[n,c] + in_shift[n,c]) (zero /
@@ -108,6 +141,18 @@ int dlb_norm_finalize(void* workspace, size_t workspace_bytes, int N, int HW, in
 int dlb_norm_stats(const float* y, int N, int HW, int C, int pooled, const float* gamma, const float* beta,
                    float eps, float* scale, float* shift, float* mean, float* rstd, void* workspace,
                    size_t workspace_bytes, dlb_stream_t stream);
+/* Training-mode nn.BatchNorm2d (track_running_stats=True, networks.py:34-37): the pooled (batch) forms of the two calls
+ * above that also update the module's buffers the way torch does — running_mean / running_var <- (1-momentum)*running +
+ * momentum*(batch mean / UNBIASED batch variance), num_batches_tracked (int64 scalar, nullable) += 1 — inside the same
+ * finalize kernel, so checkpoints written after training carry the statistics the reference would have written
+ * (base_model.py:190-212). */
+int dlb_norm_finalize_bn(void* workspace, size_t workspace_bytes, int N, int HW, int C, const float* gamma, const float* beta,
+                         float eps, float* scale, float* shift, float* mean, float* rstd, float* running_mean,
+                         float* running_var, long long* num_batches_tracked, float momentum, dlb_stream_t stream);
+int dlb_norm_stats_bn(const float* y, int N, int HW, int C, const float* gamma, const float* beta, float eps, float* scale,
+                      float* shift, float* mean, float* rstd, float* running_mean, float* running_var,
+                      long long* num_batches_tracked, float momentum, void* workspace, size_t workspace_bytes,
+                      dlb_stream_t stream);
 int dlb_norm_apply(const float* y, const float* scale, const float* shift, int act, const float* residual,
                    float* out_f32, void* out_hi, void* out_lo, int fmt, int N, int H, int W, int C, int pad,
                    int pad_mode, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_epoch,

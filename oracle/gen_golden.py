@@ -205,6 +205,95 @@ def e2e_fixture():
     save("e2e_infer_modalities", **arrs)
 
 
+def _e2e_model_dir():
+    """The model directory of the e2e fixtures: train_opt.txt written by this package's trainer options, nine seeded .pth."""
+    import tempfile
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.options import print_options
+    root = tempfile.mkdtemp()
+    p = dict(TRAIN_DEFAULTS, dataroot=root, checkpoints_dir=root, name="m", gpu_ids=(0,),
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25])
+    print_options(training.build_options(p), save=True)
+    mdir = os.path.join(root, "m")
+    for k, sd in e2e_state_dicts().items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    return mdir
+
+
+REAL_TILE = "/root/reference/Datasets/Sample_Dataset/test_cli/22_2.png"          # BASELINE config 1's tile
+REAL_ROI = ("/root/reference/Sample_Large_Tissues/ROI_7.png", (120, 200, 1120, 800))   # BASELINE config 3: crop box (l, t, r, b)
+
+
+def realtile_fixture():
+    """BASELINE configs[0]: the reference's `deepliif test` body (infer_modalities, cli.py:833-919) on the REAL sample tile
+    Datasets/Sample_Dataset/test_cli/22_2.png — PIL decode, transform, is_empty on real content, the nine generators, seg
+    aggregation, tensor2im, postprocess.  The PNG bytes travel inside the fixture (the GPU box has no /root/reference).
+    Stored at full resolution: Seg and Marker (the inputs of the mask / scoring); the other outputs 2x subsampled + sums."""
+    import io
+    from PIL import Image
+    import_reference()
+    import deepliif.models as RM
+    import deepliif.util as RU
+    mdir = _e2e_model_dir()
+    png = open(REAL_TILE, "rb").read()
+    img = Image.open(io.BytesIO(png)).convert("RGB")
+    torch.set_num_threads(os.cpu_count())
+    images, scoring = RM.infer_modalities(img, 512, mdir, eager_mode=True, return_seg_intermediate=True)
+    arrs = {"png": np.frombuffer(png, dtype=np.uint8),
+            "names": np.frombuffer(json.dumps(sorted(images)).encode(), dtype=np.uint8),
+            "scoring": np.frombuffer(json.dumps(scoring, sort_keys=True).encode(), dtype=np.uint8),
+            "variance": np.array(RU.image_variance_gray(img)), "is_empty": np.array(bool(RM.is_empty(img)))}
+    for k, im in images.items():
+        a = np.asarray(im)
+        full = k in ("Seg", "mod4-Marker", "SegOverlaid", "SegRefined")
+        arrs[f"{k}__full" if full else f"{k}__sub2"] = a.copy() if full else a[::2, ::2].copy()
+        arrs[f"{k}__sum"] = checksum(a)
+        arrs[f"{k}__shape"] = np.array(a.shape)
+    print("real tile outputs:", sorted(images), scoring)
+    save("real_tile_22_2", **arrs)
+
+
+def wsi_fixture():
+    """BASELINE configs[2]: the reference's inference() (models/__init__.py:464-579: InferenceTiler, run_dask per tile,
+    stitching) at tile_size=512, overlap_size=56 on a REAL 1000 x 600 region of Sample_Large_Tissues/ROI_7.png (6 tiles),
+    plus the InferenceTiler tile counts of all five ROIs at overlap 56 and 32.  Stored: the region as PNG bytes, Seg and
+    Marker 2x subsampled + sums, the other outputs 4x subsampled + sums."""
+    import io
+    from PIL import Image
+    import_reference()
+    import deepliif.models as RM
+    import deepliif.util as RU
+    mdir = _e2e_model_dir()
+    path, box = REAL_ROI
+    region = Image.open(path).convert("RGB").crop(box)
+    buf = io.BytesIO(); region.save(buf, format="PNG", optimize=True)
+    png = buf.getvalue()
+    img = Image.open(io.BytesIO(png)).convert("RGB")
+    torch.set_num_threads(os.cpu_count())
+    opt = RM.get_opt(mdir)
+    images = RM.inference(img, tile_size=512, overlap_size=56, model_path=mdir, eager_mode=True, opt=opt,
+                          seg_weights=opt.seg_weights)
+    counts = {}
+    import glob
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(path), "*.png"))):
+        im = Image.open(f).convert("RGB")
+        counts[os.path.basename(f)] = {"size": list(im.size),
+                                       "tiles_overlap56": sum(1 for _ in RU.InferenceTiler(im, 512, 56)),
+                                       "tiles_overlap32": sum(1 for _ in RU.InferenceTiler(im, 512, 32))}
+    arrs = {"png": np.frombuffer(png, dtype=np.uint8), "names": np.frombuffer(json.dumps(sorted(images)).encode(), dtype=np.uint8),
+            "roi_tile_counts": np.frombuffer(json.dumps(counts, sort_keys=True).encode(), dtype=np.uint8),
+            "n_tiles": np.array(sum(1 for _ in RU.InferenceTiler(img, 512, 56)))}
+    for k, im in images.items():
+        a = np.asarray(im)
+        st = 2 if k in ("Seg", "mod4-Marker") else 4
+        arrs[f"{k}__sub{st}"] = a[::st, ::st].copy()
+        arrs[f"{k}__sum"] = checksum(a)
+        arrs[f"{k}__shape"] = np.array(a.shape)
+    print("wsi region outputs:", sorted(images), "tiles:", int(arrs["n_tiles"]), counts)
+    save("wsi_region_overlap56", **arrs)
+
+
 TRAIN_CASE = dict(modalities_no=2, seg_gen=True, net_g="resnet_2blocks", net_gs="unet_128", norm="batch", no_dropout=True,
                   padding="zero", batch_size=1, hw=128)
 
@@ -267,6 +356,15 @@ def train_step_fixture():
     arrs = {"losses": np.frombuffer(json.dumps(losses, sort_keys=True).encode(), dtype=np.uint8)}
     for name, key in (("G1", "model.1.weight"), ("GS0", "model.model.0.weight"), ("D1", "model.0.weight"), ("DS2", "model.0.weight")):
         arrs[f"{name}__{key}"] = getattr(model, "net" + name).state_dict()[key].detach().numpy().copy()
+        # the gradient the reference's Adam consumed (still in .grad after the step): lets the tests separate gradient
+        # parity (floating point) from optimizer parity (our fused Adam on THIS gradient must land on the same weights)
+        arrs[f"{name}__{key}__grad"] = dict(getattr(model, "net" + name).named_parameters())[key].grad.detach().numpy().copy()
+    # BatchNorm2d buffers after the step (momentum 0.1, unbiased batch variance; a discriminator is run three times per
+    # step — fake, real, fake-for-G — and moves its statistics three times): what the reference writes into its .pth files
+    for name, key in (("G1", "model.2"), ("G1", "model.5"), ("GS0", "model.model.1.model.2"), ("D1", "model.3"), ("DS2", "model.6")):
+        sd_ = getattr(model, "net" + name).state_dict()
+        for suffix in ("running_mean", "running_var", "num_batches_tracked"):
+            arrs[f"{name}__{key}.{suffix}"] = sd_[f"{key}.{suffix}"].detach().numpy().copy()
     save("train_step", **arrs)
 
 
@@ -475,6 +573,10 @@ def main():
         return scheduler_fixture()
     if "train" in sys.argv[1:]:
         return train_step_fixture()
+    if "realtile" in sys.argv[1:]:
+        return realtile_fixture()
+    if "wsi" in sys.argv[1:]:
+        return wsi_fixture()
     if "e2e" in sys.argv[1:]:
         return e2e_fixture()
     if "cells" in sys.argv[1:]:

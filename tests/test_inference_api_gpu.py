@@ -78,7 +78,8 @@ def test_infer_modalities_matches_oracle_cascade(tmp_path):
     mask_got = pixel.create_posneg_mask(np.asarray(images["Seg"]))
     mism = int((mask_ref != mask_got).sum())
     print(f"posneg mask pixel mismatches vs oracle-from-fp32: {mism} of {mask_ref.size}")
-    assert mism <= 0.005 * mask_ref.size
+    # measured on B200: 0 of 262144 (the 1e-4 fp32 differences straddle no mask threshold on this fixture); pinned, not a band
+    assert mism == 0
     # explicit seg_weights (what `deepliif test` passes down from train_opt.txt, cli.py:878): same parts, other weights
     w2 = [0.25, 0.15, 0.25, 0.1, 0.25]
     images2, _ = infer_modalities(Image.fromarray(img), 512, mdir, seg_weights=w2)

@@ -225,3 +225,82 @@ def test_conv_tc_fused_stats(ops, case, pooled):
         sc2, sh2 = ops.norm_stats(y, gamma, beta, pooled)
         assert (sc - sc2).abs().max().item() <= 2e-6 * sc2.abs().max().item()
         assert (sh - sh2).abs().max().item() <= 5e-6 * max(1.0, sh2.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------
+# fused operand load: conv that evaluates norm + activation (+ residual, + border) while loading
+# ------------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    # name, N, H, W, cins, Cout, R, stride, pad, transposed, outpad, n_tile, border, border_mode, residual, write_back, act
+    ("trunk_zero", 2, 32, 32, [256], 256, 3, 1, 1, False, 0, 0, 0, 0, False, False, 1),
+    ("trunk_zero_resid_wb", 1, 16, 24, [256], 256, 3, 1, 1, False, 0, 0, 0, 0, True, True, 0),
+    ("trunk_reflect_resid_wb", 2, 16, 16, [128], 128, 3, 1, 0, False, 0, 0, 1, 1, True, True, 0),
+    ("trunk_ragged", 1, 21, 37, [64], 128, 3, 1, 1, False, 0, 0, 0, 0, False, False, 1),
+    ("small_planes_tile_n", 5, 4, 8, [64], 64, 3, 1, 1, False, 0, 0, 0, 0, True, True, 2),
+    ("down_s2", 2, 64, 64, [64], 128, 3, 2, 1, False, 0, 0, 0, 0, False, False, 1),
+    ("unet_down_k4s2_lrelu", 1, 32, 32, [128], 256, 4, 2, 1, False, 0, 0, 0, 0, False, False, 2),
+    ("up_ct3s2", 1, 16, 16, [256], 128, 3, 2, 1, True, 1, 0, 0, 0, True, False, 0),
+    ("unet_up_ct4s2_cat", 2, 8, 8, [256, 256], 128, 4, 2, 1, True, 0, 0, 0, 0, False, False, 1),
+    ("head_vs_zero3", 1, 16, 64, [64], 32, (7, 1), 1, 0, False, 0, 32, 3, 0, False, False, 1),
+    ("head_vs_reflect3", 2, 32, 16, [64], 32, (7, 1), 1, 0, False, 0, 32, 3, 1, False, False, 1),
+    ("n_tile128_two_cout_tiles_wb", 1, 16, 16, [256], 256, 3, 1, 1, False, 0, 128, 0, 0, True, True, 0),
+    ("hs_multi_tile_resid_wb", 3, 48, 40, [128], 256, 3, 1, 1, False, 0, 0, 0, 0, True, True, 1),
+    ("hs_unet_up_ct4s2_cat", 1, 32, 16, [128, 128], 64, 4, 2, 1, True, 0, 0, 0, 0, False, False, 1),
+    ("hs_reflect_ragged", 1, 19, 27, [64], 64, 3, 1, 0, False, 0, 0, 1, 1, True, True, 0),
+    ("tap_mode_k4s1_patchgan", 1, 20, 20, [256], 512, 4, 1, 1, False, 0, 0, 0, 0, False, False, 2),
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_conv_tc_fused_operand_is_bit_identical_to_apply_then_conv(ops, case, prec):
+    """dlb_conv_tc_fwd_fused(raw, scale, shift, act, residual, border) == dlb_norm_apply(...) -> dlb_conv_tc_fwd, bit for
+    bit (same operand arithmetic, same MMA order), and the written-back operand == dlb_norm_apply's fp32 output."""
+    name, N, Hs, Ws, cins, Cout, R, st, pad, tr, op, n_tile, b, bmode, use_res, wb, act = case
+    R, S = (R if isinstance(R, tuple) else (R, R))
+    fmt = ops.FMT_FP16 if prec.startswith("fp16") else ops.FMT_BF16
+    split = prec.endswith("x3")
+    Cin = sum(cins)
+    w = _rand((Cin, Cout, R, S) if tr else (Cout, Cin, R, S), 42, 0.05)
+    bias = _rand((Cout,), 43, 0.1).cuda()
+    H, W = Hs + 2 * b, Ws + 2 * b
+    d = ops.conv_desc(N, H, W, cins, Cout, R, S, st, pad, tr, op)
+    w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), fmt, split)
+    srcs, his, los, f32s, outs = [], [], [], [], []
+    for i, c in enumerate(cins):
+        raw = (_rand((N, Hs, Ws, c), 50 + i) * 2).cuda()
+        sc = (1 + 0.3 * _rand((N, c), 60 + i)).cuda()
+        sh = (0.4 * _rand((N, c), 70 + i)).cuda()
+        if name == "up_ct3s2":
+            sc = sh = None                                         # identity transform path (scale == NULL)
+        res = _rand((N, Hs, Ws, c), 80 + i).cuda() if (use_res and i == 0) else None
+        f32, hi, lo = ops.norm_apply(raw, sc, sh, act, res, want_f32=True, want_split=True, fmt=fmt, pad=b, pad_mode=bmode,
+                                     need_lo=split)
+        out = torch.full_like(raw, float("nan")) if (wb and i == 0) else None
+        srcs.append(dict(x=raw, scale=sc, shift=sh, act=act, residual=res, out=out, border=b, border_mode=bmode))
+        his.append(hi); los.append(lo); f32s.append(f32); outs.append(out)
+    y_ref = ops.conv_tc(d, his, los, w_hi, w_lo, bias, fmt, split, n_tile)
+    y = ops.conv_tc_fused(d, srcs, w_hi, w_lo, bias, fmt, split, n_tile)
+    mode = ops.conv_tc_fused_mode(d, split, n_tile)
+    assert mode == (2 if name.startswith(("trunk", "up_ct", "n_tile128", "hs_")) else 1 if name.startswith("head_vs") else 0), mode
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref), (name, (y - y_ref).abs().max().item())
+    if wb:
+        assert torch.equal(outs[0], f32s[0])
+
+
+def test_conv_tc_fused_operand_with_fused_stats(ops):
+    """The fused-operand kernel keeps the epilogue statistics: finalize(ws) == statistics of its stored output."""
+    N, H, W, C = 2, 32, 32, 128
+    raw = (_rand((N, H, W, C), 91) * 2).cuda()
+    sc = (1 + 0.3 * _rand((N, C), 92)).cuda(); sh = (0.4 * _rand((N, C), 93)).cuda()
+    w = _rand((C, C, 3, 3), 94, 0.05)
+    d = ops.conv_desc(N, H, W, [C], C, 3, 3, 1, 1, False, 0)
+    w_hi, w_lo = ops.pack_weights_tc(d, w.cuda(), ops.FMT_BF16, True)
+    ws = ops.stats_workspace(N, H * W, C, "cuda")
+    y = ops.conv_tc_fused(d, [dict(x=raw, scale=sc, shift=sh, act=ops.ACT_RELU)], w_hi, w_lo, None, ops.FMT_BF16, True, 0,
+                          stats_ws=ws)
+    s1, h1 = ops.norm_finalize(ws, N, H * W, C, None, None, False)
+    s2, h2 = ops.norm_stats(y, None, None, False)
+    assert (s1 - s2).abs().max().item() <= 2e-6 * s2.abs().max().item()
+    assert (h1 - h2).abs().max().item() <= 5e-6 * max(1.0, h2.abs().max().item())
