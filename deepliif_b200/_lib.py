@@ -31,12 +31,14 @@ _vpp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "dlb_last_error": (C.c_char_p, []),
     "dlb_version": (_i, []),
+    "dlb_release_thread_resources": (_i, []),
     "dlb_conv_out_shape": (_i, [_cd, C.POINTER(_i), C.POINTER(_i)]),
     "dlb_pack_weights_tc": (_i, [_cd, _vp, _i, _vp, _vp, _vp]),
     "dlb_pack_weights_direct": (_i, [_cd, _vp, _vp, _vp]),
     "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_tc_fused_mode": (_i, [_cd, _i, _i]),
     "dlb_conv_tc_fwd_fused": (_i, [_cd, C.POINTER(FusedSrc), _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dlb_conv_tc_fwd_stem": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_direct_fwd": (_i, [_cd, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dlb_norm_stats_workspace": (_sz, [_i, _i, _i]),
     "dlb_norm_finalize": (_i, [_vp, _sz, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -196,11 +196,24 @@ def trainlaunch(ctx, use_torchrun):
 @click.option("--epoch", default="latest", type=str)
 @click.option("--verbose", default=0, type=int)
 def serialize(model_dir, output_dir, device, epoch, verbose):
-    """Not needed here: the reference traces its cuDNN graphs to TorchScript to speed up loading (cli.py:760-830); this
-    package always builds its sm_100a engines from the state_dicts.  Directories the reference serialized (G1.pt ...) are
-    read directly by `test` / init_nets (the weights are extracted)."""
-    raise click.UsageError("deepliif_b200 has no TorchScript export: its engines are built from the .pth state_dicts at load "
-                           "time; `test` reads both .pth directories and directories serialized by the reference")
+    """Write the load-ready form of a model directory (the counterpart of the reference's TorchScript export,
+    cli.py:760-830): per generator one `<name>.pt` holding the fp32 weights (reference state_dict keys) AND the repacked
+    tensor-core operand planes ([tap][Cout][Cin] hi/lo 16-bit, what dlb_conv_tc_fwd consumes), plus train_opt.txt.
+    `test` / init_nets read such a directory like any other (weights_only load: a model directory is data, not code)."""
+    import shutil
+    from .models.serialized import write_packed_dir
+    if not torch.cuda.is_available():
+        raise click.UsageError("deepliif serialize packs the weights with the sm_100a library: a CUDA device is needed")
+    output_dir = output_dir or model_dir
+    os.makedirs(output_dir, exist_ok=True)
+    opt = Options(path_file=os.path.join(model_dir, "train_opt.txt"), mode="test")
+    opt.epoch = epoch
+    opt.gpu_ids = [torch.cuda.current_device()]
+    files = write_packed_dir(model_dir, output_dir, opt, verbose=bool(verbose))
+    if os.path.abspath(output_dir) != os.path.abspath(model_dir):
+        shutil.copy(os.path.join(model_dir, "train_opt.txt"), os.path.join(output_dir, "train_opt.txt"))
+    for f in files:
+        print("wrote", f)
 
 
 if __name__ == "__main__":

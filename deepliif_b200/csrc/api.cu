@@ -1,5 +1,7 @@
 // C-ABI front end: error reporting, layer geometry, and the lowering of nn.Conv2d / nn.ConvTranspose2d
 // semantics to tap-list phases executed by conv_tc.cu (tcgen05) or conv_direct.cu (fp32 CUDA cores).
+#include <mutex>
+
 #include "internal.h"
 #include "stats_ws.h"
 
@@ -15,6 +17,40 @@ int set_cuda_error(const char* where) {
   cudaError_t e = cudaGetLastError();
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
   return DLB_ERR_CUDA;
+}
+
+namespace {
+struct DeviceFacts { int num_sms = 0; bool smem_set[kNumSmemSlots] = {}; };
+std::mutex g_facts_mu;
+DeviceFacts g_facts[64];
+
+int current_device(int* dev) {
+  if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= 64) return set_cuda_error("cudaGetDevice");
+  return 0;
+}
+}  // namespace
+
+int ensure_dyn_smem(const void* func, int bytes, int slot) {
+  int dev = 0;
+  if (current_device(&dev) != 0) return DLB_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_facts_mu);
+  if (!g_facts[dev].smem_set[slot]) {
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+      return set_cuda_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    g_facts[dev].smem_set[slot] = true;
+  }
+  return 0;
+}
+
+int device_num_sms(int* num_sms) {
+  int dev = 0;
+  if (current_device(&dev) != 0) return DLB_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_facts_mu);
+  if (g_facts[dev].num_sms == 0 &&
+      cudaDeviceGetAttribute(&g_facts[dev].num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return set_cuda_error("cudaDeviceGetAttribute(multiProcessorCount)");
+  *num_sms = g_facts[dev].num_sms;
+  return 0;
 }
 
 namespace {
@@ -83,9 +119,35 @@ extern "C" int dlb_version(void) { return 100; }
 
 extern "C" int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW) { return out_shape(d, OH, OW); }
 
+namespace {
+struct ForkRes { cudaStream_t aux[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr; cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr}; };
+thread_local ForkRes t_fork[64];
+}  // namespace
+
+extern "C" int dlb_release_thread_resources(void) {
+  int keep = 0;
+  cudaGetDevice(&keep);
+  for (int dev = 0; dev < 64; ++dev) {
+    ForkRes& fr = t_fork[dev];
+    if (fr.aux[0] == nullptr && fr.ev_fork == nullptr) continue;
+    cudaSetDevice(dev);
+    for (int i = 0; i < 3; ++i) {
+      if (fr.aux[i] != nullptr) cudaStreamDestroy(fr.aux[i]);
+      if (fr.ev_join[i] != nullptr) cudaEventDestroy(fr.ev_join[i]);
+    }
+    if (fr.ev_fork != nullptr) cudaEventDestroy(fr.ev_fork);
+    fr = ForkRes();
+  }
+  cudaSetDevice(keep);
+  return 0;
+}
+
+struct StemSrc { const float* x; int C, S, pad, pad_mode; };
+
 static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
                             const dlb_fused_src* fsrc, const void* w_hi, const void* w_lo, const float* bias, float* y,
-                            int fmt, int split, int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
+                            int fmt, int split, int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream,
+                            const StemSrc* stem = nullptr) {
   int OH, OW;
   if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
   if (d->pad_mode != DLB_PAD_ZERO) return set_error("dlb_conv_tc_fwd: zero padding only (reflect border comes from dlb_norm_apply / dlb_fused_src.border)");
@@ -104,7 +166,7 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     sp = stats_ptrs(stats_ws, L);
     for (int i = 0; i < np; ++i) {
       int tw, th, tn, nt;
-      tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, fsrc != nullptr);
+      tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, fsrc != nullptr || stem != nullptr);
       if (tn != 1) return set_error("dlb_conv_tc_fwd: fused statistics need OH*OW >= 128 per phase (use dlb_norm_stats)");
       slice_base[i] = S_total;
       S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw) * 4;
@@ -122,8 +184,18 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     const long long m_tiles = (static_cast<long long>(d->N) * geo[0].OH * geo[0].OW + 127) / 128;
     fork = m_tiles * ((d->Cout + nt_eff - 1) / nt_eff) < 74;
   }
-  static thread_local cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-  static thread_local cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  // helper streams / events: created lazily, once per (host thread, device) — the one exception to "no entry point
+  // allocates"; dlb_release_thread_resources() destroys the calling thread's
+  ForkRes unused;
+  ForkRes* fr = &unused;
+  if (fork) {
+    int dev = 0;
+    if (current_device(&dev) != 0) return DLB_ERR_CUDA;
+    fr = &t_fork[dev];
+  }
+  cudaStream_t* aux = fr->aux;
+  cudaEvent_t* ev_join = fr->ev_join;
+  cudaEvent_t& ev_fork = fr->ev_fork;
   if (fork) {
     if (aux[0] == nullptr) {
       for (int i = 0; i < 3; ++i) {
@@ -142,8 +214,13 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     memset(&ph, 0, sizeof(ph));
     static_cast<PhaseGeom&>(ph) = geo[i];
     ph.nsrc = d->nsrc;
+    if (stem != nullptr) {
+      ph.fa = 2; ph.fa_x[0] = stem->x; ph.stem_C = stem->C; ph.stem_S = stem->S; ph.stem_pad = stem->pad;
+      ph.fa_border = 0; ph.fa_border_mode = stem->pad_mode; ph.fa_act[0] = DLB_ACT_NONE;
+    }
     for (int s = 0; s < d->nsrc; ++s) {
       ph.cin[s] = d->Cin[s];
+      if (stem != nullptr) continue;
       if (fsrc == nullptr) { ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; continue; }
       ph.fa = 1;
       ph.fa_x[s] = fsrc[s].x; ph.fa_scale[s] = fsrc[s].scale; ph.fa_shift[s] = fsrc[s].shift; ph.fa_res[s] = fsrc[s].residual;
@@ -202,6 +279,20 @@ extern "C" int dlb_conv_tc_fwd_fused(const dlb_conv_desc* d, const dlb_fused_src
                                      size_t stats_ws_bytes, dlb_stream_t stream) {
   if (src == nullptr) return set_error("dlb_conv_tc_fwd_fused: src is null");
   return conv_tc_fwd_impl(d, nullptr, nullptr, src, w_hi, w_lo, bias, y, fmt, split, n_tile, stats_ws, stats_ws_bytes, stream);
+}
+
+extern "C" int dlb_conv_tc_fwd_stem(const float* x_nchw, int N, int C, int H, int W, int pad, int S, int pad_mode, int Cout,
+                                    const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split,
+                                    int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream) {
+  if (x_nchw == nullptr) return set_error("dlb_conv_tc_fwd_stem: x is null");
+  if (S != 2 * pad + 1) return set_error("dlb_conv_tc_fwd_stem: S must be 2 * pad + 1");
+  dlb_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.N = N; d.H = H + 2 * pad; d.W = W; d.nsrc = 1; d.Cin[0] = 64; d.Cout = Cout; d.R = S; d.S = 1; d.stride = 1; d.pad = 0;
+  d.pad_mode = DLB_PAD_ZERO;
+  const StemSrc st{x_nchw, C, S, pad, pad_mode};
+  return conv_tc_fwd_impl(&d, nullptr, nullptr, nullptr, w_hi, w_lo, bias, y, fmt, split, n_tile, stats_ws, stats_ws_bytes,
+                          stream, &st);
 }
 
 extern "C" int dlb_conv_direct_fwd(const dlb_conv_desc* d, const float* x, int in_nchw, const float* in_scale,

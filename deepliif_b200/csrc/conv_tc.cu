@@ -43,7 +43,7 @@ constexpr int kConvWarps = 8;          // fused-operand mode: warps 6-13 build t
 constexpr int kThreadsFa = kThreads + 32 * kConvWarps;
 constexpr int kHsMaxPx = 192;          // halo-strip mode: at most this many strip pixels (3x3: 18 x 10 = 180; 2x2 taps: 17 x 9)
 constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
-constexpr int kStaticSmem = 18 * 1024; // barriers + statistics transpose buffers (static __shared__), rounded up
+constexpr int kStaticSmem = 1024;      // barriers (static __shared__), rounded up
 constexpr int kMaxDynSmem = kSmemLimit - kStaticSmem - 1024;
 
 struct alignas(64) TcParams {
@@ -95,8 +95,12 @@ struct alignas(64) TcParams {
   // per tap — and each tap's MMAs address their shifted 16 x 8 pixel window of it directly: descriptor start =
   // strip + ((dh - dh_min) * cols + (dw - dw_min)) * 128 B, group stride (SBO) = cols * 128 B.  Weights stream per
   // (chunk, tap) through the stage ring as in tap mode.
-  int hs, hs_rows, hs_cols, hs_plane_bytes, hs_dh_min, hs_dw_min;
+  int hs, hs_rows, hs_cols, hs_plane_bytes, hs_dh_min, hs_dw_min, hs_nbuf;
   int hs_off[kMaxTaps];
+  // fa == 2 ("stem" source, vertical-strip mode only): fa_x[0] is the network input, fp32 NCHW [N, stem_C <= 4, Hs, Ws];
+  // the converters build the horizontal-window operand lane (s * 8 + c) = pad(x)[n, c, row - pad, col + s - pad] of
+  // dlb_stem_window_pack on the fly, so the 21x blown-up operand tensor never exists in HBM.
+  int stem_C, stem_S, stem_pad;
 };
 
 struct TileCoord {
@@ -156,6 +160,22 @@ __device__ __forceinline__ FaPix fa_locate(const TcParams& p, int src, int n, in
   return r;
 }
 
+// Column sums of a 32 x 32 tile held one row per lane (a[j] = element (lane, j)): a butterfly that halves the values per
+// lane at every step (16 + 8 + 4 + 2 + 1 = 31 shuffles); on return lane l holds the sum of column l.  Fixed tree order.
+__device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? a[i] : a[i + s];
+      const float keep = up ? a[i + s] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return a[0];
+}
+
 __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -163,10 +183,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
-  __shared__ __align__(8) uint64_t aready_bar;   // hs mode: operand strip written (converter warps)
-  __shared__ __align__(8) uint64_t afree_bar;    // hs mode: every MMA reading the strip has retired
+  __shared__ __align__(8) uint64_t aready_bar[2];   // hs mode: operand strip buffer written (converter warps)
+  __shared__ __align__(8) uint64_t afree_bar[2];    // hs mode: every MMA reading that strip buffer has retired
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float tr_smem[4][32][33];   // per-epilogue-warp transpose buffer for the fused column statistics
 
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -177,7 +196,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   const int vs_a_bytes = p.vs_rows * p.tile_w * 128;                 // one plane of an A strip (vs mode)
   const int stage_bytes = p.hs ? p.planes * b_bytes : (p.vs ? p.planes * vs_a_bytes : p.planes * (kABytes + b_bytes));
   const int kch0 = p.kchunks[0];
-  const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : (p.hs ? p.planes * p.hs_plane_bytes : 0);
+  const int strip_bytes = p.planes * p.hs_plane_bytes;              // one operand strip buffer (hs mode)
+  const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : (p.hs ? p.hs_nbuf * strip_bytes : 0);
   uint8_t* const stage_base = smem + bres_bytes;                     // resident weights / operand strip first, then the stage ring
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     // a stage is full when the TMA bytes have landed (producer's expect_tx arrival) and, in fused-operand mode, every
     // converter warp has written its share of the A planes
     const uint32_t full_count = ((p.fa && p.vs) ? 0u : 1u) + ((p.fa && !p.hs) ? static_cast<uint32_t>(kConvWarps) : 0u);
-    mbar_init(&aready_bar, kConvWarps); mbar_init(&afree_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&aready_bar[b], kConvWarps); mbar_init(&afree_bar[b], 1); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     mbar_init(&bres_bar, 1);
@@ -289,18 +309,19 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       int acc = 0; uint32_t acc_ph = 0;
       const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
       if (p.hs) {
-        const uint32_t strip_hi = smem_u32(smem), strip_lo = strip_hi + static_cast<uint32_t>(p.hs_plane_bytes);
         const uint32_t sbo = static_cast<uint32_t>(p.hs_cols) * 128u;
-        uint32_t aph = 0;
+        uint32_t g = 0;                                  // running chunk number: strip buffer g % nbuf, phase (g / nbuf) & 1
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
           uint32_t accumulate = 0;
           const int nchunks = p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0);
-          for (int ch = 0; ch < nchunks; ++ch) {
-            mbar_wait(&aready_bar, aph);                // the converters have written this chunk's strip
-            aph ^= 1;
+          for (int ch = 0; ch < nchunks; ++ch, ++g) {
+            const uint32_t buf = g % static_cast<uint32_t>(p.hs_nbuf);
+            const uint32_t strip_hi = smem_u32(smem) + buf * static_cast<uint32_t>(strip_bytes);
+            const uint32_t strip_lo = strip_hi + static_cast<uint32_t>(p.hs_plane_bytes);
+            mbar_wait(&aready_bar[buf], (g / static_cast<uint32_t>(p.hs_nbuf)) & 1u);   // converters wrote this strip
             tc_fence_after();
             for (int tap = 0; tap < p.ntaps; ++tap) {
               mbar_wait(&full_bar[s], ph);              // this tap's weights have landed
@@ -326,7 +347,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
               umma_commit(&empty_bar[s]);
               if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            umma_commit(&afree_bar);                    // strip may be overwritten once these MMAs retire
+            umma_commit(&afree_bar[buf]);               // strip buffer may be overwritten once these MMAs retire
           }
           umma_commit(&tfull_bar[acc]);
           acc ^= 1; if (acc == 0) acc_ph ^= 1;
@@ -452,22 +473,21 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
           }
         }
         if (p.st_partial != nullptr && cvalid) {
-          // column statistics over this warp's 32 pixels: transpose through shared memory, lane <-> channel
-          float (*tr)[33] = tr_smem[q];
+          // column statistics over this warp's 32 pixels (lane = pixel, v[j] = channel c + j): two shuffle butterflies,
+          // no shared memory; lane l ends up with (sum, M2 about the slice mean) of channel c + l
+          float a[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tr[lane][j] = __uint_as_float(v[j]);
-          __syncwarp();
-          float col[32];
-          float sum = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) { col[r] = tr[r][lane]; sum += ((vmask >> r) & 1u) ? col[r] : 0.f; }
+          for (int j = 0; j < 32; ++j) a[j] = valid ? __uint_as_float(v[j]) : 0.f;
+          const float sum = warp_colsum32(a, lane);
           const float cntf = static_cast<float>(__popc(vmask));
           const float mean = cntf > 0.f ? sum / cntf : 0.f;
-          float m2 = 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) { const float d = col[r] - mean; m2 += ((vmask >> r) & 1u) ? d * d : 0.f; }
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) - __shfl_sync(0xffffffffu, mean, j);
+            a[j] = valid ? d * d : 0.f;
+          }
+          const float m2 = warp_colsum32(a, lane);
           p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(sum, m2);
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -488,9 +508,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     int s = 0; uint32_t ph = 0;
     const int lw = 31 - __clz(p.tile_w), lh = 31 - __clz(p.tile_h);
     if (p.hs) {
-      // Strip units: unit u = (pixel u >> 4 of the strip, float4 q = u & 15); thread owns units ct + 256 * j.  A chunk is
-      // loaded, transformed and packed into registers while the MMAs still read the previous chunk's strip; the shared-
-      // memory burst waits for afree_bar.
+      // Strip units: unit u = (pixel u >> 4 of the strip, float4 q = u & 15); thread owns units ct + 256 * j.  The strip is
+      // double-buffered: the converters build chunk c + 1 while the MMAs read chunk c.
       constexpr int kUnits = kHsMaxPx * 16 / 256;              // units per thread for the largest admissible strip
       const int npx = p.hs_rows * p.hs_cols;
       const int nunits = (npx * 16 - ct + 255) / 256;          // units this thread owns
@@ -501,22 +520,23 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         const int row = px_i / p.hs_cols;
         rc[j] = (static_cast<uint32_t>(row) << 16) | static_cast<uint32_t>(px_i - row * p.hs_cols);
       }
-      uint8_t* const strip_hi = smem;
-      uint8_t* const strip_lo = smem + p.hs_plane_bytes;
-      uint32_t fph = 0;
+      uint32_t g = 0;                                          // running chunk number (same sequence as the MMA issuer)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         const int vh0 = tc.h0 + p.hs_dh_min, vw0 = tc.w0 + p.hs_dw_min;
         for (int src = 0; src < p.nsrc; ++src) {
           const bool wb = (p.fa_out[src] != nullptr) && (tc.cout0 == 0);
-          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+          for (int kc = 0; kc < p.kchunks[src]; ++kc, ++g) {
+            const uint32_t buf = g % static_cast<uint32_t>(p.hs_nbuf);
+            uint8_t* const strip_hi = smem + static_cast<size_t>(buf) * strip_bytes;
+            uint8_t* const strip_lo = strip_hi + p.hs_plane_bytes;
             const int cbase = kc * kKC + q * 4;
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.fa_scale[src] != nullptr && tc.n0 < p.N) {
               sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
               sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
             }
-            uint2 hi[kUnits], lo[kUnits];
+            bool waited = false;
 #pragma unroll
             for (int j0 = 0; j0 < kUnits; j0 += 4) {
               float4 xv[4], rv[4]; FaPix px[4];
@@ -533,9 +553,16 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
                   }
                 }
               }
+              if (!waited) {
+                // the first loads of the chunk are in flight before the (rarely blocking) wait for the buffer: the MMAs that
+                // read it belong to the chunk before the previous one (two buffers) / the previous one (one buffer)
+                mbar_wait(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
+                waited = true;
+              }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u;
+                if (j >= nunits) continue;
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
                 if (px[u].ok) {
                   o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[src]) + rv[u].x;
@@ -544,31 +571,25 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
                   o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[src]) + rv[u].w;
                   // write-back of the evaluated operand: the tile's own pixels only (each source pixel belongs to exactly
                   // one tile), i.e. strip positions whose output pixel (vh - border, vw - border) lies inside this tile
-                  if (wb && px[u].interior && j < nunits) {
+                  if (wb && px[u].interior) {
                     const int row = static_cast<int>(rc[j] >> 16), col = static_cast<int>(rc[j] & 0xffffu);
                     const int oh = vh0 + row - p.fa_border, ow = vw0 + col - p.fa_border;
                     if (oh >= tc.h0 && oh < tc.h0 + p.tile_h && ow >= tc.w0 && ow < tc.w0 + p.tile_w)
                       *reinterpret_cast<float4*>(p.fa_out[src] + px[u].off + cbase) = make_float4(o[0], o[1], o[2], o[3]);
                   }
                 }
-                fa_split4(o, p.fa_is_bf16, hi[j], lo[j]);
-              }
-            }
-            mbar_wait(&afree_bar, fph ^ 1);                    // MMAs of the previous chunk are done with the strip
-            fph ^= 1;
-#pragma unroll
-            for (int j = 0; j < kUnits; ++j) {
-              if (j < nunits) {
+                uint2 hi, lo;
+                fa_split4(o, p.fa_is_bf16, hi, lo);
                 const uint32_t px_i = static_cast<uint32_t>(ct + 256 * j) >> 4;
-                // absolute-address swizzle: the strip base is 1024 B aligned, so row bits [7,10) of the address = px_i & 7
+                // absolute-address swizzle: the strip buffers are 1024 B aligned, so address bits [7,10) = px_i & 7
                 const uint32_t off = px_i * 128u + (static_cast<uint32_t>(chunk ^ (px_i & 7u)) << 4) + sub;
-                *reinterpret_cast<uint2*>(strip_hi + off) = hi[j];
-                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + off) = lo[j];
+                *reinterpret_cast<uint2*>(strip_hi + off) = hi;
+                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + off) = lo;
               }
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&aready_bar);
+            if (lane == 0) mbar_arrive(&aready_bar[buf]);
           }
         }
       }
@@ -594,7 +615,27 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             for (int u = 0; u < 4; ++u) {
               const int idx = base + u * 16 + pr;
               xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; ok[u] = false;
-              if (idx < npx) {
+              if (idx < npx && p.fa == 2) {
+                // stem: lanes 4q..4q+3 = (tap s = q / 2, channels (q & 1) * 4 ..); only c < stem_C (<= 4) are non-zero
+                const int vh = vh0 + (idx >> 3), vw = vw0 + (idx & 7), st = q >> 1;
+                int hh = vh - p.stem_pad, ww = vw + st - p.stem_pad;
+                bool in = (tc.n0 < p.N) && (vh >= 0) && (vh < p.H) && (vw >= 0) && (vw < p.W) && ((q & 1) == 0) && (st < p.stem_S);
+                if (p.fa_border_mode == DLB_PAD_REFLECT) {
+                  if (hh < 0) hh = -hh; if (hh >= p.Hs) hh = 2 * p.Hs - 2 - hh;
+                  if (ww < 0) ww = -ww; if (ww >= p.Ws) ww = 2 * p.Ws - 2 - ww;
+                } else {
+                  in = in && hh >= 0 && hh < p.Hs && ww >= 0 && ww < p.Ws;
+                }
+                ok[u] = in;
+                if (in) {
+                  const float* xp = p.fa_x[0] + (static_cast<long long>(tc.n0) * p.stem_C * p.Hs + hh) * p.Ws + ww;
+                  const long long plane = static_cast<long long>(p.Hs) * p.Ws;
+                  xv[u].x = __ldg(xp);
+                  if (p.stem_C > 1) xv[u].y = __ldg(xp + plane);
+                  if (p.stem_C > 2) xv[u].z = __ldg(xp + 2 * plane);
+                  if (p.stem_C > 3) xv[u].w = __ldg(xp + 3 * plane);
+                }
+              } else if (idx < npx) {
                 const FaPix px = fa_locate(p, 0, tc.n0, vh0 + (idx >> 3), vw0 + (idx & 7));
                 ok[u] = px.ok;
                 if (px.ok) {
@@ -766,7 +807,7 @@ static bool hs_eligible(const PhaseGeom& g, int split, int n_tile) {
   if (rows * cols > kHsMaxPx) return false;
   const int planes = split ? 2 : 1;
   const long long strip = static_cast<long long>(planes) * ((rows * cols * 128 + 1023) / 1024 * 1024);
-  return strip + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem;
+  return strip + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem;       // one strip buffer + two weight stages at least
 }
 
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
@@ -808,12 +849,9 @@ static void tc_plan_tiles_novs(const TcPhase& ph, int* tile_w, int* tile_h, int*
 }
 
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
-  static int num_sms = 0;
-  static bool attr_set = false;
-  if (num_sms == 0) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int num_sms = 0;
+  if (device_num_sms(&num_sms) != 0) return DLB_ERR_CUDA;
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel), kMaxDynSmem, kSlotConvTc) != 0) return DLB_ERR_CUDA;
   TcParams p;
   memset(&p, 0, sizeof(p));
   const int is_bf16 = (ph.fmt == DLB_FMT_BF16);
@@ -881,9 +919,17 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     if (ph.split && !encode_tiled_map(&p.a_lo[s], ph.x_lo[s], is_bf16, 5, dims, strides, box)) return -1;
   }
   if (ph.fa) {
-    p.fa = 1; p.fa_is_bf16 = is_bf16; p.fa_wb_tap = -1;
+    p.fa = ph.fa; p.fa_is_bf16 = is_bf16; p.fa_wb_tap = -1;
+    p.stem_C = ph.stem_C; p.stem_S = ph.stem_S; p.stem_pad = ph.stem_pad;
     p.fa_border = ph.fa_border; p.fa_border_mode = ph.fa_border_mode;
     p.H = ph.H; p.W = ph.W; p.Hs = ph.H - 2 * ph.fa_border; p.Ws = ph.W - 2 * ph.fa_border; p.conv_stride = ph.stride;
+    if (ph.fa == 2) {
+      // stem source: H = Hs + 2 * pad rows of the window operand, W = Ws columns (the horizontal padding lives in the lanes)
+      p.Hs = ph.H - 2 * ph.stem_pad; p.Ws = ph.W;
+      if (!use_vs) return set_error("conv_tc: the fused stem needs the vertical-strip mode (image at least 16 x 8, S x 1 filter)");
+      if (ph.stem_C < 1 || ph.stem_C > 4 || ph.stem_S < 1 || ph.stem_S > 8 || ph.cin[0] != 64 || ph.nsrc != 1)
+        return set_error("conv_tc: fused stem needs C <= 4, S <= 8 and a 64-lane operand");
+    }
     if (p.Hs < 1 || p.Ws < 1) return set_error("conv_tc: fused operand border larger than the input");
     if (ph.fa_border_mode == DLB_PAD_REFLECT && (ph.fa_border >= p.Hs || ph.fa_border >= p.Ws))
       return set_error("conv_tc: reflect border must be smaller than the source");
@@ -909,6 +955,8 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       }
       p.hs = 1; p.hs_rows = tile_h + dh1 - dh0; p.hs_cols = tile_w + dw1 - dw0; p.hs_dh_min = dh0; p.hs_dw_min = dw0;
       p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
+      // two strip buffers when they still leave room for two weight stages (the 256 -> 256 trunk conv: 2 x 46 KB + 2 x 64 KB)
+      p.hs_nbuf = (2LL * p.planes * p.hs_plane_bytes + 2LL * p.planes * n_tile * 128 + 1024 <= kMaxDynSmem) ? 2 : 1;
       for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - dh0) * p.hs_cols + (ph.tap_dw[t] - dw0)) * 128;
     }
   }
@@ -939,7 +987,8 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   }
 
   const int b_bytes = n_tile * 128;
-  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes : (use_hs ? p.planes * p.hs_plane_bytes : 0);
+  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes
+                                : (use_hs ? p.hs_nbuf * p.planes * p.hs_plane_bytes : 0);
   const int stage_bytes = use_hs ? p.planes * b_bytes
                                  : (use_vs ? p.planes * p.vs_rows * tile_w * 128 : p.planes * (kABytes + b_bytes));
   int stages = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes;
@@ -948,11 +997,6 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   if (stages < 2) return set_error("conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
   const int smem_bytes = bres_bytes + stages * stage_bytes + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
-      return set_cuda_error("cudaFuncSetAttribute(conv_tc_kernel)");
-    attr_set = true;
-  }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;

@@ -524,12 +524,7 @@ extern "C" int dlb_conv_wgrad(const dlb_conv_desc* d, const void* x_hi, const vo
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return set_error("dlb_conv_wgrad: not enough shared memory (multi-tap)");
     q.stages = stages;
-    static bool attr_set_mt = false;
-    if (!attr_set_mt) {
-      if (cudaFuncSetAttribute(conv_wgrad_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 2048) != cudaSuccess)
-        return set_cuda_error("cudaFuncSetAttribute(conv_wgrad_mt_kernel)");
-      attr_set_mt = true;
-    }
+    if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_mt_kernel), kSmemLimit - 2048, kSlotWgradMt) != 0) return DLB_ERR_CUDA;
     const int grid = g.ngroups * g.m_tiles * g.n_tiles * g.splits;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     conv_wgrad_mt_kernel<<<grid, kThreads, stages * stage_bytes + 1024, st>>>(q);
@@ -594,12 +589,7 @@ extern "C" int dlb_conv_wgrad(const dlb_conv_desc* d, const void* x_hi, const vo
   if (stages < 2) return set_error("dlb_conv_wgrad: not enough shared memory");
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 2048) != cudaSuccess)
-      return set_cuda_error("cudaFuncSetAttribute(conv_wgrad_kernel)");
-    attr_set = true;
-  }
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_kernel), kSmemLimit - 2048, kSlotWgrad) != 0) return DLB_ERR_CUDA;
   const int grid = g.taps * g.m_tiles * g.n_tiles * g.splits;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   conv_wgrad_kernel<<<grid, kThreads, smem_bytes, st>>>(p);

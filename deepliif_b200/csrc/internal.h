@@ -13,6 +13,13 @@ namespace dlb {
 int set_error(const char* msg);            // records msg for dlb_last_error(); returns DLB_ERR_INVALID
 int set_cuda_error(const char* where);     // records where + cudaGetErrorString; returns DLB_ERR_CUDA
 
+// Per-device, mutex-guarded launch facts (the only process-wide mutable state of the library).
+//   ensure_dyn_smem: raise `func`'s dynamic shared-memory limit once per device (slot = small id of the kernel);
+//   device_num_sms:  multiprocessor count of the current device.
+enum { kSlotConvTc = 0, kSlotWgradMt = 1, kSlotWgrad = 2, kNumSmemSlots = 8 };
+int ensure_dyn_smem(const void* func, int bytes, int slot);
+int device_num_sms(int* num_sms);
+
 // One phase of a convolution in tap-list form:
 //   y[n,i,j,co] = sum_t sum_ci x[n, i*stride + dh_t, j*stride + dw_t, ci] * w[widx_t][co][ci]
 struct PhaseGeom {
@@ -57,6 +64,7 @@ struct TcPhase : PhaseGeom {
   float* fa_out[2];
   int fa_act[2];
   int fa_border, fa_border_mode;
+  int stem_C, stem_S, stem_pad;   // fa == 2: fa_x[0] is the fp32 NCHW network input, see TcParams
 };
 
 // cuTensorMapEncodeTiled (16-bit elements, 128-byte swizzle, zero OOB fill) through the runtime's driver entry point.

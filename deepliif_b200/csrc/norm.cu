@@ -110,14 +110,23 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int 
   const bool cok = c < C;
   const int n_lo = pooled ? 0 : blockIdx.y, n_hi = pooled ? N : blockIdx.y + 1;
   // pass 1
+  // The slice loops are latency-bound (one L2 round trip per slice): four slices are fetched before any is consumed, and
+  // added in slice order afterwards, so the result does not depend on the unrolling.
   float cnt = 0.f, sum = 0.f;
   if (cok)
-    for (int n = n_lo; n < n_hi; ++n)
-      for (int s = w; s < S; s += 32) {
-        const float nb = ws.cnt[n * ws.S_cap + s];
-        const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
-        cnt += nb; sum += pr.x;
+    for (int n = n_lo; n < n_hi; ++n) {
+      const float* cntp = ws.cnt + static_cast<long long>(n) * ws.S_cap;
+      const float2* prp = ws.partial + static_cast<long long>(n) * ws.S_cap * C + c;
+      int s = w;
+      for (; s + 96 < S; s += 128) {
+        float nb[4]; float2 pr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { nb[u] = cntp[s + 32 * u]; pr[u] = prp[static_cast<long long>(s + 32 * u) * C]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { cnt += nb[u]; sum += pr[u].x; }
       }
+      for (; s < S; s += 32) { cnt += cntp[s]; sum += prp[static_cast<long long>(s) * C].x; }
+    }
   sm[w][lane] = cnt; sm2[w][lane] = sum;
   __syncthreads();
   double tn = 0.0, ts = 0.0;
@@ -128,12 +137,24 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(StatsPtrs ws, int 
   // pass 2
   float m2 = 0.f;
   if (cok)
-    for (int n = n_lo; n < n_hi; ++n)
-      for (int s = w; s < S; s += 32) {
-        const float nb = ws.cnt[n * ws.S_cap + s];
-        const float2 pr = ws.partial[(static_cast<long long>(n) * ws.S_cap + s) * C + c];
+    for (int n = n_lo; n < n_hi; ++n) {
+      const float* cntp = ws.cnt + static_cast<long long>(n) * ws.S_cap;
+      const float2* prp = ws.partial + static_cast<long long>(n) * ws.S_cap * C + c;
+      int s = w;
+      for (; s + 96 < S; s += 128) {
+        float nb[4]; float2 pr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { nb[u] = cntp[s + 32 * u]; pr[u] = prp[static_cast<long long>(s + 32 * u) * C]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (nb[u] > 0.f) { const float d = pr[u].x / nb[u] - mean; m2 += pr[u].y + nb[u] * d * d; }
+      }
+      for (; s < S; s += 32) {
+        const float nb = cntp[s];
+        const float2 pr = prp[static_cast<long long>(s) * C];
         if (nb > 0.f) { const float d = pr.x / nb - mean; m2 += pr.y + nb * d * d; }
       }
+    }
   sm[w][lane] = m2;
   __syncthreads();
   if (w != 0 || !cok) return;

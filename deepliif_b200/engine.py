@@ -395,8 +395,13 @@ class ResnetEngine(_EngineBase):
             if taps is not None:
                 taps[name] = a
 
-        xh, xl = ops.stem_window_pack(x, 3, self.stem_S, self.pad_mode, self.prec.fmt, self.prec.split)
-        y, ws = self.stem.run_tc([Act(None, xh, xl)], N, H + 6, W)
+        if self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
+            ws = ops.stats_workspace(N, H * W, self.stem.cout, x.device)
+            y = ops.conv_tc_stem(x, 3, self.stem_S, self.pad_mode, self.stem.cout, self.stem.w_hi, self.stem.w_lo, self.stem.bias,
+                                 self.prec.fmt, self.prec.split, self.stem.n_tile, stats_ws=ws)
+        else:
+            xh, xl = ops.stem_window_pack(x, 3, self.stem_S, self.pad_mode, self.prec.fmt, self.prec.split)
+            y, ws = self.stem.run_tc([Act(None, xh, xl)], N, H + 6, W)
         tap("stem_conv", y)
         sc, sh = self._stats(y, self.stem_norm, ws)
         cur = Lazy(y, sc, sh, ACT_RELU)
@@ -506,18 +511,28 @@ class UnetEngine(_EngineBase):
             ss.append(self._stats(y, self.down_norm[lvl], ws) if self.down_norm[lvl] is not None else (None, None))
             dims.append((h, w))
         # ---- up path --------------------------------------------------------------------------------------------------
-        below = None
+        # relu(norm(.)) of the skip and of the level below are evaluated by the up-convolution itself while it loads its
+        # two K-sources (fused operand, halo-strip mode) wherever the map is at least 16 x 8; below that one
+        # dlb_norm_apply pass per source writes the operand planes.
+        fused = _env_flag("DLB_FUSED", True)
+        below = None                                                       # Lazy: raw up-conv output + its (scale, shift)
         for lvl in range(nd - 1, -1, -1):
             h, w = dims[lvl]
             sc, sh = ss[lvl]
-            skip = self._apply(raw[lvl], sc, sh, ACT_RELU)                 # relu(norm(d_lvl)) (= relu of the skip half)
-            srcs = [skip] if lvl == nd - 1 else [skip, below]
+            lz = [Lazy(raw[lvl], sc, sh, ACT_RELU)] + ([] if lvl == nd - 1 else [below])   # relu of both skip halves
+            layer = self.up[lvl]
+            use_fused = fused and ops.conv_tc_fused_mode(layer.desc(N, h, w), self.prec.split, layer.n_tile) > 0
+            if use_fused:
+                run = lambda fs: layer.run_fused([l.src() for l in lz], N, h, w, fuse_stats=fs)
+            else:
+                acts = [self._apply(l.x, l.scale, l.shift, l.act) for l in lz]
+                run = lambda fs: layer.run_tc(acts, N, h, w, fuse_stats=fs)
             if lvl == 0:
-                z, _ = self.up[0].run_tc(srcs, N, h, w, fuse_stats=False)
+                z, _ = run(False)
                 return ops.head_finish(z, self.out_bias, 2 * w, 1, self.out_nc, ACT_TANH)
-            y, ws = self.up[lvl].run_tc(srcs, N, h, w)
+            y, ws = run(True)
             usc, ush = self._stats(y, self.up_norm[lvl], ws)
-            below = self._apply(y, usc, ush, ACT_RELU)                      # relu(norm(u_lvl)) for the level above
+            below = Lazy(y, usc, ush, ACT_RELU)                             # relu(norm(u_lvl)) for the level above
             if taps is not None:
                 taps[f"up{lvl}"] = below
 

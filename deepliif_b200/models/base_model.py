@@ -100,13 +100,14 @@ class BaseModel(ABC):
                 # Only the weights are taken (the traced graph is a cuDNN program); keys equal the eager state_dict's.
                 print("loading the weights of the serialized model %s" % pt)
                 have = net.state_dict()
-                sd = {k: v for k, v in torch.jit.load(pt, map_location="cpu").state_dict().items()}
+                from .serialized import read_pt
+                sd = read_pt(pt)
                 for k, v in have.items():      # traced eval nets carry no BatchNorm running statistics: keep the fresh ones
                     if k not in sd and k.endswith(("running_mean", "running_var", "num_batches_tracked")):
                         sd[k] = v
             else:
                 print("loading the model from %s" % path)
-                sd = torch.load(path, map_location="cpu")
+                sd = torch.load(path, map_location="cpu", weights_only=True)     # a checkpoint is data, not code
             if hasattr(sd, "_metadata"):
                 del sd._metadata
             # InstanceNorm checkpoints written by torch < 0.4 may carry running stats: drop them

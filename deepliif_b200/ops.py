@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16, PAD_REFLECT, PAD_ZERO,
                    ConvDesc, FusedSrc, check)
 
-__all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc", "conv_tc_fused", "conv_tc_fused_mode",
+__all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc", "conv_tc_fused", "conv_tc_fused_mode", "conv_tc_stem",
            "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "adam_hyper", "adam_step_dev", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
@@ -143,6 +143,20 @@ def conv_tc_fused(d, srcs, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_ti
                                             stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
           "dlb_conv_tc_fwd_fused")
     LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    return out
+
+
+def conv_tc_stem(x_nchw, pad, S, pad_mode, cout, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_tile=0, stats_ws=None):
+    """Pad(pad) + Conv2d(C <= 4 -> cout, S x S) from the fp32 NCHW input in one tensor-core kernel (the window operand is
+    built in shared memory).  w_hi / w_lo: planes of the 64-lane vertical weight (see dlb_stem_window_pack).  fp32 NHWC out."""
+    _need_cuda(x_nchw, w_hi, w_lo, bias)
+    N, Cc, H, W = x_nchw.shape
+    out = torch.empty((N, H, W, cout), dtype=torch.float32, device=x_nchw.device)
+    check(_lib.load().dlb_conv_tc_fwd_stem(_p(x_nchw), N, Cc, H, W, pad, S, pad_mode, cout, _p(w_hi), _p(w_lo) if split else None,
+                                           _p(bias), _p(out), fmt, int(split), n_tile, _p(stats_ws),
+                                           stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
+          "dlb_conv_tc_fwd_stem")
+    LAUNCHES["count"] += 1
     return out
 
 

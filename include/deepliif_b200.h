@@ -8,7 +8,11 @@
  *
  * Conventions
  *   - all pointers are DEVICE pointers owned by the caller (PyTorch caching allocator in practice);
- *     no entry point allocates, frees or synchronises; every call only enqueues work on `stream`;
+ *     no entry point allocates device memory, frees or synchronises; every call only enqueues work on `stream`;
+ *   - library state: (i) a per-device, mutex-guarded table of launch facts (SM count, "shared-memory limit raised" flags);
+ *     (ii) per (host thread, device) three helper streams + events, created on first use by dlb_conv_tc_fwd[_fused] to
+ *     run the independent output-parity phases of a small ConvTranspose2d side by side (forked from / joined back into
+ *     `stream` with events, valid under stream capture) and destroyed by dlb_release_thread_resources(); nothing else;
  *   - activations are NHWC.  fp32 tensors are plain float; "split" tensors are two 16-bit planes
  *     (hi, lo) with hi = round16(x), lo = round16(x - hi), format DLB_FMT_BF16 or DLB_FMT_FP16;
  *   - return value 0 = ok, negative = error (message via dlb_last_error(), thread-local);
@@ -52,6 +56,8 @@ typedef struct dlb_conv_desc {
 
 const char* dlb_last_error(void);
 int dlb_version(void);
+/* Destroys the helper streams / events the calling host thread created (see "library state" above). */
+int dlb_release_thread_resources(void);
 
 /* Output extent of the layer (PyTorch formulas). */
 int dlb_conv_out_shape(const dlb_conv_desc* d, int* OH, int* OW);
@@ -207,6 +213,15 @@ int dlb_conv_wgrad(const dlb_conv_desc* d, const void* x_hi, const void* x_lo, c
  * wk[co][s*8 + c][r] = w[co][c][r][s].  x: fp32 NCHW. */
 int dlb_stem_window_pack(const float* x_nchw, int N, int C, int H, int W, int pad, int S, int pad_mode, int fmt,
                          void* out_hi, void* out_lo, dlb_stream_t stream);
+
+/* The stem in one kernel: ReflectionPad2d/ZeroPad2d(pad) + Conv2d(C <= 4, Cout, S x S) (networks.py:386-397) straight from the
+ * fp32 NCHW network input.  Converter warps build the window operand of dlb_stem_window_pack inside shared memory (that
+ * tensor, 21x the input, is never written to HBM) and the S x 1 vertical convolution over it runs on the tensor cores in
+ * vertical-strip mode; w_hi / w_lo are the planes of wk[co][s*8 + c][r] packed by dlb_pack_weights_tc (R = S, S = 1,
+ * Cin = 64).  y: fp32 NHWC [N, H, W, Cout]; stats_ws as in dlb_conv_tc_fwd.  Needs H >= 16, W >= 8, S = 2 * pad + 1 <= 8. */
+int dlb_conv_tc_fwd_stem(const float* x_nchw, int N, int C, int H, int W, int pad, int S, int pad_mode, int Cout,
+                         const void* w_hi, const void* w_lo, const float* bias, float* y, int fmt, int split, int n_tile,
+                         void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream);
 
 /* Head finish.  The 7x7 Cout=3 head (Pad(3) + Conv2d(ngf, 3, 7) + Tanh, networks.py:438-444) has N = 3, far too
  * narrow for a tensor-core tile; it is run as a vertical R=7, S=1 convolution with the S horizontal taps moved

@@ -246,3 +246,130 @@ def test_infer_modalities_matches_reference_end_to_end_golden(tmp_path):
         frac = float((d > 0).mean())
         print(f"{k}: max |d| {d.max()} LSB, {100 * frac:.3f}% of the sampled bytes differ")
         assert d.max() <= 1 and frac < 0.02, k
+
+
+def _golden_model_dir(tmp_path):
+    from deepliif_b200 import training
+    from deepliif_b200.cli import TRAIN_DEFAULTS
+    from deepliif_b200.options import print_options
+    from oracle.gen_golden import e2e_state_dicts
+    p = dict(TRAIN_DEFAULTS, dataroot=str(tmp_path), checkpoints_dir=str(tmp_path), name="m", gpu_ids=(0,),
+             modalities_names=["IHC", "Hema", "DAPI", "Lap2", "Marker"], seg_weights=[0.25, 0.15, 0.25, 0.1, 0.25])
+    print_options(training.build_options(p), save=True)
+    mdir = os.path.join(str(tmp_path), "m")
+    for k, sd in e2e_state_dicts().items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    return mdir
+
+
+def _compare_u8(name, got, ref, max_frac):
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    frac = float((d > 0).mean())
+    print(f"{name}: max |d| {d.max()} LSB, {100 * frac:.4f}% of {d.size} bytes differ")
+    assert d.max() <= 1 and frac <= max_frac, name
+    return int((d > 0).sum())
+
+
+def test_real_sample_tile_matches_the_reference_golden(tmp_path):
+    """BASELINE config 1: the reference's infer_modalities on the REAL tile Datasets/Sample_Dataset/test_cli/22_2.png
+    (tests/golden/real_tile_22_2.npz carries the PNG bytes and the reference outputs).  Same PNG -> PIL decode -> this
+    package: names, shapes, is_empty statistic and scoring equal; Seg / Marker / overlays compared at FULL resolution."""
+    import io
+    from deepliif_b200.models import infer_modalities
+    from deepliif_b200.util import image_variance_gray, is_empty
+    from oracle import pixel
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_tile_22_2.npz"))
+    img = Image.open(io.BytesIO(gold["png"].tobytes())).convert("RGB")
+    assert img.size == (512, 512)
+    assert abs(image_variance_gray(np.asarray(img)) - float(gold["variance"])) <= 1e-9 * float(gold["variance"])
+    assert is_empty(np.asarray(img)) == bool(gold["is_empty"]) == False          # noqa: E712  (real tissue: not an empty tile)
+    mdir = _golden_model_dir(tmp_path)
+    images, scoring = infer_modalities(img, 512, mdir, return_seg_intermediate=True)
+    assert sorted(images) == json.loads(bytes(gold["names"]).decode())
+    assert json.dumps(scoring, sort_keys=True) == bytes(gold["scoring"]).decode()
+    for k, im in images.items():
+        a = np.asarray(im)
+        assert list(a.shape) == gold[f"{k}__shape"].tolist(), k
+        if f"{k}__full" in gold:
+            ref = gold[f"{k}__full"]
+            if k in ("SegOverlaid", "SegRefined"):
+                # integer post-processing of Seg / Marker images that themselves differ by isolated LSBs
+                bad = int((a != ref).any(axis=-1).sum())
+                print(f"{k}: {bad} of {a.shape[0] * a.shape[1]} pixels differ from the reference")
+                assert bad <= 0.001 * a.shape[0] * a.shape[1]
+            else:
+                _compare_u8(k, a, ref, 0.004)
+        else:
+            _compare_u8(k, a[::2, ::2], gold[f"{k}__sub2"], 0.004)
+    # the thresholded uint8 segmentation mask (north_star: bit-exact) on the real tile, against the reference's Seg image
+    m_ref = pixel.create_posneg_mask(gold["Seg__full"])
+    m_got = pixel.create_posneg_mask(np.asarray(images["Seg"]))
+    mism = int((m_ref != m_got).sum())
+    print(f"posneg mask on the real tile: {mism} of {m_ref.size} pixels differ from the reference's")
+    assert mism <= 2
+
+
+def test_wsi_region_overlap56_matches_the_reference_golden(tmp_path):
+    """BASELINE config 3: the reference's inference() at tile_size=512, overlap_size=56 on a real 1000 x 600 region of
+    Sample_Large_Tissues/ROI_7.png (6 tiles; the PNG bytes travel in tests/golden/wsi_region_overlap56.npz), plus the
+    InferenceTiler tile counts of all five ROIs at overlap 56 and 32 against TileGrid."""
+    import io
+    from deepliif_b200.models import get_opt, inference
+    from deepliif_b200.util import TileGrid
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "wsi_region_overlap56.npz"))
+    counts = json.loads(bytes(gold["roi_tile_counts"]).decode())
+    assert len(counts) == 5
+    for name, c in counts.items():
+        W_, H_ = c["size"]
+        blank = np.zeros((H_, W_, 3), np.uint8)
+        assert len(TileGrid(blank, 512, 56).tiles()) == c["tiles_overlap56"], name
+        assert len(TileGrid(blank, 512, 32).tiles()) == c["tiles_overlap32"], name
+    assert sum(c["tiles_overlap56"] for c in counts.values()) == 102 and sum(c["tiles_overlap32"] for c in counts.values()) == 83
+    img = Image.open(io.BytesIO(gold["png"].tobytes())).convert("RGB")
+    assert len(TileGrid(np.asarray(img), 512, 56).tiles()) == int(gold["n_tiles"]) == 6
+    mdir = _golden_model_dir(tmp_path)
+    opt = get_opt(mdir)
+    images = inference(img, tile_size=512, overlap_size=56, model_path=mdir, opt=opt, seg_weights=opt.seg_weights)
+    assert sorted(images) == json.loads(bytes(gold["names"]).decode())
+    for k, im in images.items():
+        a = np.asarray(im)
+        assert list(a.shape) == gold[f"{k}__shape"].tolist(), k
+        st = 2 if f"{k}__sub2" in gold else 4
+        _compare_u8(k, a[::st, ::st], gold[f"{k}__sub{st}"], 0.004)
+
+
+def test_serialize_command_writes_a_packed_directory_that_test_reads(tmp_path):
+    """`deepliif serialize`: the output directory holds <name>.pt files with the fp32 weights plus the
+    repacked tensor-core operand planes, and gives the same images as the .pth directory it was made from."""
+    from click.testing import CliRunner
+    from deepliif_b200.cli import cli
+    from deepliif_b200.models import infer_modalities, init_nets
+    from deepliif_b200.models.serialized import FORMAT
+    mdir, _ = _write_model_dir(tmp_path, net_g="resnet_2blocks", net_gs="unet_128", n_blocks=2)
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, 2, "batch", True, "zero")
+    s_shapes = nets.unet_param_shapes(7, 64, 3, 3, "batch")
+    sds = {**{f"G{i}": nets.make_state_dict(g_shapes, 50 + i, "stress") for i in range(1, 5)},
+           **{f"GS{i}": nets.make_state_dict(s_shapes, 60 + i, "stress") for i in range(5)}}
+    for k, sd in sds.items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    out = str(tmp_path / "packed")
+    init_nets.cache_clear()
+    r = CliRunner().invoke(cli, ["serialize", "--model-dir", mdir, "--output-dir", out])
+    assert r.exit_code == 0, r.output
+    blob = torch.load(os.path.join(out, "G1.pt"), weights_only=True)
+    assert blob["format"] == FORMAT and blob["arch"]["kind"] == "resnet"
+    w = sds["G1"]["model.4.weight"]                                   # 64 -> 128 3x3 stride-2 conv
+    pk = blob["packed"]["model.4"]
+    assert tuple(pk["hi"].shape) == (9, 128, 64) and pk["hi"].dtype == torch.bfloat16
+    ref = w.permute(2, 3, 0, 1).reshape(9, 128, 64)
+    assert torch.equal(pk["hi"], ref.to(torch.bfloat16))
+    assert torch.equal(pk["lo"], (ref - ref.to(torch.bfloat16).float()).to(torch.bfloat16))
+    rng = np.random.default_rng(23)
+    img = Image.fromarray((rng.random((256, 256, 3)) * 255).astype(np.uint8))
+    init_nets.cache_clear()
+    base, _ = infer_modalities(img, 256, mdir)
+    init_nets.cache_clear()
+    got, _ = infer_modalities(img, 256, out, eager_mode=False)
+    assert set(got) == set(base)
+    for k in base:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(base[k])), k

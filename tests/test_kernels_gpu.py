@@ -254,8 +254,10 @@ FUSED_CASES = [
 @pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
 def test_conv_tc_fused_operand_is_bit_identical_to_apply_then_conv(ops, case, prec):
-    """dlb_conv_tc_fwd_fused(raw, scale, shift, act, residual, border) == dlb_norm_apply(...) -> dlb_conv_tc_fwd, bit for
-    bit (same operand arithmetic, same MMA order), and the written-back operand == dlb_norm_apply's fp32 output."""
+    """dlb_conv_tc_fwd_fused(raw, scale, shift, act, residual, border) against dlb_norm_apply(...) -> dlb_conv_tc_fwd.  The
+    operand arithmetic is the same; in tap / vertical-strip mode the MMA order is the same too and the outputs agree bit
+    for bit; the halo-strip mode walks K chunk-major instead of tap-major (fp32 accumulation order differs), so there the
+    outputs agree to accumulation rounding.  The written-back operand always equals dlb_norm_apply's fp32 output exactly."""
     name, N, Hs, Ws, cins, Cout, R, st, pad, tr, op, n_tile, b, bmode, use_res, wb, act = case
     R, S = (R if isinstance(R, tuple) else (R, R))
     fmt = ops.FMT_FP16 if prec.startswith("fp16") else ops.FMT_BF16
@@ -284,7 +286,12 @@ def test_conv_tc_fused_operand_is_bit_identical_to_apply_then_conv(ops, case, pr
     mode = ops.conv_tc_fused_mode(d, split, n_tile)
     assert mode == (2 if name.startswith(("trunk", "up_ct", "n_tile128", "hs_")) else 1 if name.startswith("head_vs") else 0), mode
     torch.cuda.synchronize()
-    assert torch.equal(y, y_ref), (name, (y - y_ref).abs().max().item())
+    if mode == 2:
+        scale = y_ref.abs().max().item()
+        err = (y - y_ref).abs().max().item()
+        assert err <= 3e-5 * scale, (name, err, scale)         # measured on B200: ~1e-5 of the output scale
+    else:
+        assert torch.equal(y, y_ref), (name, (y - y_ref).abs().max().item())
     if wb:
         assert torch.equal(outs[0], f32s[0])
 
@@ -304,3 +311,27 @@ def test_conv_tc_fused_operand_with_fused_stats(ops):
     s2, h2 = ops.norm_stats(y, None, None, False)
     assert (s1 - s2).abs().max().item() <= 2e-6 * s2.abs().max().item()
     assert (h1 - h2).abs().max().item() <= 5e-6 * max(1.0, h2.abs().max().item())
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
+@pytest.mark.parametrize("N,C,H,W,pad_mode", [(2, 3, 32, 40, 0), (1, 3, 48, 24, 1), (3, 4, 21, 19, 1), (1, 1, 16, 8, 0)])
+def test_conv_tc_stem_is_bit_identical_to_window_pack_then_conv(ops, prec, N, C, H, W, pad_mode):
+    """dlb_conv_tc_fwd_stem (window operand built in shared memory) == dlb_stem_window_pack -> dlb_conv_tc_fwd, bit for bit,
+    and both equal Pad(3) + Conv2d(C, 64, 7) of the fp32 oracle to the split-precision tolerance."""
+    fmt = ops.FMT_FP16 if prec.startswith("fp16") else ops.FMT_BF16
+    split = prec.endswith("x3")
+    x = _rand((N, C, H, W), 101)
+    w = _rand((64, C, 7, 7), 102, 0.1)
+    b = _rand((64,), 103, 0.1)
+    wk = torch.zeros((64, 64, 7, 1))
+    wk.view(64, 8, 8, 7)[:, :7, :C, :] = w.permute(0, 3, 1, 2)          # wk[co, s*8 + c, r, 0] = w[co, c, r, s]
+    d = ops.conv_desc(N, H + 6, W, [64], 64, 7, 1, 1, 0, False, 0)
+    w_hi, w_lo = ops.pack_weights_tc(d, wk.cuda(), fmt, split)
+    xh, xl = ops.stem_window_pack(x.cuda(), 3, 7, pad_mode, fmt, split)
+    y_ref = ops.conv_tc(d, [xh], [xl], w_hi, w_lo, b.cuda(), fmt, split, 0)
+    y = ops.conv_tc_stem(x.cuda(), 3, 7, pad_mode, 64, w_hi, w_lo, b.cuda(), fmt, split, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref), (y - y_ref).abs().max().item()
+    if split:
+        ref = F.conv2d(F.pad(x.double(), (3, 3, 3, 3), mode="reflect" if pad_mode else "constant"), w.double(), b.double()).float()
+        assert (nchw(y.cpu()) - ref).abs().max().item() < 3e-5 * ref.abs().max().item()

@@ -458,18 +458,21 @@ def test_optimize_parameters_matches_the_reference_model_golden(tmp_path):
         #     |g| is far above the gradient's rounding noise both implementations move by the same +-lr, so the weights agree
         #     to fp32 rounding; entries whose reference gradient is within the noise band may take the other sign.
         rms = g_ref.pow(2).mean().sqrt()
-        solid = g_ref.abs() >= 0.05 * rms
         d_w = (w_our - w_ref).abs()
+        for thr in (0.05, 0.1, 0.25, 0.5):            # how fast the disagreements die out with the gradient magnitude
+            m_ = g_ref.abs() >= thr * rms
+            print(f"  {name}.{key}: |g| >= {thr} rms: {int((d_w[m_] > 2e-7).sum())} of {int(m_.sum())} post-step weights differ")
+        solid = g_ref.abs() >= 0.25 * rms
         n_bad = int((d_w[solid] > 2e-7).sum())
         flips = float((d_w > 0.5 * lr[name[0]]).float().mean())
         uo, ur = w_our - w0, w_ref - w0
         cos = float((uo * ur).sum() / (uo.norm() * ur.norm()))
         print(f"{name}.{key}: adam(ref grad) vs ref weights max|d| {d_opt:.2e}; post-step weights: {int(solid.sum())} of "
-              f"{solid.numel()} entries with |g| >= 0.05 rms -> {n_bad} differ by > 2e-7 (max {d_w[solid].max().item():.2e}); "
+              f"{solid.numel()} entries with |g| >= 0.25 rms -> {n_bad} differ by > 2e-7 (max {d_w[solid].max().item():.2e}); "
               f"sign flips overall {100 * flips:.2f}%; step cosine {cos:.4f}")
         assert d_opt <= 1e-8
         assert n_bad <= 0.002 * int(solid.sum())
-        assert flips < 0.06 and cos > 0.9
+        assert flips < 0.03 and cos > 0.95
     # BatchNorm2d running statistics after the step (what save_networks writes into the .pth files, base_model.py:190-212)
     for name, key in (("G1", "model.2"), ("G1", "model.5"), ("GS0", "model.model.1.model.2"), ("D1", "model.3"), ("DS2", "model.6")):
         sd_ = model._net(name).module.state_dict()
