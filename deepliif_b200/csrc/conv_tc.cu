@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
       const bool valid = (n < p.N) && (h < p.OH) && (w < p.OW);
       float* yp = p.y + p.y_base + n * p.ys_n + h * p.ys_h + w * p.ys_w + tc.cout0;
-      mbar_wait(&tfull_bar[acc], acc_ph);
+      mbar_wait_sleep(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
@@ -508,24 +508,39 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     int s = 0; uint32_t ph = 0;
     const int lw = 31 - __clz(p.tile_w), lh = 31 - __clz(p.tile_h);
     if (p.hs) {
-      // Strip units: unit u = (pixel u >> 4 of the strip, float4 q = u & 15); thread owns units ct + 256 * j.  The strip is
-      // double-buffered: the converters build chunk c + 1 while the MMAs read chunk c.
+      // Strip units: unit u = (strip pixel u >> 4, float4 q = u & 15); thread owns units ct + 256 * j.  The strip is double-
+      // buffered: the converters build chunk c + 1 while the MMAs read chunk c.  Per-unit facts that do not depend on the
+      // tile (shared-memory offset, pixel offset inside the strip, "belongs to the tile's own 16 x 8 pixels") are computed
+      // once; a tile whose strip lies wholly inside the source needs no per-pixel border logic at all.
       constexpr int kUnits = kHsMaxPx * 16 / 256;              // units per thread for the largest admissible strip
       const int npx = p.hs_rows * p.hs_cols;
       const int nunits = (npx * 16 - ct + 255) / 256;          // units this thread owns
-      uint32_t rc[kUnits];                                     // (row << 16) | col of unit j's pixel
+      uint32_t soff[kUnits];                                   // swizzled byte offset inside a strip plane
+      int poff[kUnits];                                        // row * Ws + col: source pixel offset relative to the strip origin
+      uint32_t own_mask = 0;                                   // bit j: unit j's pixel is one of the tile's own output pixels
 #pragma unroll
       for (int j = 0; j < kUnits; ++j) {
         const int px_i = (ct + 256 * j) >> 4;
-        const int row = px_i / p.hs_cols;
-        rc[j] = (static_cast<uint32_t>(row) << 16) | static_cast<uint32_t>(px_i - row * p.hs_cols);
+        const int row = px_i / p.hs_cols, col = px_i - row * p.hs_cols;
+        poff[j] = row * p.Ws + col;
+        // absolute-address swizzle: the strip buffers are 1024 B aligned, so address bits [7,10) = px_i & 7
+        soff[j] = static_cast<uint32_t>(px_i) * 128u + (static_cast<uint32_t>(chunk ^ (px_i & 7)) << 4) + sub;
+        const int oh_l = row + p.hs_dh_min - p.fa_border, ow_l = col + p.hs_dw_min - p.fa_border;
+        if (oh_l >= 0 && oh_l < p.tile_h && ow_l >= 0 && ow_l < p.tile_w) own_mask |= 1u << j;
       }
       uint32_t g = 0;                                          // running chunk number (same sequence as the MMA issuer)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         const int vh0 = tc.h0 + p.hs_dh_min, vw0 = tc.w0 + p.hs_dw_min;
+        const int sh0 = vh0 - p.fa_border, sw0 = vw0 - p.fa_border;      // strip origin in source coordinates
+        const bool inside = (tc.n0 < p.N) && sh0 >= 0 && sw0 >= 0 && sh0 + p.hs_rows <= p.Hs && sw0 + p.hs_cols <= p.Ws;
+        const long long origin = (static_cast<long long>(tc.n0) * p.Hs + sh0) * p.Ws + sw0;
         for (int src = 0; src < p.nsrc; ++src) {
           const bool wb = (p.fa_out[src] != nullptr) && (tc.cout0 == 0);
+          const int C = p.fa_cin[src];
+          const float* __restrict__ xs = p.fa_x[src];
+          const float* __restrict__ rs = p.fa_res[src];
+          const int act = p.fa_act[src];
           for (int kc = 0; kc < p.kchunks[src]; ++kc, ++g) {
             const uint32_t buf = g % static_cast<uint32_t>(p.hs_nbuf);
             uint8_t* const strip_hi = smem + static_cast<size_t>(buf) * strip_bytes;
@@ -533,58 +548,62 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             const int cbase = kc * kKC + q * 4;
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.fa_scale[src] != nullptr && tc.n0 < p.N) {
-              sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
-              sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[src] + static_cast<long long>(tc.n0) * p.fa_cin[src] + cbase));
+              sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[src] + static_cast<long long>(tc.n0) * C + cbase));
+              sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[src] + static_cast<long long>(tc.n0) * C + cbase));
             }
+            const float* const xo = xs + origin * C + cbase;          // only dereferenced when `inside`
+            const float* const ro = rs != nullptr ? rs + origin * C + cbase : nullptr;
             bool waited = false;
 #pragma unroll
-            for (int j0 = 0; j0 < kUnits; j0 += 4) {
-              float4 xv[4], rv[4]; FaPix px[4];
+            for (int j0 = 0; j0 < kUnits; j0 += 6) {
+              float4 xv[6], rv[6]; int goff[6]; uint32_t okm = 0, inm = 0;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 6; ++u) {
                 const int j = j0 + u;
-                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; px[u].ok = false; px[u].interior = false;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; goff[u] = 0;
                 if (j < nunits) {
-                  const int row = static_cast<int>(rc[j] >> 16), col = static_cast<int>(rc[j] & 0xffffu);
-                  px[u] = fa_locate(p, src, tc.n0, vh0 + row, vw0 + col);
-                  if (px[u].ok) {
-                    xv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_x[src] + px[u].off + cbase));
-                    if (p.fa_res[src] != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_res[src] + px[u].off + cbase));
+                  if (inside) {
+                    goff[u] = poff[j] * C;
+                    okm |= 1u << u; inm |= 1u << u;
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(xo + goff[u]));
+                    if (ro != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(ro + goff[u]));
+                  } else {
+                    const int px_i = (ct + 256 * j) >> 4;               // border tile: per-pixel zero / reflect logic
+                    const int row = px_i / p.hs_cols, col = px_i - row * p.hs_cols;
+                    const FaPix px = fa_locate(p, src, tc.n0, vh0 + row, vw0 + col);
+                    if (px.ok) {
+                      okm |= 1u << u; if (px.interior) inm |= 1u << u;
+                      goff[u] = static_cast<int>(px.off - origin * C);  // same addressing as the fast path
+                      xv[u] = __ldg(reinterpret_cast<const float4*>(xs + px.off + cbase));
+                      if (rs != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(rs + px.off + cbase));
+                    }
                   }
                 }
               }
               if (!waited) {
-                // the first loads of the chunk are in flight before the (rarely blocking) wait for the buffer: the MMAs that
-                // read it belong to the chunk before the previous one (two buffers) / the previous one (one buffer)
-                mbar_wait(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
+                // the first loads of the chunk are in flight before the (rarely blocking) wait for the strip buffer
+                mbar_wait_sleep(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
                 waited = true;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 6; ++u) {
                 const int j = j0 + u;
                 if (j >= nunits) continue;
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
-                if (px[u].ok) {
-                  o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[src]) + rv[u].x;
-                  o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), p.fa_act[src]) + rv[u].y;
-                  o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), p.fa_act[src]) + rv[u].z;
-                  o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[src]) + rv[u].w;
+                if ((okm >> u) & 1u) {
+                  o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), act) + rv[u].x;
+                  o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), act) + rv[u].y;
+                  o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), act) + rv[u].z;
+                  o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), act) + rv[u].w;
                   // write-back of the evaluated operand: the tile's own pixels only (each source pixel belongs to exactly
-                  // one tile), i.e. strip positions whose output pixel (vh - border, vw - border) lies inside this tile
-                  if (wb && px[u].interior) {
-                    const int row = static_cast<int>(rc[j] >> 16), col = static_cast<int>(rc[j] & 0xffffu);
-                    const int oh = vh0 + row - p.fa_border, ow = vw0 + col - p.fa_border;
-                    if (oh >= tc.h0 && oh < tc.h0 + p.tile_h && ow >= tc.w0 && ow < tc.w0 + p.tile_w)
-                      *reinterpret_cast<float4*>(p.fa_out[src] + px[u].off + cbase) = make_float4(o[0], o[1], o[2], o[3]);
-                  }
+                  // one tile); `interior` excludes reflected border positions, which alias other pixels
+                  if (wb && ((own_mask >> j) & 1u) && ((inm >> u) & 1u))
+                    *reinterpret_cast<float4*>(p.fa_out[src] + origin * C + cbase + goff[u]) = make_float4(o[0], o[1], o[2], o[3]);
                 }
                 uint2 hi, lo;
                 fa_split4(o, p.fa_is_bf16, hi, lo);
-                const uint32_t px_i = static_cast<uint32_t>(ct + 256 * j) >> 4;
-                // absolute-address swizzle: the strip buffers are 1024 B aligned, so address bits [7,10) = px_i & 7
-                const uint32_t off = px_i * 128u + (static_cast<uint32_t>(chunk ^ (px_i & 7u)) << 4) + sub;
-                *reinterpret_cast<uint2*>(strip_hi + off) = hi;
-                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + off) = lo;
+                *reinterpret_cast<uint2*>(strip_hi + soff[j]) = hi;
+                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + soff[j]) = lo;
               }
             }
             fence_proxy_async();
@@ -600,7 +619,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         const int npx = p.vs_rows * p.tile_w;                 // tile_w == 8: one image row = one 1024 B swizzle atom
         const int vw0 = tc.w0 + p.tap_off[0][1], vh0 = tc.h0 + p.vs_dh_min;
         for (int kc = 0; kc < kch0; ++kc) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_sleep(&empty_bar[s], ph ^ 1);
           uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
           uint8_t* a_lo = a_hi + vs_a_bytes;
           const int cbase = kc * kKC + q * 4;
@@ -673,7 +692,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
           for (int src = 0; src < p.nsrc; ++src) {
             const bool wb = (p.fa_out[src] != nullptr) && (tap == p.fa_wb_tap) && (tc.cout0 == 0);
             for (int kc = 0; kc < p.kchunks[src]; ++kc) {
-              mbar_wait(&empty_bar[s], ph ^ 1);
+              mbar_wait_sleep(&empty_bar[s], ph ^ 1);
               uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
               uint8_t* a_lo = a_hi + kABytes;
               const int cbase = kc * kKC + q * 4;

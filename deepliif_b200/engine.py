@@ -235,6 +235,11 @@ class ResnetEngine(_EngineBase):
         # consuming convolution; fuse_residual also folds the ResnetBlock skip add into the next block's first conv.
         self.fused = (backend == "tc") and (_env_flag("DLB_FUSED", True) if fused is None else bool(fused))
         self.fuse_residual = _env_flag("DLB_FUSE_RESIDUAL", True) if fuse_residual is None else bool(fuse_residual)
+        # per-stage switches (measured choices): the trunk always gains; the stem / head / ConvTranspose stages
+        # have little MMA work per converted strip and are converter-bound
+        self.fuse_stem = _env_flag("DLB_FUSE_STEM", False)
+        self.fuse_up = _env_flag("DLB_FUSE_UP", False)
+        self.fuse_head = _env_flag("DLB_FUSE_HEAD", False)
         if padding_type not in ("zero", "reflect"):
             raise NotImplementedError("padding [%s] is not implemented" % padding_type)
         self.n_blocks, self.padding_type = n_blocks, padding_type
@@ -361,14 +366,14 @@ class ResnetEngine(_EngineBase):
         return self.head.run_direct(y, N, h, w, pad_mode=self.pad_mode, in_scale=sc, in_shift=sh, in_act=ACT_RELU,
                                     out_act=ACT_TANH, out_nchw=True)
 
-    def _consume(self, layer, lazy, N, H, W, *, pad=None, border=0, keep=False, fuse_stats=True, block=False):
+    def _consume(self, layer, lazy, N, H, W, *, pad=None, border=0, keep=False, fuse_stats=True, block=False, allow=True):
         """Run `layer` on the lazy activation.  Strip-eligible layers evaluate it in-kernel (no HBM pass); the others
         (stride 2, maps below 16 x 8) get their operand planes from one dlb_norm_apply pass.  keep: also materialise the
         evaluated activation in fp32 (the ResnetBlock residual stream).  Returns (y, stats_ws, kept fp32 | None)."""
         Hv, Wv = H + 2 * border, W + 2 * border
         d = layer.desc(N, Hv, Wv, pad)
         kept = None
-        if layer.use_tc and ops.conv_tc_fused_mode(d, self.prec.split, layer.n_tile) > 0:
+        if allow and layer.use_tc and ops.conv_tc_fused_mode(d, self.prec.split, layer.n_tile) > 0:
             if keep:
                 kept = torch.empty_like(lazy.x)
             srcs = [lazy.src(border, self.pad_mode, out=kept)]
@@ -395,7 +400,7 @@ class ResnetEngine(_EngineBase):
             if taps is not None:
                 taps[name] = a
 
-        if self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
+        if self.fuse_stem and self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
             ws = ops.stats_workspace(N, H * W, self.stem.cout, x.device)
             y = ops.conv_tc_stem(x, 3, self.stem_S, self.pad_mode, self.stem.cout, self.stem.w_hi, self.stem.w_lo, self.stem.bias,
                                  self.prec.fmt, self.prec.split, self.stem.n_tile, stats_ws=ws)
@@ -426,11 +431,11 @@ class ResnetEngine(_EngineBase):
             cur = Lazy(y, sc, sh, ACT_NONE, residual=r)
             tap(f"block{bi}", cur)
         for i in range(2):
-            y, ws, _ = self._consume(self.up[i], cur, N, h, w)
+            y, ws, _ = self._consume(self.up[i], cur, N, h, w, allow=self.fuse_up)
             h, w = h * 2, w * 2
             sc, sh = self._stats(y, self.up_norm[i], ws)
             cur = Lazy(y, sc, sh, ACT_RELU)
-        z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False)
+        z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False, allow=self.fuse_head)
         return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
 
     __call__ = forward
