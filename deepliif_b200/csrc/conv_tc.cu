@@ -27,6 +27,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -41,6 +43,7 @@ constexpr int kABytes = 128 * 128;     // one A plane of a stage: 128 pixels x 1
 constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int kConvWarps = 8;          // fused-operand mode: warps 6-13 build the A planes from fp32 producer outputs
 constexpr int kThreadsFa = kThreads + 32 * kConvWarps;
+constexpr int kStemPatchBytes = 4 * 24 * 16 * 4;   // fused stem: fp32 input patch [4 ch][<= 24 rows][16 cols] per strip stage
 constexpr int kHsMaxPx = 192;          // halo-strip mode: at most this many strip pixels (3x3: 18 x 10 = 180; 2x2 taps: 17 x 9)
 constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
 constexpr int kStaticSmem = 1024;      // barriers (static __shared__), rounded up
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
   const int vs_a_bytes = p.vs_rows * p.tile_w * 128;                 // one plane of an A strip (vs mode)
-  const int stage_bytes = p.hs ? p.planes * b_bytes : (p.vs ? p.planes * vs_a_bytes : p.planes * (kABytes + b_bytes));
+  const int stage_bytes = p.hs ? p.planes * b_bytes
+                               : (p.vs ? p.planes * vs_a_bytes + (p.fa == 2 ? kStemPatchBytes : 0) : p.planes * (kABytes + b_bytes));
   const int kch0 = p.kchunks[0];
   const int strip_bytes = p.planes * p.hs_plane_bytes;              // one operand strip buffer (hs mode)
   const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : (p.hs ? p.hs_nbuf * strip_bytes : 0);
@@ -507,7 +511,87 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     const int chunk = q >> 1;
     int s = 0; uint32_t ph = 0;
     const int lw = 31 - __clz(p.tile_w), lh = 31 - __clz(p.tile_h);
-    if (p.hs) {
+    if (p.fa == 2) {
+      // ---- fused stem: the window operand lane (s * 8 + c) of strip pixel (row, col) is pad(x)[n, c, row, col + s].  Per tile
+      // the (vs_rows) x (8 + S - 1) x C input patch is staged once in shared memory (coalesced row loads, zero / reflect
+      // border resolved there; the NEXT tile's patch is already in flight in registers while this one is expanded), then
+      // every converter thread expands its strip units from the patch: no global latency inside the expansion.
+      const int prow = p.vs_rows, pcol = 8 + p.stem_S - 1;          // patch extents (pcol <= 15)
+      const int pelems = p.stem_C * prow * pcol;
+      const long long plane = static_cast<long long>(p.Hs) * p.Ws;
+      constexpr int kPE = 6;                                        // patch elements per thread: 4 x 24 x 15 = 1440 <= 6 x 256
+      // element k of this thread: (channel, patch row, patch col) — tile-independent, decoded once (three integer divisions
+      // per element would otherwise be paid for every tile)
+      int pe_c[kPE], pe_r[kPE], pe_cc[kPE];
+#pragma unroll
+      for (int k = 0; k < kPE; ++k) {
+        const int e = ct + 256 * k;
+        pe_c[k] = -1; pe_r[k] = 0; pe_cc[k] = 0;
+        if (e < pelems) { pe_c[k] = e / (prow * pcol); const int rem = e - pe_c[k] * (prow * pcol); pe_r[k] = rem / pcol; pe_cc[k] = rem - pe_r[k] * pcol; }
+      }
+      auto patch_load = [&](int t, float (&v)[kPE]) {
+        const TileCoord tc = decode_tile(p, t);
+        const float* xn = p.fa_x[0] + static_cast<long long>(tc.n0) * p.stem_C * plane;
+#pragma unroll
+        for (int k = 0; k < kPE; ++k) {
+          v[k] = 0.f;
+          if (pe_c[k] >= 0 && tc.n0 < p.N) {
+            int hh = tc.h0 + p.vs_dh_min + pe_r[k] - p.stem_pad, ww = tc.w0 + pe_cc[k] - p.stem_pad;
+            if (p.fa_border_mode == DLB_PAD_REFLECT) {
+              if (hh < 0) hh = -hh; if (hh >= p.Hs) hh = 2 * p.Hs - 2 - hh;
+              if (ww < 0) ww = -ww; if (ww >= p.Ws) ww = 2 * p.Ws - 2 - ww;
+            }
+            if (hh >= 0 && hh < p.Hs && ww >= 0 && ww < p.Ws)          // zero border / tile overhang beyond the image
+              v[k] = __ldg(xn + pe_c[k] * plane + hh * p.Ws + ww);
+          }
+        }
+      };
+      float pre[kPE], pre2[kPE];                                    // patches of this tile and the next, in flight
+      int t = blockIdx.x;
+      if (t < total_tiles) patch_load(t, pre);
+      if (t + static_cast<int>(gridDim.x) < total_tiles) patch_load(t + gridDim.x, pre2);
+      const int npx = p.vs_rows * p.tile_w;
+      const int st = q >> 1;
+      const bool lane_live = ((q & 1) == 0) && (st < p.stem_S);
+      for (; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
+        uint8_t* a_lo = a_hi + vs_a_bytes;
+        float* patch = reinterpret_cast<float*>(a_hi + p.planes * vs_a_bytes);      // [c][row][16]
+#pragma unroll
+        for (int k = 0; k < kPE; ++k)
+          if (pe_c[k] >= 0) patch[(pe_c[k] * 24 + pe_r[k]) * 16 + pe_cc[k]] = pre[k];
+        asm volatile("bar.sync 1, 256;" ::: "memory");                 // converter warps only: the patch is complete
+#pragma unroll
+        for (int k = 0; k < kPE; ++k) pre[k] = pre2[k];
+        if (t + 2 * static_cast<int>(gridDim.x) < total_tiles) patch_load(t + 2 * gridDim.x, pre2);   // two tiles ahead
+        const bool row_ok = true;
+        for (int base = 0; base < npx; base += 16) {
+          const int idx = base + pr;
+          if (idx >= npx) break;
+          const int row = idx >> 3, col = idx & 7;
+          const int vh = tc.h0 + p.vs_dh_min + row, vw = tc.w0 + col;
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+          if (row_ok && lane_live && tc.n0 < p.N && vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
+            const float* pp = patch + row * 16 + col + st;
+            o[0] = pp[0];
+            if (p.stem_C > 1) o[1] = pp[24 * 16];
+            if (p.stem_C > 2) o[2] = pp[2 * 24 * 16];
+            if (p.stem_C > 3) o[3] = pp[3 * 24 * 16];
+          }
+          uint2 hi, lo;
+          fa_split4(o, p.fa_is_bf16, hi, lo);
+          const uint32_t off = static_cast<uint32_t>(idx) * 128u + (static_cast<uint32_t>(chunk ^ (idx & 7)) << 4) + sub;
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          if (p.planes == 2) *reinterpret_cast<uint2*>(a_lo + off) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    } else if (p.hs) {
       // Strip units: unit u = (strip pixel u >> 4, float4 q = u & 15); thread owns units ct + 256 * j.  The strip is double-
       // buffered: the converters build chunk c + 1 while the MMAs read chunk c.  Per-unit facts that do not depend on the
       // tile (shared-memory offset, pixel offset inside the strip, "belongs to the tile's own 16 x 8 pixels") are computed
@@ -554,58 +638,67 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             const float* const xo = xs + origin * C + cbase;          // only dereferenced when `inside`
             const float* const ro = rs != nullptr ? rs + origin * C + cbase : nullptr;
             bool waited = false;
+            // One latency wave per chunk when there is a single fp32 source (12 float4 in flight per thread), two waves of six
+            // (value + residual) for the block's first conv: the loads are register-staged, so in-flight bytes are what the
+            // 128-register budget allows.
+            auto convert = [&](auto batch_tag) {
+              constexpr int kBatch = decltype(batch_tag)::value;
+              constexpr bool kRes = kBatch == 6;
 #pragma unroll
-            for (int j0 = 0; j0 < kUnits; j0 += 6) {
-              float4 xv[6], rv[6]; int goff[6]; uint32_t okm = 0, inm = 0;
+              for (int j0 = 0; j0 < kUnits; j0 += kBatch) {
+                float4 xv[kBatch], rv[kRes ? kBatch : 1]; int goff[kBatch]; uint32_t okm = 0, inm = 0;
 #pragma unroll
-              for (int u = 0; u < 6; ++u) {
-                const int j = j0 + u;
-                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; goff[u] = 0;
-                if (j < nunits) {
-                  if (inside) {
-                    goff[u] = poff[j] * C;
-                    okm |= 1u << u; inm |= 1u << u;
-                    xv[u] = __ldg(reinterpret_cast<const float4*>(xo + goff[u]));
-                    if (ro != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(ro + goff[u]));
-                  } else {
-                    const int px_i = (ct + 256 * j) >> 4;               // border tile: per-pixel zero / reflect logic
-                    const int row = px_i / p.hs_cols, col = px_i - row * p.hs_cols;
-                    const FaPix px = fa_locate(p, src, tc.n0, vh0 + row, vw0 + col);
-                    if (px.ok) {
-                      okm |= 1u << u; if (px.interior) inm |= 1u << u;
-                      goff[u] = static_cast<int>(px.off - origin * C);  // same addressing as the fast path
-                      xv[u] = __ldg(reinterpret_cast<const float4*>(xs + px.off + cbase));
-                      if (rs != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(rs + px.off + cbase));
+                for (int u = 0; u < kBatch; ++u) {
+                  const int j = j0 + u;
+                  xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); goff[u] = 0;
+                  if (kRes) rv[u] = xv[u];
+                  if (j < nunits) {
+                    if (inside) {
+                      goff[u] = poff[j] * C;
+                      okm |= 1u << u; inm |= 1u << u;
+                      xv[u] = __ldg(reinterpret_cast<const float4*>(xo + goff[u]));
+                      if (kRes) rv[u] = __ldg(reinterpret_cast<const float4*>(ro + goff[u]));
+                    } else {
+                      const int px_i = (ct + 256 * j) >> 4;               // border tile: per-pixel zero / reflect logic
+                      const int row = px_i / p.hs_cols, col = px_i - row * p.hs_cols;
+                      const FaPix px = fa_locate(p, src, tc.n0, vh0 + row, vw0 + col);
+                      if (px.ok) {
+                        okm |= 1u << u; if (px.interior) inm |= 1u << u;
+                        goff[u] = static_cast<int>(px.off - origin * C);  // same addressing as the fast path
+                        xv[u] = __ldg(reinterpret_cast<const float4*>(xs + px.off + cbase));
+                        if (kRes) rv[u] = __ldg(reinterpret_cast<const float4*>(rs + px.off + cbase));
+                      }
                     }
                   }
                 }
-              }
-              if (!waited) {
-                // the first loads of the chunk are in flight before the (rarely blocking) wait for the strip buffer
-                mbar_wait_sleep(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
-                waited = true;
-              }
-#pragma unroll
-              for (int u = 0; u < 6; ++u) {
-                const int j = j0 + u;
-                if (j >= nunits) continue;
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-                if ((okm >> u) & 1u) {
-                  o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), act) + rv[u].x;
-                  o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), act) + rv[u].y;
-                  o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), act) + rv[u].z;
-                  o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), act) + rv[u].w;
-                  // write-back of the evaluated operand: the tile's own pixels only (each source pixel belongs to exactly
-                  // one tile); `interior` excludes reflected border positions, which alias other pixels
-                  if (wb && ((own_mask >> j) & 1u) && ((inm >> u) & 1u))
-                    *reinterpret_cast<float4*>(p.fa_out[src] + origin * C + cbase + goff[u]) = make_float4(o[0], o[1], o[2], o[3]);
+                if (!waited) {
+                  // the first loads of the chunk are in flight before the (rarely blocking) wait for the strip buffer
+                  mbar_wait_sleep(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
+                  waited = true;
                 }
-                uint2 hi, lo;
-                fa_split4(o, p.fa_is_bf16, hi, lo);
-                *reinterpret_cast<uint2*>(strip_hi + soff[j]) = hi;
-                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + soff[j]) = lo;
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                  const int j = j0 + u;
+                  if (j >= nunits) continue;
+                  float o[4] = {0.f, 0.f, 0.f, 0.f};
+                  if ((okm >> u) & 1u) {
+                    o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), act); o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), act);
+                    o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), act); o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), act);
+                    if (kRes) { o[0] += rv[u].x; o[1] += rv[u].y; o[2] += rv[u].z; o[3] += rv[u].w; }
+                    // write-back of the evaluated operand: the tile's own pixels only (each source pixel belongs to exactly
+                    // one tile); `interior` excludes reflected border positions, which alias other pixels
+                    if (wb && ((own_mask >> j) & 1u) && ((inm >> u) & 1u))
+                      *reinterpret_cast<float4*>(p.fa_out[src] + origin * C + cbase + goff[u]) = make_float4(o[0], o[1], o[2], o[3]);
+                  }
+                  uint2 hi, lo;
+                  fa_split4(o, p.fa_is_bf16, hi, lo);
+                  *reinterpret_cast<uint2*>(strip_hi + soff[j]) = hi;
+                  if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + soff[j]) = lo;
+                }
               }
-            }
+            };
+            if (rs != nullptr) convert(std::integral_constant<int, 6>{});
+            else convert(std::integral_constant<int, 12>{});
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&aready_bar[buf]);
@@ -619,7 +712,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         const int npx = p.vs_rows * p.tile_w;                 // tile_w == 8: one image row = one 1024 B swizzle atom
         const int vw0 = tc.w0 + p.tap_off[0][1], vh0 = tc.h0 + p.vs_dh_min;
         for (int kc = 0; kc < kch0; ++kc) {
-          mbar_wait_sleep(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1);                     // short stage cycles: poll (a suspended wait wakes up too coarsely)
           uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
           uint8_t* a_lo = a_hi + vs_a_bytes;
           const int cbase = kc * kKC + q * 4;
@@ -628,51 +721,36 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
             sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
           }
-          for (int base = 0; base < npx; base += 64) {
-            float4 xv[4], rv[4]; bool ok[4];
+          // One latency wave per strip: every unit of this thread (a strip has at most 16 x 12 pixels) is loaded before any is
+          // used — with waves of four the strip cost three global round trips and the converters, not the MMAs, set the pace.
+          constexpr int kB = 12;
+          const bool has_res = p.fa_res[0] != nullptr;
+          for (int base = 0; base < npx; base += 16 * kB) {
+            float4 xv[kB]; uint32_t okm = 0; long long offs[kB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kB; ++u) {
               const int idx = base + u * 16 + pr;
-              xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = xv[u]; ok[u] = false;
-              if (idx < npx && p.fa == 2) {
-                // stem: lanes 4q..4q+3 = (tap s = q / 2, channels (q & 1) * 4 ..); only c < stem_C (<= 4) are non-zero
-                const int vh = vh0 + (idx >> 3), vw = vw0 + (idx & 7), st = q >> 1;
-                int hh = vh - p.stem_pad, ww = vw + st - p.stem_pad;
-                bool in = (tc.n0 < p.N) && (vh >= 0) && (vh < p.H) && (vw >= 0) && (vw < p.W) && ((q & 1) == 0) && (st < p.stem_S);
-                if (p.fa_border_mode == DLB_PAD_REFLECT) {
-                  if (hh < 0) hh = -hh; if (hh >= p.Hs) hh = 2 * p.Hs - 2 - hh;
-                  if (ww < 0) ww = -ww; if (ww >= p.Ws) ww = 2 * p.Ws - 2 - ww;
-                } else {
-                  in = in && hh >= 0 && hh < p.Hs && ww >= 0 && ww < p.Ws;
-                }
-                ok[u] = in;
-                if (in) {
-                  const float* xp = p.fa_x[0] + (static_cast<long long>(tc.n0) * p.stem_C * p.Hs + hh) * p.Ws + ww;
-                  const long long plane = static_cast<long long>(p.Hs) * p.Ws;
-                  xv[u].x = __ldg(xp);
-                  if (p.stem_C > 1) xv[u].y = __ldg(xp + plane);
-                  if (p.stem_C > 2) xv[u].z = __ldg(xp + 2 * plane);
-                  if (p.stem_C > 3) xv[u].w = __ldg(xp + 3 * plane);
-                }
-              } else if (idx < npx) {
+              xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); offs[u] = 0;
+              if (idx < npx) {
                 const FaPix px = fa_locate(p, 0, tc.n0, vh0 + (idx >> 3), vw0 + (idx & 7));
-                ok[u] = px.ok;
                 if (px.ok) {
+                  okm |= 1u << u; offs[u] = px.off;
                   xv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_x[0] + px.off + cbase));
-                  if (p.fa_res[0] != nullptr) rv[u] = __ldg(reinterpret_cast<const float4*>(p.fa_res[0] + px.off + cbase));
                 }
               }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kB; ++u) {
               const int idx = base + u * 16 + pr;
               if (idx >= npx) continue;
               float o[4] = {0.f, 0.f, 0.f, 0.f};
-              if (ok[u]) {
-                o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[0]) + rv[u].x;
-                o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), p.fa_act[0]) + rv[u].y;
-                o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), p.fa_act[0]) + rv[u].z;
-                o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[0]) + rv[u].w;
+              if ((okm >> u) & 1u) {
+                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_res) rv = __ldg(reinterpret_cast<const float4*>(p.fa_res[0] + offs[u] + cbase));
+                o[0] = fa_act1(fmaf(xv[u].x, sc.x, sh.x), p.fa_act[0]) + rv.x;
+                o[1] = fa_act1(fmaf(xv[u].y, sc.y, sh.y), p.fa_act[0]) + rv.y;
+                o[2] = fa_act1(fmaf(xv[u].z, sc.z, sh.z), p.fa_act[0]) + rv.z;
+                o[3] = fa_act1(fmaf(xv[u].w, sc.w, sh.w), p.fa_act[0]) + rv.w;
               }
               uint2 hi, lo;
               fa_split4(o, p.fa_is_bf16, hi, lo);
@@ -948,6 +1026,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       if (!use_vs) return set_error("conv_tc: the fused stem needs the vertical-strip mode (image at least 16 x 8, S x 1 filter)");
       if (ph.stem_C < 1 || ph.stem_C > 4 || ph.stem_S < 1 || ph.stem_S > 8 || ph.cin[0] != 64 || ph.nsrc != 1)
         return set_error("conv_tc: fused stem needs C <= 4, S <= 8 and a 64-lane operand");
+      if (tile_h + ph.stem_S - 1 > 24) return set_error("conv_tc: fused stem patch rows exceed 24");
     }
     if (p.Hs < 1 || p.Ws < 1) return set_error("conv_tc: fused operand border larger than the input");
     if (ph.fa_border_mode == DLB_PAD_REFLECT && (ph.fa_border >= p.Hs || ph.fa_border >= p.Ws))
@@ -1009,7 +1088,8 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes
                                 : (use_hs ? p.hs_nbuf * p.planes * p.hs_plane_bytes : 0);
   const int stage_bytes = use_hs ? p.planes * b_bytes
-                                 : (use_vs ? p.planes * p.vs_rows * tile_w * 128 : p.planes * (kABytes + b_bytes));
+                                 : (use_vs ? p.planes * p.vs_rows * tile_w * 128 + (ph.fa == 2 ? kStemPatchBytes : 0)
+                                           : p.planes * (kABytes + b_bytes));
   int stages = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;

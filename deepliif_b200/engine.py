@@ -237,7 +237,7 @@ class ResnetEngine(_EngineBase):
         self.fuse_residual = _env_flag("DLB_FUSE_RESIDUAL", True) if fuse_residual is None else bool(fuse_residual)
         # per-stage switches (measured choices): the trunk always gains; the stem / head / ConvTranspose stages
         # have little MMA work per converted strip and are converter-bound
-        self.fuse_stem = _env_flag("DLB_FUSE_STEM", False)
+        self.fuse_stem = _env_flag("DLB_FUSE_STEM", True)
         self.fuse_up = _env_flag("DLB_FUSE_UP", False)
         self.fuse_head = _env_flag("DLB_FUSE_HEAD", False)
         if padding_type not in ("zero", "reflect"):
@@ -366,14 +366,14 @@ class ResnetEngine(_EngineBase):
         return self.head.run_direct(y, N, h, w, pad_mode=self.pad_mode, in_scale=sc, in_shift=sh, in_act=ACT_RELU,
                                     out_act=ACT_TANH, out_nchw=True)
 
-    def _consume(self, layer, lazy, N, H, W, *, pad=None, border=0, keep=False, fuse_stats=True, block=False, allow=True):
+    def _consume(self, layer, lazy, N, H, W, *, pad=None, border=0, keep=False, fuse_stats=True, block=False, allow=(2,)):
         """Run `layer` on the lazy activation.  Strip-eligible layers evaluate it in-kernel (no HBM pass); the others
         (stride 2, maps below 16 x 8) get their operand planes from one dlb_norm_apply pass.  keep: also materialise the
         evaluated activation in fp32 (the ResnetBlock residual stream).  Returns (y, stats_ws, kept fp32 | None)."""
         Hv, Wv = H + 2 * border, W + 2 * border
         d = layer.desc(N, Hv, Wv, pad)
         kept = None
-        if allow and layer.use_tc and ops.conv_tc_fused_mode(d, self.prec.split, layer.n_tile) > 0:
+        if allow and layer.use_tc and ops.conv_tc_fused_mode(d, self.prec.split, layer.n_tile) in allow:
             if keep:
                 kept = torch.empty_like(lazy.x)
             srcs = [lazy.src(border, self.pad_mode, out=kept)]
@@ -431,11 +431,11 @@ class ResnetEngine(_EngineBase):
             cur = Lazy(y, sc, sh, ACT_NONE, residual=r)
             tap(f"block{bi}", cur)
         for i in range(2):
-            y, ws, _ = self._consume(self.up[i], cur, N, h, w, allow=self.fuse_up)
+            y, ws, _ = self._consume(self.up[i], cur, N, h, w, allow=(1, 2, 3) if self.fuse_up else ())
             h, w = h * 2, w * 2
             sc, sh = self._stats(y, self.up_norm[i], ws)
             cur = Lazy(y, sc, sh, ACT_RELU)
-        z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False, allow=self.fuse_head)
+        z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False, allow=(1, 2, 3) if self.fuse_head else ())
         return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
 
     __call__ = forward
@@ -526,7 +526,7 @@ class UnetEngine(_EngineBase):
             sc, sh = ss[lvl]
             lz = [Lazy(raw[lvl], sc, sh, ACT_RELU)] + ([] if lvl == nd - 1 else [below])   # relu of both skip halves
             layer = self.up[lvl]
-            use_fused = fused and ops.conv_tc_fused_mode(layer.desc(N, h, w), self.prec.split, layer.n_tile) > 0
+            use_fused = fused and ops.conv_tc_fused_mode(layer.desc(N, h, w), self.prec.split, layer.n_tile) == 2
             if use_fused:
                 run = lambda fs: layer.run_fused([l.src() for l in lz], N, h, w, fuse_stats=fs)
             else:

@@ -107,10 +107,14 @@ typedef struct dlb_fused_src {
   int border;
   int border_mode;
 } dlb_fused_src;
-/* How dlb_conv_tc_fwd_fused would run this layer: 2 = every phase in halo-strip mode (each input value converted once per
- * output tile; the efficient case: stride-1 layers on maps of at least 16 x 8), 1 = vertical-strip mode with resident
- * weights (R x 1 filters: the head), 0 = at least one phase would fall back to per-tap conversion (stride-2 layers, tiny
- * maps) — still correct, but slower than dlb_norm_apply + dlb_conv_tc_fwd; callers use this to choose. */
+/* How dlb_conv_tc_fwd_fused would run this layer (callers use it to choose between the fused call and
+ * dlb_norm_apply + dlb_conv_tc_fwd; every mode computes the same function):
+ *   2  every phase in halo-strip mode AND enough tensor-core work per converted strip (taps x N) that the converter warps
+ *      stay hidden behind the MMAs — the 256 -> 256 3x3 ResNet-block convolutions in split precision: use the fused call;
+ *   3  halo-strip mode, but too little MMA work per strip (ConvTranspose phases, narrow layers, single-pass precision):
+ *      the converters set the pace, the unfused pair is faster;
+ *   1  vertical-strip mode with resident weights (R x 1 filters: the head) — converter-bound as well;
+ *   0  at least one phase would convert per tap (stride-2 layers, maps below 16 x 8): slowest. */
 int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_tile);
 int dlb_conv_tc_fwd_fused(const dlb_conv_desc* d, const dlb_fused_src* src, const void* w_hi, const void* w_lo,
                           const float* bias, float* y, int fmt, int split, int n_tile, void* stats_ws,
