@@ -112,49 +112,95 @@ def _pipeline(nets, gen_keys, seg_keys, weights, micro_batch, n_streams):
     return pipe
 
 
-def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3, seg_only=False):
-    """uint8 tiles [T,ts,ts,3] (numpy) -> dict[name -> uint8 [T,ts,ts,3]] with the reference's result keys
-    (G1.., G{S}, and per-modality seg G{S}k), skipping empty tiles exactly like run_wrapper (:399-443).
-    seg_only: the seg generators whose weight is zero are not run, nor the modality generators that only feed them
-    (models/__init__.py:318-325; the Marker generator always runs) — their keys are then absent from the result."""
+_PINNED = {}
+
+
+def _pinned(tag, shape):
+    """Reusable pinned staging buffer (cudaHostAlloc costs milliseconds: never per image)."""
+    n = int(np.prod(shape))
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < n:
+        buf = _PINNED[tag] = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+    return buf[:n].view(shape)
+
+
+def _plan_nets(opt, seg_weights, mod_only, seg_only):
+    """Which generators run (reference run_dask, models/__init__.py:296-325) and the keys of the result."""
     gens, segs = _names(opt)
-    T, ts = tiles_u8.shape[0], tiles_u8.shape[1]
-    S = opt.mod_id_seg
     with_seg = bool(segs) and not mod_only
     w = _seg_weights(opt, seg_weights) if with_seg else None
     run_gens, run_segs = list(gens), (list(segs) if with_seg else None)
     if with_seg and seg_only:
-        marker = None
-        if "Marker" in opt.modalities_names:
-            marker = f"G{opt.modalities_names.index('Marker')}"
+        marker = f"G{opt.modalities_names.index('Marker')}" if "Marker" in opt.modalities_names else None
         run_segs = [k if w[i] != 0 else None for i, k in enumerate(segs)]
         run_gens = [k if (run_segs[i + 1] is not None or k == marker) else None for i, k in enumerate(gens)]
-    keys = [k for k in run_gens if k] + ([f"G{S}"] + [k for k in run_segs if k] if with_seg else [])
-    out = {k: np.zeros((T, ts, ts, 3), np.uint8) for k in keys}
+    return gens, segs, with_seg, w, run_gens, run_segs
+
+
+def run_batch_device(tiles_dev, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3, seg_only=False,
+                     want_parts=True):
+    """uint8 tiles [T,ts,ts,3] ON THE DEVICE -> dict[name -> uint8 [T,ts,ts,3] on the device] with the reference's result
+    keys (G1.., G{S}, and — with want_parts — the per-modality seg outputs G{S}k), skipping empty tiles exactly like
+    run_wrapper (:399-443).  Nothing returns to the host here except the 3 integers per tile of the is_empty statistic.
+    seg_only: seg generators whose weight is zero are not run, nor the modality generators that only feed them
+    (models/__init__.py:318-325; the Marker generator always runs) — their keys are then absent from the result."""
+    gens, segs, with_seg, w, run_gens, run_segs = _plan_nets(opt, seg_weights, mod_only, seg_only)
+    T, ts = tiles_dev.shape[0], tiles_dev.shape[1]
+    S = opt.mod_id_seg
+    dev = tiles_dev.device
+    keys = [k for k in run_gens if k] + ([f"G{S}"] + ([k for k in run_segs if k] if want_parts else []) if with_seg else [])
+    out = {k: torch.zeros((T, ts, ts, 3), dtype=torch.uint8, device=dev) for k in keys}
     if T == 0:
         return out
     # is_empty(): gray-level variance per tile, computed on the device from the uint8 batch (exact integer sums)
-    var = ops.tile_gray_variance(torch.from_numpy(np.ascontiguousarray(tiles_u8)).cuda())
+    var = ops.tile_gray_variance(tiles_dev)
     live = [i for i in range(T) if var[i] >= EMPTY_TILE_VARIANCE]
-    for i in set(range(T)) - set(live):
+    dead = sorted(set(range(T)) - set(live))
+    if dead:
+        di = torch.tensor(dead, device=dev)
         for j, k in enumerate(gens):
             if k in out:
-                out[k][i] = np.array(opt.background_colors[j], np.uint8)
+                out[k][di] = torch.tensor(opt.background_colors[j], dtype=torch.uint8, device=dev)
     if live:
-        batch = torch.from_numpy(np.ascontiguousarray(tiles_u8[live])).pin_memory()
+        all_live = len(live) == T
+        li = None if all_live else torch.tensor(live, device=dev)
+        batch = tiles_dev if all_live else tiles_dev.index_select(0, li)
         pipe = _pipeline(nets, run_gens, run_segs, w, micro_batch, n_streams)
+
+        def put(key, val):
+            if all_live:
+                out[key].copy_(val)
+            else:
+                out[key].index_copy_(0, li, val)
         if with_seg:
-            res = pipe.infer_u8(batch, want_parts=True)
-            torch.cuda.synchronize()
-            out[f"G{S}"][live] = res["seg"].numpy()
-            for j, k in enumerate(pipe.part_index):
-                out[segs[k]][live] = res["parts"][j].numpy()
+            mods_u8, seg_u8, _, parts_u8 = pipe.infer_u8_device(batch, want_parts=want_parts)
+            put(f"G{S}", seg_u8)
+            if want_parts:
+                for j, k in enumerate(pipe.part_index):
+                    put(segs[k], parts_u8[j])
+            for j, i in enumerate(pipe.mod_index):
+                put(gens[i], mods_u8[j])
         else:
-            res = pipe.infer_mods_u8(batch)
-            torch.cuda.synchronize()
-        for j, i in enumerate(pipe.mod_index if with_seg else range(len(gens))):
-            out[gens[i]][live] = res["mods"][j].numpy()
+            x = ops.u8_to_f32(batch.contiguous())
+            mb = micro_batch if micro_batch > 0 else x.shape[0]
+            for i, k in enumerate(gens):
+                o = torch.cat([nets[k](x[s_:s_ + mb]) for s_ in range(0, x.shape[0], mb)])
+                put(k, ops.f32_to_u8(o))
     return out
+
+
+def run_batch(tiles_u8, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3, seg_only=False):
+    """uint8 tiles [T,ts,ts,3] (numpy) -> dict[name -> uint8 numpy [T,ts,ts,3]]: host wrapper of run_batch_device (one
+    pinned H2D copy in, one D2H copy per result key out)."""
+    tiles_u8 = np.ascontiguousarray(tiles_u8)
+    if tiles_u8.shape[0] == 0:
+        dev_in = torch.zeros(tiles_u8.shape, dtype=torch.uint8, device="cuda")
+    else:
+        stage = _pinned("in", tiles_u8.shape)
+        stage.copy_(torch.from_numpy(tiles_u8))
+        dev_in = stage.to("cuda", non_blocking=True)
+    res = run_batch_device(dev_in, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only)
+    return {k: v.cpu().numpy() for k, v in res.items()}
 
 
 def run_dask(img, model_path=None, nets=None, eager_mode=True, opt=None, seg_only=False, mod_only=False,
@@ -178,13 +224,15 @@ def run_wrapper(tile, run_fn, model_path=None, nets=None, eager_mode=True, opt=N
 
 
 def infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=None, mod_only=False, seg_only=False, micro_batch=8,
-                n_streams=3):
+                n_streams=3, want_parts=True):
     """PIL image -> dict[net key -> stitched PIL image] (None on non-zero ranks of a torchrun launch).
 
     The tile -> infer -> stitch loop of the reference's inference() (models/__init__.py:484-500, InferenceTiler
-    util/__init__.py:129-331).  One process per GPU: every rank tiles the image itself (cheap, deterministic), infers tiles
-    rank, rank+W, ... (tile sharding, no data-path collective; SURVEY.md 8e, BASELINE config 3) and rank 0 receives every
-    rank's uint8 results in ONE gather (all output keys stacked) and stitches."""
+    util/__init__.py:129-331).  One process per GPU: every rank tiles the image itself (cheap, deterministic), uploads and
+    infers tiles rank, rank+W, ... (tile sharding, no data-path collective; SURVEY.md 8e, BASELINE config 3); the uint8
+    results stay on the device, all output keys stacked, until ONE NCCL gather brings them to rank 0, which copies them to
+    the host once and stitches.  want_parts=False skips the per-modality seg outputs (only `return_seg_intermediate` needs
+    them): half the result bytes."""
     import torch.distributed as dist
     from .. import sharding
     grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
@@ -194,21 +242,30 @@ def infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=None, mod_o
     distributed = dist.is_available() and dist.is_initialized()      # a group of any size (also 1) takes the gather path
     world = dist.get_world_size() if distributed else 1
     rank = dist.get_rank() if distributed else 0
+    mine = np.ascontiguousarray(sharding.shard(tiles, rank, world)) if distributed else tiles
+    if len(mine):
+        stage = _pinned("in", mine.shape)
+        stage.copy_(torch.from_numpy(mine))
+        dev_in = stage.to("cuda", non_blocking=True)
+    else:
+        dev_in = torch.zeros((0,) + tuple(tiles.shape[1:]), dtype=torch.uint8, device="cuda")
+    local = run_batch_device(dev_in, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only, want_parts)
+    keys = sorted(local.keys())
+    stacked = torch.stack([local[k] for k in keys], dim=1) if len(mine) else \
+        torch.zeros((0, len(keys)) + tuple(tiles.shape[1:]), dtype=torch.uint8, device="cuda")
     if distributed:
-        mine = sharding.shard(tiles, rank, world)
-        # an idle rank (fewer tiles than GPUs) still learns the key list from a zero-tile call
-        local = run_batch(mine, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only)
-        keys = sorted(local.keys())
-        stacked = np.stack([local[k] for k in keys], axis=1) if len(mine) else \
-            np.zeros((0, len(keys)) + tuple(tiles.shape[1:]), np.uint8)
-        full = sharding.gather_to_rank0(torch.from_numpy(np.ascontiguousarray(stacked)), len(tiles))
+        full = sharding.gather_to_rank0(stacked, len(tiles), to_numpy=False)       # [T, K, ts, ts, 3] on rank 0's device
         if rank != 0:
             return None
-        res = {k: full[:, j] for j, k in enumerate(keys)}
     else:
-        res = run_batch(tiles, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only)
+        full = stacked
+    host = _pinned("out", tuple(full.shape))
+    host.copy_(full, non_blocking=True)
+    torch.cuda.synchronize()
+    full_np = host.numpy()
     results = {}
-    for k, v in res.items():
+    for j, k in enumerate(keys):
+        v = full_np[:, j]
         if tile_size != opt.scale_size:
             v = np.stack([np.asarray(Image.fromarray(t).resize((tile_size, tile_size))) for t in v])
         results[k] = Image.fromarray(grid.stitch(v))
@@ -234,7 +291,8 @@ def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, ea
         raise NotImplementedError("inference(): models with several input images side by side (input_no > 1, SDG-style) are "
                                   "outside the B200 hot-path scope")
     nets = init_nets(os.getenv("DEEPLIIF_MODEL_DIR", model_path), True, opt)
-    results = infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=seg_weights, mod_only=mod_only, seg_only=seg_only)
+    results = infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=seg_weights, mod_only=mod_only, seg_only=seg_only,
+                          want_parts=bool(return_seg_intermediate) and not seg_only)
     if results is None:
         return {}
     # ---- the reference's naming (models/__init__.py:502-565) -----------------------------------------------

@@ -204,6 +204,22 @@ class TilePipeline:
         return out_host
 
     @torch.no_grad()
+    def infer_u8_device(self, x_u8, want_parts=False):
+        """x_u8: uint8 [N,H,W,3] already on the device.  Returns device tensors (mods_u8 [M,N,H,W,3], seg_u8 [N,H,W,3],
+        mask [N,H,W], parts_u8 [K,N,H,W,3] | None).  With use_graph these are the captured graph's static buffers: consume
+        (copy / scatter) them before the next call of the same shape."""
+        self._keep_parts = [] if want_parts else None
+        cap = None
+        if self.use_graph:
+            cap = self._graphed("u8", x_u8.shape, torch.uint8, x_u8.device, self._u8_body)
+        if cap is not None:
+            cap.static_in.copy_(x_u8, non_blocking=True)
+            cap.graph.replay()
+            ops.LAUNCHES["count"] += cap.launches
+            return cap.outs
+        return self._u8_body(x_u8.contiguous())
+
+    @torch.no_grad()
     def infer_mods_u8(self, tiles_u8_host):
         """Modalities only (mod_only / seg_gen=False): no seg generators are run."""
         dev = torch.device("cuda", torch.cuda.current_device())

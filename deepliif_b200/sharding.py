@@ -18,10 +18,13 @@ def shard(items, rank, world):
     return items[rank::world]
 
 
-def gather_to_rank0(local, n_items, group=None):
+def gather_to_rank0(local, n_items, group=None, to_numpy=True):
     """local: uint8 tensor/array [n_local, ...] holding this rank's results in shard order.  Returns on rank 0 the
-    full [n_items, ...] array in the original tile order (None elsewhere).  Works on gloo (CPU) and nccl (CUDA)."""
+    full [n_items, ...] array in the original tile order (None elsewhere).  Works on gloo (CPU) and nccl (CUDA).
+    to_numpy=False keeps the result a tensor on the gather's device (rank 0 of an NCCL group: its GPU)."""
     if not (dist.is_available() and dist.is_initialized()):
+        if not to_numpy:
+            return local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
         return np.asarray(local.cpu() if isinstance(local, torch.Tensor) else local)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
@@ -35,6 +38,13 @@ def gather_to_rank0(local, n_items, group=None):
     dist.gather(pad, bufs, dst=0, group=group)
     if rank != 0:
         return None
+    if not to_numpy:
+        out_t = torch.empty((n_items,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        for r in range(world):
+            idx = shard_indices(n_items, r, world)
+            if idx:
+                out_t[torch.tensor(idx, device=t.device)] = bufs[r][: len(idx)]
+        return out_t
     out = np.empty((n_items,) + tuple(t.shape[1:]), dtype=np.asarray(pad.cpu()).dtype)
     for r in range(world):
         idx = shard_indices(n_items, r, world)
