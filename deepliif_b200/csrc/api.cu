@@ -157,7 +157,7 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
   const long long C = d->Cout;
   const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
   if (np < 0) return np;
-  // fused statistics: slices are 32-pixel row groups of the CTA tiles, phases concatenated
+  // fused statistics: one slice per 128-pixel CTA tile (the four epilogue warps merge their partials), phases concatenated
   StatsPtrs sp; memset(&sp, 0, sizeof(sp));
   int slice_base[4] = {0, 0, 0, 0}, S_total = 0;
   if (stats_ws != nullptr) {
@@ -169,7 +169,7 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
       tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, fsrc != nullptr || stem != nullptr);
       if (tn != 1) return set_error("dlb_conv_tc_fwd: fused statistics need OH*OW >= 128 per phase (use dlb_norm_stats)");
       slice_base[i] = S_total;
-      S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw) * 4;
+      S_total += ((geo[i].OH + th - 1) / th) * ((geo[i].OW + tw - 1) / tw);      // one slice per 128-pixel CTA tile
     }
     if (S_total > L.S_cap) return set_error("dlb_conv_tc_fwd: statistics workspace slice capacity exceeded");
   }

@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t aready_bar[2];   // hs mode: operand strip buffer written (converter warps)
   __shared__ __align__(8) uint64_t afree_bar[2];    // hs mode: every MMA reading that strip buffer has retired
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float2 st_x[4][32];               // per-epilogue-warp (sum, M2) of one 32-channel group, merged per tile
+  __shared__ float st_n[4];
 
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -450,8 +452,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       // slice of the statistics workspace this warp's 32 rows belong to (tile_n == 1 when stats are fused)
       const int th_i = tc.h0 / p.tile_h, tw_i = tc.w0 / p.tile_w;
-      const long long st_row = static_cast<long long>(n) * p.st_S_cap + p.st_slice_base + (th_i * p.tiles_w + tw_i) * 4 + q;
-      if (p.st_partial != nullptr && tc.cout0 == 0 && lane == 0) p.st_cnt[st_row] = static_cast<float>(__popc(vmask));
+      // one statistics slice per CTA tile (tile_n == 1: the tile lies in image tc.n0); the four epilogue warps merge their
+      // 32-pixel partials in shared memory before anything is written
+      const long long st_row = static_cast<long long>(tc.n0) * p.st_S_cap + p.st_slice_base + (th_i * p.tiles_w + tw_i);
       for (int c = 0; c < p.n_tile; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
@@ -491,7 +494,23 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             a[j] = valid ? d * d : 0.f;
           }
           const float m2 = warp_colsum32(a, lane);
-          p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(sum, m2);
+          st_x[q][lane] = make_float2(sum, m2);
+          if (lane == 0) st_n[q] = cntf;
+          asm volatile("bar.sync 2, 128;" ::: "memory");            // the four epilogue warps
+          if (q == 0) {
+            // merge in warp-quarter order (fixed => deterministic): n = sum n_q, S = sum S_q, M2 = sum (M2_q + n_q (mean_q - mean)^2)
+            float nt = 0.f, st = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { nt += st_n[k]; st += st_x[k][lane].x; }
+            const float mt = nt > 0.f ? st / nt : 0.f;
+            float m2t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (st_n[k] > 0.f) { const float d = st_x[k][lane].x / st_n[k] - mt; m2t += st_x[k][lane].y + st_n[k] * d * d; }
+            p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(st, m2t);
+            if (tc.cout0 == 0 && c == 0 && lane == 0) p.st_cnt[st_row] = nt;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");            // st_x is reused by the next channel group
         }
       }
       tc_fence_before();
