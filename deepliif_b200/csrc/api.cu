@@ -257,23 +257,26 @@ extern "C" int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_t
   const long long C = d->Cout;
   const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
   if (np < 0) return np;
-  int best = 2;
-  bool light = false;
+  bool light = false, staged = d->nsrc == 1;
+  int n_vs = 0;
   for (int i = 0; i < np; ++i) {
     if (geo[i].ntaps > 16) return 0;
     int tw, th, tn, nt;
     const int m = tc_plan_tiles(geo[i], d->nsrc, d->Cin, d->Cout, split, n_tile, &tw, &th, &tn, &nt, 1);
     if (m == 0) return 0;
-    best = m < best ? m : best;
     // tensor-pipe cycles one 64-channel chunk of this phase keeps the MMA busy: taps x 4 K-steps x (3 | 1) MMAs x N/2 cycles.
-    // The converter warps need ~4-6 us per strip (measured: register-staged global loads, two latency waves); below ~8k
-    // cycles of MMA work per strip they, not the tensor pipe, set the pace.
+    // The converter warps need ~4-6 us per strip when they load from HBM (measured: register-staged global loads); below
+    // ~8k cycles of MMA work per strip they, not the tensor pipe, set the pace — unless the source is staged by TMA.
     // (N of the widest tile the layer could use, not the planned one: the choice must not depend on the batch size, which
     // only changes how many CTAs share the work — results for a tile are then identical at every batch size.)
     const int n_wide = d->Cout >= 256 ? 256 : (d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32));
+    if (m == 1) { ++n_vs; light = true; }                     // resident-weight vertical strips: few taps, narrow N
     if (m == 2 && geo[i].ntaps * 4 * (split ? 3 : 1) * (n_wide / 2) < 8192) light = true;
+    if (m == 2 && !hs_staging_fits(geo[i], split, nt)) staged = false;
   }
-  return (best == 2 && light) ? 3 : best;
+  if (np == 1 && n_vs == 1) return 1;
+  if (!light) return 2;
+  return staged ? 4 : 3;
 }
 
 extern "C" int dlb_conv_tc_fwd(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,

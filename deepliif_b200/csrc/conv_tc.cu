@@ -42,7 +42,7 @@ constexpr int kKC = 64;                // channels per pipeline stage: 64 x 2 B 
 constexpr int kABytes = 128 * 128;     // one A plane of a stage: 128 pixels x 128 B
 constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int kConvWarps = 8;          // fused-operand mode: warps 6-13 build the A planes from fp32 producer outputs
-constexpr int kThreadsFa = kThreads + 32 * kConvWarps;
+constexpr int kThreadsFa = kThreads + 32 * kConvWarps + 32;   // + warp 14: fp32 source staging producer (ht mode)
 constexpr int kStemPatchBytes = 4 * 24 * 16 * 4;   // fused stem: fp32 input patch [4 ch][<= 24 rows][16 cols] per strip stage
 constexpr int kHsMaxPx = 192;          // halo-strip mode: at most this many strip pixels (3x3: 18 x 10 = 180; 2x2 taps: 17 x 9)
 constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
@@ -104,6 +104,15 @@ struct alignas(64) TcParams {
   // the converters build the horizontal-window operand lane (s * 8 + c) = pad(x)[n, c, row - pad, col + s - pad] of
   // dlb_stem_window_pack on the fly, so the 21x blown-up operand tensor never exists in HBM.
   int stem_C, stem_S, stem_pad;
+  // vertical-strip fused mode with TMA staging (vt): the producer thread streams the fp32 source rows of every strip into
+  // a two-slot shared-memory staging ring (half a strip per slot) and the converter warps transform smem -> smem; no
+  // global-load latency sits inside the conversion.  Zero border only (TMA out-of-bounds fill = the zero padding).
+  int vt, vt_half_rows;
+  CUtensorMap a_f32;
+  // halo-strip mode with TMA staging (ht): a dedicated producer thread (warp 14) streams the fp32 strip of every chunk
+  // (box 64 ch x cols x rows) into a two-slot staging ring; the converters transform smem -> smem.  This is what makes the
+  // fused operand pay off for layers with little MMA work per strip (ConvTranspose phases).  Single plain source, zero border.
+  int ht, ht_slot_bytes;
 };
 
 struct TileCoord {
@@ -189,6 +198,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t aready_bar[2];   // hs mode: operand strip buffer written (converter warps)
   __shared__ __align__(8) uint64_t afree_bar[2];    // hs mode: every MMA reading that strip buffer has retired
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(8) uint64_t sfull_bar[2];    // vt mode: staging slot filled by TMA
+  __shared__ __align__(8) uint64_t sempty_bar[2];   // vt mode: staging slot read by every converter warp
   __shared__ float2 st_x[4][32];               // per-epilogue-warp (sum, M2) of one 32-channel group, merged per tile
   __shared__ float st_n[4];
 
@@ -204,7 +215,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   const int kch0 = p.kchunks[0];
   const int strip_bytes = p.planes * p.hs_plane_bytes;              // one operand strip buffer (hs mode)
   const int bres_bytes = p.vs ? p.ntaps * kch0 * p.planes * b_bytes : (p.hs ? p.hs_nbuf * strip_bytes : 0);
-  uint8_t* const stage_base = smem + bres_bytes;                     // resident weights / operand strip first, then the stage ring
+  const int vt_slot_bytes = p.vt ? p.vt_half_rows * p.tile_w * 256 : (p.ht ? p.ht_slot_bytes : 0);   // fp32 staging slot
+  uint8_t* const vt_stage = smem + bres_bytes;                       // vt mode: two staging slots behind the resident weights
+  uint8_t* const stage_base = smem + bres_bytes + 2 * vt_slot_bytes; // resident weights / operand strip first, then the stage ring
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
 
@@ -219,7 +232,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     // a stage is full when the TMA bytes have landed (producer's expect_tx arrival) and, in fused-operand mode, every
     // converter warp has written its share of the A planes
     const uint32_t full_count = ((p.fa && p.vs) ? 0u : 1u) + ((p.fa && !p.hs) ? static_cast<uint32_t>(kConvWarps) : 0u);
-    for (int b = 0; b < 2; ++b) { mbar_init(&aready_bar[b], kConvWarps); mbar_init(&afree_bar[b], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&aready_bar[b], kConvWarps); mbar_init(&afree_bar[b], 1);
+      mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], kConvWarps);
+    }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     mbar_init(&bres_bar, 1);
@@ -263,6 +279,22 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             tma_load_3d(dst, &p.b_hi, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
             if (p.planes == 2) tma_load_3d(dst + b_bytes, &p.b_lo, &bres_bar, kc * kKC, 0, p.tap_w[tap]);
           }
+        if (p.vt) {
+          prefetch_tensormap(&p.a_f32);
+          uint32_t hn = 0;                                   // running half-strip number: slot hn & 1, phase (hn >> 1) & 1
+          for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+            for (int kc = 0; kc < kch0; ++kc)
+              for (int half = 0; half < 2; ++half, ++hn) {
+                const uint32_t slot = hn & 1u;
+                mbar_wait(&sempty_bar[slot], ((hn >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&sfull_bar[slot], static_cast<uint32_t>(vt_slot_bytes));
+                tma_load_4d(vt_stage + slot * vt_slot_bytes, &p.a_f32, &sfull_bar[slot], kc * kKC,
+                            tc.w0 + p.tap_off[0][1] - p.fa_border,
+                            tc.h0 + p.vs_dh_min - p.fa_border + half * p.vt_half_rows, tc.n0);
+              }
+          }
+        }
         if (!p.fa)
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           const TileCoord tc = decode_tile(p, t);
@@ -433,6 +465,22 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }
+  } else if (warp == 14) {
+    // ===================== fp32 source staging producer (ht mode) =====================
+    if (lane == 0 && p.ht) {
+      prefetch_tensormap(&p.a_f32);
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int kc = 0; kc < p.kchunks[0]; ++kc, ++g) {
+          const uint32_t slot = g & 1u;
+          mbar_wait(&sempty_bar[slot], ((g >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sfull_bar[slot], static_cast<uint32_t>(p.hs_rows * p.hs_cols * 256));
+          tma_load_4d(vt_stage + slot * vt_slot_bytes, &p.a_f32, &sfull_bar[slot], kc * kKC,
+                      tc.w0 + p.hs_dw_min - p.fa_border, tc.h0 + p.hs_dh_min - p.fa_border, tc.n0);
+        }
+      }
+    }
   } else if (warp < 6) {
     // ===================== epilogue: TMEM -> registers -> (+bias) -> fp32 NHWC =====================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
@@ -518,7 +566,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
-  } else if (p.fa) {
+  } else if (p.fa && warp < 14) {
     // ===================== operand converters (fused-operand mode) =====================
     // 256 threads; thread = (q: one float4 = 4 channels of the 64-channel chunk, pr: pixel row group).  A warp-wide
     // float4 load covers two pixels x 256 contiguous bytes; each thread writes 8 B of the hi and 8 B of the lo plane at
@@ -656,6 +704,40 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             }
             const float* const xo = xs + origin * C + cbase;          // only dereferenced when `inside`
             const float* const ro = rs != nullptr ? rs + origin * C + cbase : nullptr;
+            if (p.ht) {
+              // staged source: fp32 strip in shared memory ([pixel][64 ch], plain layout) -> transform -> swizzled strip
+              const uint32_t slot = g & 1u;
+              mbar_wait(&sfull_bar[slot], (g >> 1) & 1u);
+              mbar_wait_sleep(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
+              const uint8_t* stg = vt_stage + slot * vt_slot_bytes;
+#pragma unroll
+              for (int j = 0; j < kUnits; ++j) {
+                if (j >= nunits) continue;
+                const int px_i = (ct + 256 * j) >> 4;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                bool ok = inside;
+                if (!inside) {                                   // border tile: positions outside the source are zero padding
+                  const int row = px_i / p.hs_cols, col = px_i - row * p.hs_cols;
+                  const int hh = sh0 + row, ww = sw0 + col;
+                  ok = tc.n0 < p.N && hh >= 0 && hh < p.Hs && ww >= 0 && ww < p.Ws;
+                }
+                if (ok) {
+                  const float4 v = *reinterpret_cast<const float4*>(stg + static_cast<size_t>(px_i) * 256 + q * 16);
+                  o[0] = fa_act1(fmaf(v.x, sc.x, sh.x), act); o[1] = fa_act1(fmaf(v.y, sc.y, sh.y), act);
+                  o[2] = fa_act1(fmaf(v.z, sc.z, sh.z), act); o[3] = fa_act1(fmaf(v.w, sc.w, sh.w), act);
+                }
+                uint2 hi, lo;
+                fa_split4(o, p.fa_is_bf16, hi, lo);
+                *reinterpret_cast<uint2*>(strip_hi + soff[j]) = hi;
+                if (p.planes == 2) *reinterpret_cast<uint2*>(strip_lo + soff[j]) = lo;
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sempty_bar[slot]);   // this warp has read the staging slot
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&aready_bar[buf]);
+              continue;
+            }
             bool waited = false;
             // One latency wave per chunk when there is a single fp32 source (12 float4 in flight per thread), two waves of six
             // (value + residual) for the block's first conv: the loads are register-staged, so in-flight bytes are what the
@@ -722,6 +804,56 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&aready_bar[buf]);
           }
+        }
+      }
+    } else if (p.vt) {
+      // ---- vertical strip fed from the TMA staging ring: smem (fp32, plain layout [row][8 px][64 ch]) -> transform ->
+      // swizzled hi / lo strip.  A position outside the source is the conv's zero padding (the staged zeros must NOT go
+      // through act(0 * scale + shift)), so validity is recomputed from the coordinates.
+      uint32_t hn = 0;
+      const int half_px = p.vt_half_rows * p.tile_w;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int sw0 = tc.w0 + p.tap_off[0][1] - p.fa_border, sh0 = tc.h0 + p.vs_dh_min - p.fa_border;
+        for (int kc = 0; kc < kch0; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_hi = stage_base + static_cast<size_t>(s) * stage_bytes;
+          uint8_t* a_lo = a_hi + vs_a_bytes;
+          const int cbase = kc * kKC + q * 4;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.fa_scale[0] != nullptr && tc.n0 < p.N) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.fa_scale[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
+            sh = __ldg(reinterpret_cast<const float4*>(p.fa_shift[0] + static_cast<long long>(tc.n0) * p.fa_cin[0] + cbase));
+          }
+          for (int half = 0; half < 2; ++half, ++hn) {
+            const uint32_t slot = hn & 1u;
+            mbar_wait(&sfull_bar[slot], (hn >> 1) & 1u);
+            const uint8_t* st = vt_stage + slot * vt_slot_bytes;
+            const int rows_here = min(p.vt_half_rows, p.vs_rows - half * p.vt_half_rows);
+            const int npx_h = rows_here * p.tile_w;
+            for (int i = pr; i < npx_h; i += 16) {
+              const int row = half * p.vt_half_rows + (i >> 3), col = i & 7;
+              const int hh = sh0 + row, ww = sw0 + col;
+              float o[4] = {0.f, 0.f, 0.f, 0.f};
+              if (tc.n0 < p.N && hh >= 0 && hh < p.Hs && ww >= 0 && ww < p.Ws) {
+                const float4 v = *reinterpret_cast<const float4*>(st + static_cast<size_t>(i) * 256 + q * 16);
+                o[0] = fa_act1(fmaf(v.x, sc.x, sh.x), p.fa_act[0]); o[1] = fa_act1(fmaf(v.y, sc.y, sh.y), p.fa_act[0]);
+                o[2] = fa_act1(fmaf(v.z, sc.z, sh.z), p.fa_act[0]); o[3] = fa_act1(fmaf(v.w, sc.w, sh.w), p.fa_act[0]);
+              }
+              uint2 hi, lo;
+              fa_split4(o, p.fa_is_bf16, hi, lo);
+              const int idx = half * half_px + i;
+              const uint32_t off = static_cast<uint32_t>(idx) * 128u + (static_cast<uint32_t>(chunk ^ (idx & 7)) << 4) + sub;
+              *reinterpret_cast<uint2*>(a_hi + off) = hi;
+              if (p.planes == 2) *reinterpret_cast<uint2*>(a_lo + off) = lo;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty_bar[slot]);      // this warp has read the slot
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     } else
@@ -877,6 +1009,26 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// fp32 source staging map (fused-operand vertical-strip mode): no swizzle, zero OOB fill.
+static bool encode_f32_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(fp32) failed with CUresult %d (rank %d)", (int)r, rank);
+    set_error(buf);
+    return false;
+  }
+  return true;
+}
+
 bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
@@ -924,6 +1076,18 @@ static bool hs_eligible(const PhaseGeom& g, int split, int n_tile) {
   const int planes = split ? 2 : 1;
   const long long strip = static_cast<long long>(planes) * ((rows * cols * 128 + 1023) / 1024 * 1024);
   return strip + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem;       // one strip buffer + two weight stages at least
+}
+
+// Would a halo-strip phase fit the TMA staging ring (two fp32 slots) next to its strips and two weight stages?
+bool hs_staging_fits(const PhaseGeom& g, int split, int n_tile) {
+  int dh0 = g.tap_dh[0], dh1 = dh0, dw0 = g.tap_dw[0], dw1 = dw0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    dh0 = min(dh0, g.tap_dh[t]); dh1 = max(dh1, g.tap_dh[t]); dw0 = min(dw0, g.tap_dw[t]); dw1 = max(dw1, g.tap_dw[t]);
+  }
+  const int rows = 16 + dh1 - dh0, cols = 8 + dw1 - dw0, planes = split ? 2 : 1;
+  const long long plane = (rows * cols * 128 + 1023) / 1024 * 1024, slot = (rows * cols * 256 + 1023) / 1024 * 1024;
+  const long long nbuf = (2 * planes * plane + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem) ? 2 : 1;
+  return nbuf * planes * plane + 2 * slot + 2LL * planes * n_tile * 128 + 1024 <= kMaxDynSmem;
 }
 
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
@@ -1074,6 +1238,19 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
       // two strip buffers when they still leave room for two weight stages (the 256 -> 256 trunk conv: 2 x 46 KB + 2 x 64 KB)
       p.hs_nbuf = (2LL * p.planes * p.hs_plane_bytes + 2LL * p.planes * n_tile * 128 + 1024 <= kMaxDynSmem) ? 2 : 1;
+      // TMA staging of the fp32 source (ht) when it is a plain single source and two slots fit next to the strips and two
+      // weight stages
+      const int slot = (p.hs_rows * p.hs_cols * 256 + 1023) / 1024 * 1024;
+      if (ph.nsrc == 1 && ph.fa_res[0] == nullptr && ph.fa_out[0] == nullptr &&
+          (ph.fa_border == 0 || ph.fa_border_mode == DLB_PAD_ZERO) &&
+          static_cast<long long>(p.hs_nbuf) * p.planes * p.hs_plane_bytes + 2LL * slot + 2LL * p.planes * n_tile * 128 + 1024 <= kMaxDynSmem) {
+        const uint64_t C = ph.cin[0];
+        uint64_t dims[4] = {C, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)ph.N};
+        uint64_t strides[3] = {C * 4, (uint64_t)p.Ws * C * 4, (uint64_t)p.Hs * p.Ws * C * 4};
+        uint32_t box[4] = {(uint32_t)kKC, (uint32_t)p.hs_cols, (uint32_t)p.hs_rows, 1};
+        if (!encode_f32_map(&p.a_f32, ph.fa_x[0], 4, dims, strides, box)) return -1;
+        p.ht = 1; p.ht_slot_bytes = slot;
+      }
       for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - dh0) * p.hs_cols + (ph.tap_dw[t] - dw0)) * 128;
     }
   }
@@ -1104,8 +1281,25 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   }
 
   const int b_bytes = n_tile * 128;
-  const int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes
-                                : (use_hs ? p.hs_nbuf * p.planes * p.hs_plane_bytes : 0);
+  int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes
+                          : (use_hs ? p.hs_nbuf * p.planes * p.hs_plane_bytes : 0);
+  if (p.ht) bres_bytes += 2 * p.ht_slot_bytes;               // the staging ring sits between the strips and the weight stages
+  // vertical strip + plain fused source (no residual, zero border): feed the converters from a TMA staging ring
+  if (use_vs && ph.fa == 1 && ph.nsrc == 1 && ph.fa_res[0] == nullptr && ph.fa_out[0] == nullptr &&
+      (ph.fa_border == 0 || ph.fa_border_mode == DLB_PAD_ZERO) && ph.cin[0] % kKC == 0) {
+    const int half_rows = (p.vs_rows + 1) / 2;
+    const int slot = half_rows * tile_w * 256;
+    const int strip = p.planes * p.vs_rows * tile_w * 128;
+    if (bres_bytes + 2 * slot + 2 * strip + 1024 <= kMaxDynSmem) {
+      const uint64_t C = ph.cin[0];
+      uint64_t dims[4] = {C, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)ph.N};
+      uint64_t strides[3] = {C * 4, (uint64_t)p.Ws * C * 4, (uint64_t)p.Hs * p.Ws * C * 4};
+      uint32_t box[4] = {(uint32_t)kKC, (uint32_t)tile_w, (uint32_t)half_rows, 1};
+      if (!encode_f32_map(&p.a_f32, ph.fa_x[0], 4, dims, strides, box)) return -1;
+      p.vt = 1; p.vt_half_rows = half_rows;
+      bres_bytes += 2 * slot;                                  // the staging ring sits behind the resident weights
+    }
+  }
   const int stage_bytes = use_hs ? p.planes * b_bytes
                                  : (use_vs ? p.planes * p.vs_rows * tile_w * 128 + (ph.fa == 2 ? kStemPatchBytes : 0)
                                            : p.planes * (kABytes + b_bytes));

@@ -75,6 +75,8 @@ bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank,
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
                   int* tile_h, int* tile_n, int* n_tile_out, int fa = 0);
 
+bool hs_staging_fits(const PhaseGeom& g, int split, int n_tile);
+
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream);
 
 struct DirectPhase : PhaseGeom {

@@ -111,8 +111,10 @@ typedef struct dlb_fused_src {
  * dlb_norm_apply + dlb_conv_tc_fwd; every mode computes the same function):
  *   2  every phase in halo-strip mode AND enough tensor-core work per converted strip (taps x N) that the converter warps
  *      stay hidden behind the MMAs — the 256 -> 256 3x3 ResNet-block convolutions in split precision: use the fused call;
- *   3  halo-strip mode, but too little MMA work per strip (ConvTranspose phases, narrow layers, single-pass precision):
- *      the converters set the pace, the unfused pair is faster;
+ *   4  halo-strip mode with little MMA work per strip (ConvTranspose phases, narrow layers, single-pass precision) whose
+ *      fp32 source can be staged through shared memory by TMA: efficient for a PLAIN source (one K-source, no residual, no
+ *      write-back, no or zero border) — converters then read shared memory, not HBM; otherwise as 3;
+ *   3  the same without room for the staging ring: the converters set the pace, the unfused pair is faster;
  *   1  vertical-strip mode with resident weights (R x 1 filters: the head) — converter-bound as well;
  *   0  at least one phase would convert per tap (stride-2 layers, maps below 16 x 8): slowest. */
 int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_tile);

@@ -27,6 +27,22 @@ yd, cd = d.forward_train(rnd((1, 6, 64, 64), 5).cuda())
 gd, dxd = d.backward(cd, rnd(tuple(yd.shape), 6).cuda())
 sdr = nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 1, "instance", False, "reflect"), 6, "stress")
 yr = engine.ResnetEngine(sdr, n_blocks=1, norm="instance", padding_type="reflect").forward(x)
+# round 2: the fused-operand inference path — fused stem (patch staged in smem), halo-strip trunk convs with the skip add
+# and the fp32 write-back (zero and reflect borders), and, forced on, the vertical-strip head and ConvTranspose phases
+os.environ.update(DLB_FUSE_UP="1", DLB_FUSE_HEAD="1")
+for pad_t, sd_ in (("reflect", sdr), ("zero", nets.make_state_dict(nets.resnet_param_shapes(3, 3, 64, 2, "instance", False, "zero"), 7, "stress"))):
+    nb = 1 if pad_t == "reflect" else 2
+    yf = engine.ResnetEngine(sd_, n_blocks=nb, norm="instance", padding_type=pad_t, fused=True, fuse_residual=True).forward(rnd((2, 3, 64, 96), 11).cuda())
+    yn = engine.ResnetEngine(sd_, n_blocks=nb, norm="instance", padding_type=pad_t, fused=False).forward(rnd((2, 3, 64, 96), 11).cuda())
+    print("fused vs unfused", pad_t, float((yf - yn).abs().max()))
+# per-tap fused conversion (stride 2) and the dual-source halo strip (UNet up-convolution)
+xr = rnd((1, 32, 32, 128), 12).cuda(); xr2 = rnd((1, 32, 32, 128), 13).cuda()
+dd = ops.conv_desc(1, 32, 32, [128], 64, 4, 4, 2, 1, False, 0)
+wh, wl = ops.pack_weights_tc(dd, (rnd((64, 128, 4, 4), 14) * 0.05).cuda())
+ops.conv_tc_fused(dd, [dict(x=xr, act=ops.ACT_LRELU02)], wh, wl)
+du = ops.conv_desc(1, 32, 32, [128, 128], 64, 4, 4, 2, 1, True, 0)
+wh, wl = ops.pack_weights_tc(du, (rnd((256, 64, 4, 4), 15) * 0.05).cuda())
+ops.conv_tc_fused(du, [dict(x=xr, act=ops.ACT_RELU), dict(x=xr2, act=ops.ACT_RELU)], wh, wl)
 _, u8, mask = ops.seg_finish([yr], [1.0])
 t = ops.u8_to_f32(u8)
 # cell post-processing (union-find labelling, statistics, classification, boundaries)
