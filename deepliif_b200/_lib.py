@@ -36,6 +36,7 @@ SIGNATURES = {
     "dlb_pack_weights_tc": (_i, [_cd, _vp, _i, _vp, _vp, _vp]),
     "dlb_pack_weights_direct": (_i, [_cd, _vp, _vp, _vp]),
     "dlb_conv_tc_fwd": (_i, [_cd, _vpp, _vpp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dlb_conv_tc_launches": (_i, [_cd, _i, _i, _i]),
     "dlb_conv_tc_fused_mode": (_i, [_cd, _i, _i]),
     "dlb_conv_tc_fwd_fused": (_i, [_cd, C.POINTER(FusedSrc), _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dlb_conv_tc_fwd_stem": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),

@@ -144,6 +144,41 @@ extern "C" int dlb_release_thread_resources(void) {
 
 struct StemSrc { const float* x; int C, S, pad, pad_mode; };
 
+// Can the output-parity phases of this layer run as ONE launch with one TMEM accumulator per phase (halo-strip mode)?
+// On success fills the merged tap list / accumulator bases and returns the UMMA N to use; 0 otherwise.
+static int plan_merged(const dlb_conv_desc* d, const PhaseGeom* geo, int np, int split, int n_tile, int fa, TcPhase* out) {
+  // Measured (profiles/r02_*): merging pays when all output channels fit ONE 64-wide tile with four accumulators side by
+  // side (Cout <= 64: ResNet up1 0.55 -> 0.43 ms, UNet outermost 0.92 -> 0.73 ms); wider layers would need several channel
+  // tiles of narrow, shared-memory-bound N = 64 MMAs and lose (Cout 128: 0.31 -> 0.38 ms, Cout 256: 0.18 -> 0.42 ms).
+  if (np < 2 || np > 4 || d->Cout % 32 != 0 || d->Cout > 64) return 0;
+  int total_taps = 0;
+  for (int i = 0; i < np; ++i) {
+    if (geo[i].OH != geo[0].OH || geo[i].OW != geo[0].OW || geo[i].stride != 1) return 0;
+    total_taps += geo[i].ntaps;
+  }
+  if (total_taps > 16) return 0;
+  int nt_m = n_tile ? n_tile : (d->Cout >= 64 ? 64 : 32);
+  while (2 * np * nt_m > 512 && nt_m > 32) nt_m >>= 1;
+  if (2 * np * nt_m > 512) return 0;
+  TcPhase ph;
+  memset(&ph, 0, sizeof(ph));
+  static_cast<PhaseGeom&>(ph) = geo[0];
+  ph.ntaps = 0;
+  for (int i = 0; i < np; ++i) {
+    for (int t = 0; t < geo[i].ntaps; ++t) {
+      ph.tap_dh[ph.ntaps] = geo[i].tap_dh[t]; ph.tap_dw[ph.ntaps] = geo[i].tap_dw[t]; ph.tap_widx[ph.ntaps] = geo[i].tap_widx[t];
+      ph.tap_acc[ph.ntaps] = i;
+      ++ph.ntaps;
+    }
+    ph.acc_ybase[i] = geo[i].y_base;
+  }
+  ph.nacc = np;
+  int tw, th, tn, nt;
+  if (tc_plan_tiles(ph, d->nsrc, d->Cin, d->Cout, split, nt_m, &tw, &th, &tn, &nt, fa) != 2) return 0;
+  *out = ph;
+  return nt_m;
+}
+
 static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, const void* const* x_lo,
                             const dlb_fused_src* fsrc, const void* w_hi, const void* w_lo, const float* bias, float* y,
                             int fmt, int split, int n_tile, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream,
@@ -173,19 +208,59 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     }
     if (S_total > L.S_cap) return set_error("dlb_conv_tc_fwd: statistics workspace slice capacity exceeded");
   }
-  // The output-parity phases of a ConvTranspose2d (and of a stride-2 data gradient) are independent launches.  When one
+  cudaStream_t main_stream = reinterpret_cast<cudaStream_t>(stream);
+  auto fill_sources = [&](TcPhase& ph) -> int {
+    ph.nsrc = d->nsrc;
+    if (stem != nullptr) {
+      ph.fa = 2; ph.fa_x[0] = stem->x; ph.stem_C = stem->C; ph.stem_S = stem->S; ph.stem_pad = stem->pad;
+      ph.fa_border = 0; ph.fa_border_mode = stem->pad_mode; ph.fa_act[0] = DLB_ACT_NONE;
+    }
+    for (int s = 0; s < d->nsrc; ++s) {
+      ph.cin[s] = d->Cin[s];
+      if (stem != nullptr) continue;
+      if (fsrc == nullptr) { ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; continue; }
+      ph.fa = 1;
+      ph.fa_x[s] = fsrc[s].x; ph.fa_scale[s] = fsrc[s].scale; ph.fa_shift[s] = fsrc[s].shift; ph.fa_res[s] = fsrc[s].residual;
+      ph.fa_out[s] = fsrc[s].out; ph.fa_act[s] = fsrc[s].act;
+      ph.fa_border = fsrc[0].border; ph.fa_border_mode = fsrc[0].border_mode;
+      if (fsrc[s].border != fsrc[0].border || fsrc[s].border_mode != fsrc[0].border_mode)
+        return set_error("dlb_conv_tc_fwd_fused: every source needs the same border");
+      if (fsrc[s].act != DLB_ACT_NONE && fsrc[s].act != DLB_ACT_RELU && fsrc[s].act != DLB_ACT_LRELU02)
+        return set_error("dlb_conv_tc_fwd_fused: act must be none / relu / lrelu0.2");
+    }
+    ph.w_hi = w_hi; ph.w_lo = split ? w_lo : nullptr; ph.bias = bias; ph.y = y;
+    ph.fmt = fmt; ph.split = split ? 1 : 0;
+    return 0;
+  };
+  // ---- merged output-parity phases: the phases of a stride-2 ConvTranspose2d (and of a stride-2 data gradient) read the
+  // same input; one launch loads (or converts) each input strip once and accumulates every phase in its own TMEM
+  // accumulator, instead of one launch per phase each re-reading its shifted input through L2 ----
+  {
+    TcPhase ph;
+    const int nt_m = plan_merged(d, geo, np, split, n_tile, fsrc != nullptr || stem != nullptr, &ph);
+    if (nt_m > 0) {
+      if (fill_sources(ph) != 0) return DLB_ERR_INVALID;
+      ph.n_tile = nt_m;
+      if (stats_ws != nullptr) {
+        const int tiles = ((ph.OH + 15) / 16) * ((ph.OW + 7) / 8);          // halo-strip tiles: 16 x 8 output pixels
+        if (np * tiles > sp.S_cap) return set_error("dlb_conv_tc_fwd: statistics workspace slice capacity exceeded");
+        ph.st_partial = sp.partial; ph.st_cnt = sp.cnt; ph.st_S = sp.S; ph.st_S_cap = sp.S_cap;
+        for (int i = 0; i < np; ++i) ph.acc_slice[i] = i * tiles;
+        ph.st_slice_base = 0; ph.st_S_total = np * tiles;
+      }
+      return launch_conv_tc_phase(ph, main_stream);
+    }
+  }
+  // The output-parity phases of a ConvTranspose2d (and of a stride-2 data gradient) are otherwise independent launches.  When one
   // phase cannot fill the GPU (inner UNet levels: a few CTAs streaming megabytes of weights, latency-bound), the
   // phases run side by side on helper streams forked from and joined back into the caller's stream (plain event
   // fork/join: also valid inside a stream capture).
-  cudaStream_t main_stream = reinterpret_cast<cudaStream_t>(stream);
   bool fork = false;
   if (np > 1) {
     int nt_eff = n_tile ? n_tile : (d->Cout >= 256 ? 256 : (d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32)));
     const long long m_tiles = (static_cast<long long>(d->N) * geo[0].OH * geo[0].OW + 127) / 128;
     fork = m_tiles * ((d->Cout + nt_eff - 1) / nt_eff) < 74;
   }
-  // helper streams / events: created lazily, once per (host thread, device) — the one exception to "no entry point
-  // allocates"; dlb_release_thread_resources() destroys the calling thread's
   ForkRes unused;
   ForkRes* fr = &unused;
   if (fork) {
@@ -213,26 +288,8 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     TcPhase ph;
     memset(&ph, 0, sizeof(ph));
     static_cast<PhaseGeom&>(ph) = geo[i];
-    ph.nsrc = d->nsrc;
-    if (stem != nullptr) {
-      ph.fa = 2; ph.fa_x[0] = stem->x; ph.stem_C = stem->C; ph.stem_S = stem->S; ph.stem_pad = stem->pad;
-      ph.fa_border = 0; ph.fa_border_mode = stem->pad_mode; ph.fa_act[0] = DLB_ACT_NONE;
-    }
-    for (int s = 0; s < d->nsrc; ++s) {
-      ph.cin[s] = d->Cin[s];
-      if (stem != nullptr) continue;
-      if (fsrc == nullptr) { ph.x_hi[s] = x_hi[s]; ph.x_lo[s] = split ? x_lo[s] : nullptr; continue; }
-      ph.fa = 1;
-      ph.fa_x[s] = fsrc[s].x; ph.fa_scale[s] = fsrc[s].scale; ph.fa_shift[s] = fsrc[s].shift; ph.fa_res[s] = fsrc[s].residual;
-      ph.fa_out[s] = fsrc[s].out; ph.fa_act[s] = fsrc[s].act;
-      ph.fa_border = fsrc[0].border; ph.fa_border_mode = fsrc[0].border_mode;
-      if (fsrc[s].border != fsrc[0].border || fsrc[s].border_mode != fsrc[0].border_mode)
-        return set_error("dlb_conv_tc_fwd_fused: every source needs the same border");
-      if (fsrc[s].act != DLB_ACT_NONE && fsrc[s].act != DLB_ACT_RELU && fsrc[s].act != DLB_ACT_LRELU02)
-        return set_error("dlb_conv_tc_fwd_fused: act must be none / relu / lrelu0.2");
-    }
-    ph.w_hi = w_hi; ph.w_lo = split ? w_lo : nullptr; ph.bias = bias; ph.y = y;
-    ph.fmt = fmt; ph.split = split ? 1 : 0; ph.n_tile = n_tile;
+    if (fill_sources(ph) != 0) return DLB_ERR_INVALID;
+    ph.n_tile = n_tile;
     if (stats_ws != nullptr) {
       ph.st_partial = sp.partial; ph.st_cnt = sp.cnt; ph.st_S = sp.S; ph.st_S_cap = sp.S_cap;
       ph.st_slice_base = slice_base[i]; ph.st_S_total = S_total;
@@ -247,6 +304,17 @@ static int conv_tc_fwd_impl(const dlb_conv_desc* d, const void* const* x_hi, con
     }
   }
   return 0;
+}
+
+extern "C" int dlb_conv_tc_launches(const dlb_conv_desc* d, int split, int n_tile, int fused) {
+  int OH, OW;
+  if (out_shape(d, &OH, &OW) != 0) return DLB_ERR_INVALID;
+  PhaseGeom geo[4];
+  const long long C = d->Cout;
+  const int np = build_phases(d, OH, OW, static_cast<long long>(OH) * OW * C, static_cast<long long>(OW) * C, C, geo);
+  if (np < 0) return np;
+  TcPhase ph;
+  return plan_merged(d, geo, np, split, n_tile, fused, &ph) > 0 ? 1 : np;
 }
 
 extern "C" int dlb_conv_tc_fused_mode(const dlb_conv_desc* d, int split, int n_tile) {

@@ -113,6 +113,17 @@ struct alignas(64) TcParams {
   // (box 64 ch x cols x rows) into a two-slot staging ring; the converters transform smem -> smem.  This is what makes the
   // fused operand pay off for layers with little MMA work per strip (ConvTranspose phases).  Single plain source, zero border.
   int ht, ht_slot_bytes;
+  // hp: halo strips loaded by TMA straight from the operand planes (unfused operands: the box (64 ch, cols, rows) of a
+  // 128B-swizzled tensor map lands in exactly the strip layout) — each input value crosses L2 -> SM once per tile, not once
+  // per tap.
+  int hp;
+  // Merged output-parity phases of a ConvTranspose2d: the phases share the input strip; tap t accumulates into TMEM
+  // accumulator tap_acc[t] (nacc x n_tile columns per set) and the epilogue writes accumulator a at output offset acc_ybase[a]
+  // with statistics slice base acc_slice[a].
+  int nacc;
+  int tap_acc[kMaxTaps];
+  long long acc_ybase[4];
+  int acc_slice[4];
 };
 
 struct TileCoord {
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
-  __shared__ __align__(8) uint64_t aready_bar[2];   // hs mode: operand strip buffer written (converter warps)
-  __shared__ __align__(8) uint64_t afree_bar[2];    // hs mode: every MMA reading that strip buffer has retired
+  __shared__ __align__(8) uint64_t aready_bar[4];   // hs mode: operand strip buffer written (converter warps / TMA)
+  __shared__ __align__(8) uint64_t afree_bar[4];    // hs mode: every MMA reading that strip buffer has retired
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(8) uint64_t sfull_bar[2];    // vt mode: staging slot filled by TMA
   __shared__ __align__(8) uint64_t sempty_bar[2];   // vt mode: staging slot read by every converter warp
@@ -219,7 +230,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
   uint8_t* const vt_stage = smem + bres_bytes;                       // vt mode: two staging slots behind the resident weights
   uint8_t* const stage_base = smem + bres_bytes + 2 * vt_slot_bytes; // resident weights / operand strip first, then the stage ring
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
-  const uint32_t tmem_cols = 2u * p.n_tile;   // 128 / 256 / 512: power of two >= 32
+  const uint32_t acc_cols = static_cast<uint32_t>(p.nacc * p.n_tile);    // one accumulator set
+  uint32_t tmem_cols = 32;                                               // two sets, rounded up to a power of two >= 32
+  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsrc && !p.fa; ++s) {
@@ -232,10 +245,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     // a stage is full when the TMA bytes have landed (producer's expect_tx arrival) and, in fused-operand mode, every
     // converter warp has written its share of the A planes
     const uint32_t full_count = ((p.fa && p.vs) ? 0u : 1u) + ((p.fa && !p.hs) ? static_cast<uint32_t>(kConvWarps) : 0u);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&aready_bar[b], kConvWarps); mbar_init(&afree_bar[b], 1);
-      mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], kConvWarps);
-    }
+    for (int b = 0; b < 4; ++b) { mbar_init(&aready_bar[b], p.hp ? 1 : kConvWarps); mbar_init(&afree_bar[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], kConvWarps); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     mbar_init(&bres_bar, 1);
@@ -256,10 +267,22 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       int s = 0; uint32_t ph = 0;
       if (p.hs) {
         // weights only: one (chunk, tap) tile per stage, chunk-major so the strip of a chunk serves all its taps
+        uint32_t g = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           const TileCoord tc = decode_tile(p, t);
           for (int src = 0; src < p.nsrc; ++src)
-            for (int kc = 0; kc < p.kchunks[src]; ++kc)
+            for (int kc = 0; kc < p.kchunks[src]; ++kc, ++g) {
+              if (p.hp) {
+                // the chunk's operand strip: one TMA box per plane, zero padding = out-of-bounds fill
+                const uint32_t buf = g % static_cast<uint32_t>(p.hs_nbuf);
+                mbar_wait(&afree_bar[buf], ((g / static_cast<uint32_t>(p.hs_nbuf)) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&aready_bar[buf], static_cast<uint32_t>(p.planes * p.hs_rows * p.hs_cols * 128));
+                uint8_t* st = smem + static_cast<size_t>(buf) * strip_bytes;
+                tma_load_5d(st, &p.a_hi[src], &aready_bar[buf], kc * kKC, tc.w0 + p.hs_dw_min, tc.h0 + p.hs_dh_min, tc.n0, 0);
+                if (p.planes == 2)
+                  tma_load_5d(st + p.hs_plane_bytes, &p.a_lo[src], &aready_bar[buf], kc * kKC, tc.w0 + p.hs_dw_min,
+                              tc.h0 + p.hs_dh_min, tc.n0, 0);
+              }
               for (int tap = 0; tap < p.ntaps; ++tap) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
@@ -269,6 +292,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
                 if (p.planes == 2) tma_load_3d(sb + b_bytes, &p.b_lo, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
               }
+            }
         }
       } else if (p.vs) {
         // resident weights: every tap / channel chunk / plane once per CTA
@@ -352,8 +376,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-          uint32_t accumulate = 0;
+          const uint32_t d_set = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
+          uint32_t started = 0;                          // bit a: accumulator a has received its first MMA of this tile
           const int nchunks = p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0);
           for (int ch = 0; ch < nchunks; ++ch, ++g) {
             const uint32_t buf = g % static_cast<uint32_t>(p.hs_nbuf);
@@ -367,6 +391,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
               const uint32_t aoff = static_cast<uint32_t>(p.hs_off[tap]);
               const uint32_t b_hi = smem_u32(stage_base + static_cast<size_t>(s) * stage_bytes);
               const uint32_t b_lo = b_hi + b_bytes;
+              const int a_i = p.tap_acc[tap];
+              const uint32_t d_tmem = d_set + static_cast<uint32_t>(a_i * p.n_tile);
+              uint32_t accumulate = (started >> a_i) & 1u;
+              started |= 1u << a_i;
 #pragma unroll
               for (int k = 0; k < kKC / 16; ++k) {
                 const uint64_t da_hi = make_sw128_kmajor_desc_sbo(strip_hi + aoff + k * 32, sbo);
@@ -397,7 +425,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
           uint32_t accumulate = 0;
           for (int kc = 0; kc < kch0; ++kc) {
             mbar_wait(&full_bar[s], ph);
@@ -434,7 +462,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
         uint32_t accumulate = 0;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[s], ph);                // TMA bytes have landed
@@ -493,16 +521,20 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       const TileCoord tc = decode_tile(p, t);
       const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
       const bool valid = (n < p.N) && (h < p.OH) && (w < p.OW);
-      float* yp = p.y + p.y_base + n * p.ys_n + h * p.ys_h + w * p.ys_w + tc.cout0;
+      float* const yp0 = p.y + n * p.ys_n + h * p.ys_h + w * p.ys_w + tc.cout0;
       mbar_wait_sleep(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       // slice of the statistics workspace this warp's 32 rows belong to (tile_n == 1 when stats are fused)
       const int th_i = tc.h0 / p.tile_h, tw_i = tc.w0 / p.tile_w;
+      for (int ai = 0; ai < p.nacc; ++ai) {                // merged ConvTranspose phases: one accumulator per output parity
+      float* const yp = yp0 + (p.nacc > 1 ? p.acc_ybase[ai] : p.y_base);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * acc_cols +
+                             static_cast<uint32_t>(ai * p.n_tile);
       // one statistics slice per CTA tile (tile_n == 1: the tile lies in image tc.n0); the four epilogue warps merge their
       // 32-pixel partials in shared memory before anything is written
-      const long long st_row = static_cast<long long>(tc.n0) * p.st_S_cap + p.st_slice_base + (th_i * p.tiles_w + tw_i);
+      const long long st_row = static_cast<long long>(tc.n0) * p.st_S_cap + (p.nacc > 1 ? p.acc_slice[ai] : p.st_slice_base) +
+                               (th_i * p.tiles_w + tw_i);
       for (int c = 0; c < p.n_tile; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
@@ -560,6 +592,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");            // st_x is reused by the next channel group
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -1091,7 +1124,7 @@ bool hs_staging_fits(const PhaseGeom& g, int split, int n_tile) {
 }
 
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
-                  int* tile_h, int* tile_n, int* n_tile_out, int fa) {
+                  int* tile_h, int* tile_n, int* n_tile_out, int fa, int allow_hp) {
   int n_tile = n_tile_req;
   if (n_tile == 0) n_tile = auto_n_tile(cout, static_cast<long long>(g.N) * g.OH * g.OW);
   *n_tile_out = n_tile;
@@ -1113,8 +1146,9 @@ int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int sp
     if (resident + 2 * strip + 1024 > kMaxDynSmem) vs = false;
   }
   if (vs) { *tile_w = 8; *tile_h = 16; *tile_n = 1; return 1; }
-  // ---- halo strip (fused-operand mode only): any stride-1 tap set whose strip fits ----
-  if (fa && hs_eligible(g, split, n_tile)) { *tile_w = 8; *tile_h = 16; *tile_n = 1; return 2; }
+  // ---- halo strip: any stride-1 tap set whose strip fits.  Fused operands: built by the converter warps; plane operands
+  // (hp): loaded by TMA, worthwhile from two taps on (one tap = the strip is the tile) ----
+  if ((fa || (allow_hp && g.ntaps >= 2)) && hs_eligible(g, split, n_tile)) { *tile_w = 8; *tile_h = 16; *tile_n = 1; return 2; }
   return 0;
 }
 
@@ -1151,8 +1185,19 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   // ---- tile shape: 128 output pixels = tile_n x tile_h x tile_w ---------------------------------
   int tile_w, tile_h, tile_n, n_tile_plan;
   const int mode = ph.no_vs ? (tc_plan_tiles_novs(ph, &tile_w, &tile_h, &tile_n, &n_tile_plan), 0)
-                           : tc_plan_tiles(ph, ph.nsrc, ph.cin, ph.cout, ph.split, ph.n_tile, &tile_w, &tile_h, &tile_n, &n_tile_plan, ph.fa);
+                           : tc_plan_tiles(ph, ph.nsrc, ph.cin, ph.cout, ph.split, ph.n_tile, &tile_w, &tile_h, &tile_n, &n_tile_plan, ph.fa,
+                                           !ph.no_hs);
   const int use_vs = mode == 1, use_hs = mode == 2;
+  // halo-strip extents (needed by the plane tensor maps below)
+  int hs_dh0 = ph.tap_dh[0], hs_dh1 = hs_dh0, hs_dw0 = ph.tap_dw[0], hs_dw1 = hs_dw0;
+  for (int t = 0; t < ph.ntaps; ++t) {
+    hs_dh0 = min(hs_dh0, ph.tap_dh[t]); hs_dh1 = max(hs_dh1, ph.tap_dh[t]);
+    hs_dw0 = min(hs_dw0, ph.tap_dw[t]); hs_dw1 = max(hs_dw1, ph.tap_dw[t]);
+  }
+  p.nacc = ph.nacc > 1 ? ph.nacc : 1;
+  if (p.nacc > 1 && !use_hs) return set_error("conv_tc: merged phases need the halo-strip mode");
+  for (int t = 0; t < ph.ntaps; ++t) p.tap_acc[t] = p.nacc > 1 ? ph.tap_acc[t] : 0;
+  for (int a = 0; a < 4; ++a) { p.acc_ybase[a] = ph.acc_ybase[a]; p.acc_slice[a] = ph.acc_slice[a]; }
   p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n;
   p.tiles_w = (ph.OW + tile_w - 1) / tile_w;
   p.tiles_h = (ph.OH + tile_h - 1) / tile_h;
@@ -1165,6 +1210,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   p.N = ph.N; p.OH = ph.OH; p.OW = ph.OW; p.cout_total = ph.cout;
   p.ys_n = ph.ys_n; p.ys_h = ph.ys_h; p.ys_w = ph.ys_w; p.y_base = ph.y_base;
   p.y = ph.y; p.bias = ph.bias;
+  if (2 * p.nacc * n_tile > 512) return set_error("conv_tc: merged phases need 2 * nacc * n_tile <= 512 TMEM columns");
   p.idesc = make_idesc_f16(128, n_tile, is_bf16);
   p.st_partial = ph.st_partial; p.st_cnt = ph.st_cnt; p.st_S = ph.st_S;
   p.st_S_cap = ph.st_S_cap; p.st_slice_base = ph.st_slice_base; p.st_S_total = ph.st_S_total;
@@ -1185,6 +1231,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
         for (int t = 0; t < ph.ntaps; ++t) p.vs_row_off[t] = ph.tap_dh[t] - dmin;
         box[2] = p.vs_rows;
       }
+      if (use_hs && !ph.fa) { box[1] = tile_w + hs_dw1 - hs_dw0; box[2] = tile_h + hs_dh1 - hs_dh0; box[3] = 1; }
       p.dim_sel[0] = 0; p.dim_sel[1] = 1; p.dim_sel[2] = 2; p.dim_sel[3] = 3; p.dim_sel[4] = 4;
     } else {
       if ((W & 1) || (H & 1)) return set_error("conv_tc: stride-2 needs even H and W");
@@ -1230,10 +1277,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     if (any_out && (use_vs || p.fa_wb_tap < 0 || ph.OH != p.Hs || ph.OW != p.Ws))
       return set_error("conv_tc: operand write-back needs a stride-1 'same' convolution in tap / halo-strip mode");
     if (use_hs) {
-      int dh0 = ph.tap_dh[0], dh1 = dh0, dw0 = ph.tap_dw[0], dw1 = dw0;
-      for (int t = 0; t < ph.ntaps; ++t) {
-        dh0 = min(dh0, ph.tap_dh[t]); dh1 = max(dh1, ph.tap_dh[t]); dw0 = min(dw0, ph.tap_dw[t]); dw1 = max(dw1, ph.tap_dw[t]);
-      }
+      const int dh0 = hs_dh0, dh1 = hs_dh1, dw0 = hs_dw0, dw1 = hs_dw1;
       p.hs = 1; p.hs_rows = tile_h + dh1 - dh0; p.hs_cols = tile_w + dw1 - dw0; p.hs_dh_min = dh0; p.hs_dw_min = dw0;
       p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
       // two strip buffers when they still leave room for two weight stages (the 256 -> 256 trunk conv: 2 x 46 KB + 2 x 64 KB)
@@ -1253,6 +1297,21 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       }
       for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - dh0) * p.hs_cols + (ph.tap_dw[t] - dw0)) * 128;
     }
+  }
+  if (use_hs && !ph.fa) {
+    // plane-fed halo strips: the strip of a chunk is one TMA box per plane (tensor maps above)
+    p.hs = 1; p.hp = 1;
+    p.hs_rows = tile_h + hs_dh1 - hs_dh0; p.hs_cols = tile_w + hs_dw1 - hs_dw0; p.hs_dh_min = hs_dh0; p.hs_dw_min = hs_dw0;
+    p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
+    // strip buffers: as many as fit (up to 4) while at least 4 weight stages remain — a strip load has ~1-2 us of TMA latency
+    // and a narrow layer spends no more than that on a chunk's MMAs, so two buffers are not enough to stay ahead
+    p.hs_nbuf = 1;
+    for (int nb = 2; nb <= 4; ++nb) {
+      const long long need = static_cast<long long>(nb) * p.planes * p.hs_plane_bytes +
+                             (nb == 2 ? 2LL : 4LL) * p.planes * n_tile * 128 + 1024;
+      if (need <= kMaxDynSmem) p.hs_nbuf = nb;
+    }
+    for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - hs_dh0) * p.hs_cols + (ph.tap_dw[t] - hs_dw0)) * 128;
   }
   // ---- weight tensor map: [taps_total][Cout][Cin_total] ---------------------------------------------
   {

@@ -48,6 +48,13 @@ struct TcPhase : PhaseGeom {
   int max_stages;              // 0 = as many as fit
   int max_ctas;                // 0 = #SMs
   int no_vs;                   // 1 = never use the vertical-strip mode (A/B testing)
+  int no_hs;                   // 1 = never use the plane-fed halo-strip mode (A/B testing)
+  // merged output-parity phases of a ConvTranspose2d (nacc > 1): tap t accumulates into accumulator tap_acc[t]; accumulator a
+  // is written at output base acc_ybase[a] with statistics slice base acc_slice[a].  nacc = 0 / 1: a single accumulator.
+  int nacc;
+  int tap_acc[64];
+  long long acc_ybase[4];
+  int acc_slice[4];
   // fused normalisation statistics (see stats_ws.h); st_partial == nullptr disables
   float2* st_partial;
   float* st_cnt;
@@ -73,7 +80,7 @@ bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank,
 
 // Returns the phase's execution mode: 0 tap mode, 1 vertical strip (resident weights), 2 halo strip (fa only).
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
-                  int* tile_h, int* tile_n, int* n_tile_out, int fa = 0);
+                  int* tile_h, int* tile_n, int* n_tile_out, int fa = 0, int allow_hp = 1);
 
 bool hs_staging_fits(const PhaseGeom& g, int split, int n_tile);
 

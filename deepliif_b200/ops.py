@@ -107,7 +107,7 @@ def conv_tc(d, xs_hi, xs_lo, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_
                                       _p(out), fmt, int(split), n_tile, _p(stats_ws),
                                       stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
           "dlb_conv_tc_fwd")
-    LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    LAUNCHES["count"] += _lib.load().dlb_conv_tc_launches(C.byref(d), int(split), n_tile, 0) if d.transposed else 1
     return out
 
 
@@ -142,7 +142,7 @@ def conv_tc_fused(d, srcs, w_hi, w_lo, bias=None, fmt=FMT_BF16, split=True, n_ti
                                             int(split), n_tile, _p(stats_ws),
                                             stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()),
           "dlb_conv_tc_fwd_fused")
-    LAUNCHES["count"] += (d.stride * d.stride if d.transposed else 1)
+    LAUNCHES["count"] += _lib.load().dlb_conv_tc_launches(C.byref(d), int(split), n_tile, 1) if d.transposed else 1
     return out
 
 

@@ -107,6 +107,9 @@ typedef struct dlb_fused_src {
   int border;
   int border_mode;
 } dlb_fused_src;
+/* Number of kernel launches dlb_conv_tc_fwd / dlb_conv_tc_fwd_fused make for this layer: 1 for a Conv2d and for a
+ * ConvTranspose2d whose output-parity phases run merged (one input strip, one TMEM accumulator per phase), stride^2 otherwise. */
+int dlb_conv_tc_launches(const dlb_conv_desc* d, int split, int n_tile, int fused);
 /* How dlb_conv_tc_fwd_fused would run this layer (callers use it to choose between the fused call and
  * dlb_norm_apply + dlb_conv_tc_fwd; every mode computes the same function):
  *   2  every phase in halo-strip mode AND enough tensor-core work per converted strip (taps x N) that the converter warps
