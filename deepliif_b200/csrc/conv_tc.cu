@@ -27,6 +27,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "internal.h"
@@ -117,6 +119,10 @@ struct alignas(64) TcParams {
   // 128B-swizzled tensor map lands in exactly the strip layout) — each input value crosses L2 -> SM once per tile, not once
   // per tap.
   int hp;
+  // cta2: CTA pair (cluster of 2, cta_group::2).  The two CTAs work on consecutive pixel tiles with the same output channels;
+  // ONE M = 256 MMA (issued by the even CTA) multiplies both strips with a weight tile of which each CTA holds half the rows,
+  // so every SM loads, stores in shared memory and feeds to the tensor core only half of B.
+  int cta2;
   // Merged output-parity phases of a ConvTranspose2d: the phases share the input strip; tap t accumulates into TMEM
   // accumulator tap_acc[t] (nacc x n_tile columns per set) and the epilogue writes accumulator a at output offset acc_ybase[a]
   // with statistics slice base acc_slice[a].
@@ -199,7 +205,10 @@ __device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
   return a[0];
 }
 
-__global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// CTA2 = true: the CTA-pair instance (launched as clusters of two; contains the cta_group::2 instructions, which make a kernel
+// cluster-only — a plain launch of it fails with "cluster misconfiguration", hence two instances).
+template <bool CTA2>
+__global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -219,7 +228,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b_bytes = p.n_tile * 128;
+  uint32_t crank = 0u;                                          // 0 = leader (issues the MMAs), 1 = follower
+  if constexpr (CTA2) crank = cluster_ctarank();
+  const int b_bytes = (CTA2 ? p.n_tile / 2 : p.n_tile) * 128; // rows of the weight tile THIS CTA holds
   const int vs_a_bytes = p.vs_rows * p.tile_w * 128;                 // one plane of an A strip (vs mode)
   const int stage_bytes = p.hs ? p.planes * b_bytes
                                : (p.vs ? p.planes * vs_a_bytes + (p.fa == 2 ? kStemPatchBytes : 0) : p.planes * (kABytes + b_bytes));
@@ -245,19 +256,23 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     // a stage is full when the TMA bytes have landed (producer's expect_tx arrival) and, in fused-operand mode, every
     // converter warp has written its share of the A planes
     const uint32_t full_count = ((p.fa && p.vs) ? 0u : 1u) + ((p.fa && !p.hs) ? static_cast<uint32_t>(kConvWarps) : 0u);
-    for (int b = 0; b < 4; ++b) { mbar_init(&aready_bar[b], p.hp ? 1 : kConvWarps); mbar_init(&afree_bar[b], 1); }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&aready_bar[b], p.hp ? 1 : (CTA2 ? 2 * kConvWarps : kConvWarps));   // cta2: both CTAs' converters arrive on the leader's
+      mbar_init(&afree_bar[b], 1);
+    }
     for (int b = 0; b < 2; ++b) { mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], kConvWarps); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], CTA2 ? 8 : 4); }
     mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_smem, tmem_cols);
-    tmem_relinquish();
+    if constexpr (CTA2) { tmem_alloc_2sm(&tmem_base_smem, tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();       // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       if (p.hs) {
         // weights only: one (chunk, tap) tile per stage, chunk-major so the strip of a chunk serves all its taps
         uint32_t g = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t - static_cast<int>(crank) < total_tiles; t += gridDim.x) {
           const TileCoord tc = decode_tile(p, t);
           for (int src = 0; src < p.nsrc; ++src)
             for (int kc = 0; kc < p.kchunks[src]; ++kc, ++g) {
@@ -285,11 +300,21 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
               }
               for (int tap = 0; tap < p.ntaps; ++tap) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
                 uint8_t* sb = stage_base + static_cast<size_t>(s) * stage_bytes;
                 const int kw = p.src_koff[src] + kc * kKC;
-                tma_load_3d(sb, &p.b_hi, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
-                if (p.planes == 2) tma_load_3d(sb + b_bytes, &p.b_lo, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+                if constexpr (CTA2) {
+                  // each CTA loads its half of the weight rows into its own stage; both halves complete on the LEADER's barrier
+                  if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+                  // (one channel tile only in this mode: the pair's weight rows are [0, n_tile), also when the follower's own
+                  // tile index lies past the end of an odd tile count)
+                  const int co = static_cast<int>(crank) * (p.n_tile / 2);
+                  tma_load_3d_2sm(sb, &p.b_hi, &full_bar[s], kw, co, p.tap_w[tap]);
+                  if (p.planes == 2) tma_load_3d_2sm(sb + b_bytes, &p.b_lo, &full_bar[s], kw, co, p.tap_w[tap]);
+                } else {
+                  mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+                  tma_load_3d(sb, &p.b_hi, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+                  if (p.planes == 2) tma_load_3d(sb + b_bytes, &p.b_lo, &full_bar[s], kw, tc.cout0, p.tap_w[tap]);
+                }
                 if (++s == p.stages) { s = 0; ph ^= 1; }
               }
             }
@@ -370,7 +395,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
-      if (p.hs) {
+      if (p.hs && crank != 0) {
+        // follower of a CTA pair: the leader issues the MMAs for both
+      } else if (p.hs) {
         const uint32_t sbo = static_cast<uint32_t>(p.hs_cols) * 128u;
         uint32_t g = 0;                                  // running chunk number: strip buffer g % nbuf, phase (g / nbuf) & 1
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -399,7 +426,19 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
               for (int k = 0; k < kKC / 16; ++k) {
                 const uint64_t da_hi = make_sw128_kmajor_desc_sbo(strip_hi + aoff + k * 32, sbo);
                 const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
-                if (p.planes == 2) {
+                if constexpr (CTA2) {
+                  // M = 256 across the pair: the hardware takes rows 0-127 of A (and of B) from this CTA's shared memory and
+                  // rows 128-255 from the same offsets in the peer's
+                  if (p.planes == 2) {
+                    const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
+                    const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
+                    umma_f16_2sm(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                    umma_f16_2sm(d_tmem, da_hi, db_lo, p.idesc, 1);
+                    umma_f16_2sm(d_tmem, da_hi, db_hi, p.idesc, 1);
+                  } else {
+                    umma_f16_2sm(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                  }
+                } else if (p.planes == 2) {
                   const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
                   const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
                   umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);
@@ -410,12 +449,12 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
                 }
                 accumulate = 1;
               }
-              umma_commit(&empty_bar[s]);
+              if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
               if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            umma_commit(&afree_bar[buf]);               // strip buffer may be overwritten once these MMAs retire
+            if constexpr (CTA2) umma_commit_2sm(&afree_bar[buf]); else umma_commit(&afree_bar[buf]);   // strip buffer reusable once these MMAs retire
           }
-          umma_commit(&tfull_bar[acc]);
+          if constexpr (CTA2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
           acc ^= 1; if (acc == 0) acc_ph ^= 1;
         }
       } else if (p.vs) {
@@ -517,10 +556,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
     const int w_l = m % p.tile_w;
     const int h_l = (m / p.tile_w) % p.tile_h;
     const int n_l = m / (p.tile_w * p.tile_h);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t - static_cast<int>(crank) < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
-      const bool valid = (n < p.N) && (h < p.OH) && (w < p.OW);
+      const bool valid = (t < total_tiles) && (n < p.N) && (h < p.OH) && (w < p.OW);
       float* const yp0 = p.y + n * p.ys_n + h * p.ys_h + w * p.ys_w + tc.cout0;
       mbar_wait_sleep(&tfull_bar[acc], acc_ph);
       tc_fence_after();
@@ -539,7 +578,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
-        const bool cvalid = (tc.cout0 + c) < p.cout_total;
+        const bool cvalid = (t < total_tiles) && (tc.cout0 + c) < p.cout_total;
         if (p.bias != nullptr && cvalid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -596,7 +635,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) { if (crank == 0) mbar_arrive(&tempty_bar[acc]); else mbar_arrive_remote(&tempty_bar[acc], 0); }
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
   } else if (p.fa && warp < 14) {
@@ -713,8 +755,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
         if (oh_l >= 0 && oh_l < p.tile_h && ow_l >= 0 && ow_l < p.tile_w) own_mask |= 1u << j;
       }
       uint32_t g = 0;                                          // running chunk number (same sequence as the MMA issuer)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int t = blockIdx.x; t - static_cast<int>(crank) < total_tiles; t += gridDim.x) {
+        TileCoord tc = decode_tile(p, t);
+        if (t >= total_tiles) tc.n0 = p.N;                     // odd tile count: the pair's second tile does not exist -> zeros
         const int vh0 = tc.h0 + p.hs_dh_min, vw0 = tc.w0 + p.hs_dw_min;
         const int sh0 = vh0 - p.fa_border, sw0 = vw0 - p.fa_border;      // strip origin in source coordinates
         const bool inside = (tc.n0 < p.N) && sh0 >= 0 && sw0 >= 0 && sh0 + p.hs_rows <= p.Hs && sw0 + p.hs_cols <= p.Ws;
@@ -768,7 +811,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
               if (lane == 0) mbar_arrive(&sempty_bar[slot]);   // this warp has read the staging slot
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&aready_bar[buf]);
+              if (lane == 0) {
+              if constexpr (CTA2) { if (crank == 0) mbar_arrive(&aready_bar[buf]); else mbar_arrive_remote(&aready_bar[buf], 0); }
+              else mbar_arrive(&aready_bar[buf]);
+            }
               continue;
             }
             bool waited = false;
@@ -835,7 +881,10 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
             else convert(std::integral_constant<int, 12>{});
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&aready_bar[buf]);
+            if (lane == 0) {
+              if constexpr (CTA2) { if (crank == 0) mbar_arrive(&aready_bar[buf]); else mbar_arrive_remote(&aready_bar[buf], 0); }
+              else mbar_arrive(&aready_bar[buf]);
+            }
           }
         }
       }
@@ -1010,10 +1059,11 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();       // nobody leaves while the peer may still arrive on / read from this CTA
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -1165,7 +1215,7 @@ static void tc_plan_tiles_novs(const TcPhase& ph, int* tile_w, int* tile_h, int*
 int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   int num_sms = 0;
   if (device_num_sms(&num_sms) != 0) return DLB_ERR_CUDA;
-  if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel), kMaxDynSmem, kSlotConvTc) != 0) return DLB_ERR_CUDA;
+  if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel_t<false>), kMaxDynSmem, kSlotConvTc) != 0) return DLB_ERR_CUDA;
   TcParams p;
   memset(&p, 0, sizeof(p));
   const int is_bf16 = (ph.fmt == DLB_FMT_BF16);
@@ -1211,7 +1261,13 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   p.ys_n = ph.ys_n; p.ys_h = ph.ys_h; p.ys_w = ph.ys_w; p.y_base = ph.y_base;
   p.y = ph.y; p.bias = ph.bias;
   if (2 * p.nacc * n_tile > 512) return set_error("conv_tc: merged phases need 2 * nacc * n_tile <= 512 TMEM columns");
-  p.idesc = make_idesc_f16(128, n_tile, is_bf16);
+  // CTA pair (cta_group::2) for the wide fused-operand halo-strip convolutions (the 256 -> 256 trunk): each SM then loads,
+  // stores and feeds the tensor core only half of every weight tile.  DLB_CTA2=0 switches it off (A/B measurements).
+  static const bool cta2_enabled = []() { const char* e = getenv("DLB_CTA2"); return !(e != nullptr && e[0] == '0'); }();
+  const bool use_cta2 = cta2_enabled && use_hs && ph.fa == 1 && ph.nsrc == 1 && n_tile == 256 && ph.cout == 256 && p.nacc == 1 &&
+                        !ph.no_cta2 && (num_sms % 2 == 0);
+  p.cta2 = use_cta2 ? 1 : 0;
+  p.idesc = make_idesc_f16(use_cta2 ? 256 : 128, n_tile, is_bf16);
   p.st_partial = ph.st_partial; p.st_cnt = ph.st_cnt; p.st_S = ph.st_S;
   p.st_S_cap = ph.st_S_cap; p.st_slice_base = ph.st_slice_base; p.st_S_total = ph.st_S_total;
   if (ph.st_partial != nullptr && tile_n != 1) return set_error("conv_tc: fused statistics need H*W >= 128 per image");
@@ -1281,7 +1337,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       p.hs = 1; p.hs_rows = tile_h + dh1 - dh0; p.hs_cols = tile_w + dw1 - dw0; p.hs_dh_min = dh0; p.hs_dw_min = dw0;
       p.hs_plane_bytes = (p.hs_rows * p.hs_cols * 128 + 1023) / 1024 * 1024;
       // two strip buffers when they still leave room for two weight stages (the 256 -> 256 trunk conv: 2 x 46 KB + 2 x 64 KB)
-      p.hs_nbuf = (2LL * p.planes * p.hs_plane_bytes + 2LL * p.planes * n_tile * 128 + 1024 <= kMaxDynSmem) ? 2 : 1;
+      p.hs_nbuf = (2LL * p.planes * p.hs_plane_bytes + 2LL * p.planes * (p.cta2 ? n_tile / 2 : n_tile) * 128 + 1024 <= kMaxDynSmem) ? 2 : 1;
       // TMA staging of the fp32 source (ht) when it is a plain single source and two slots fit next to the strips and two
       // weight stages
       const int slot = (p.hs_rows * p.hs_cols * 256 + 1023) / 1024 * 1024;
@@ -1317,7 +1373,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   {
     uint64_t dims[3] = {(uint64_t)cin_total, (uint64_t)ph.cout, (uint64_t)ph.w_taps};
     uint64_t strides[2] = {(uint64_t)cin_total * 2, (uint64_t)cin_total * ph.cout * 2};
-    uint32_t box[3] = {(uint32_t)kKC, (uint32_t)n_tile, 1};
+    uint32_t box[3] = {(uint32_t)kKC, (uint32_t)(p.cta2 ? n_tile / 2 : n_tile), 1};   // cta2: each CTA loads half the rows
     if (!encode_tiled_map(&p.b_hi, ph.w_hi, is_bf16, 3, dims, strides, box)) return -1;
     if (ph.split && !encode_tiled_map(&p.b_lo, ph.w_lo, is_bf16, 3, dims, strides, box)) return -1;
   }
@@ -1339,7 +1395,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     }
   }
 
-  const int b_bytes = n_tile * 128;
+  const int b_bytes = (p.cta2 ? n_tile / 2 : n_tile) * 128;
   int bres_bytes = use_vs ? ph.ntaps * p.kchunks[0] * p.planes * b_bytes
                           : (use_hs ? p.hs_nbuf * p.planes * p.hs_plane_bytes : 0);
   if (p.ht) bres_bytes += 2 * p.ht_slot_bytes;               // the staging ring sits between the strips and the weight stages
@@ -1371,8 +1427,39 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;
-  conv_tc_kernel<<<grid, ph.fa ? kThreadsFa : kThreads, smem_bytes, stream>>>(p);
-  if (cudaGetLastError() != cudaSuccess) return set_cuda_error("conv_tc_kernel launch");
+  if (p.cta2) {
+    // clusters of two CTAs (consecutive blockIdx.x = consecutive tiles); an even grid, at most one CTA per SM
+    grid = (grid + 1) & ~1;
+    if (grid > num_sms) grid = num_sms & ~1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreadsFa, 1, 1); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel_t<true>), kMaxDynSmem, kSlotConvTc2) != 0) return DLB_ERR_CUDA;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel_t<true>, p);
+    if (e != cudaSuccess) {
+      char buf[200];
+      snprintf(buf, sizeof(buf), "conv_tc_kernel cluster launch (grid %d, smem %d): %s", grid, smem_bytes, cudaGetErrorString(e));
+      cudaGetLastError();
+      set_error(buf);
+      return DLB_ERR_CUDA;
+    }
+    return 0;
+  }
+  conv_tc_kernel_t<false><<<grid, ph.fa ? kThreadsFa : kThreads, smem_bytes, stream>>>(p);
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      char buf[200];
+      snprintf(buf, sizeof(buf), "conv_tc_kernel launch (grid %d, threads %d, smem %d): %s", grid, ph.fa ? kThreadsFa : kThreads,
+               smem_bytes, cudaGetErrorString(e));
+      set_error(buf);
+      return DLB_ERR_CUDA;
+    }
+  }
   return 0;
 }
 

@@ -16,7 +16,7 @@ int set_cuda_error(const char* where);     // records where + cudaGetErrorString
 // Per-device, mutex-guarded launch facts (the only process-wide mutable state of the library).
 //   ensure_dyn_smem: raise `func`'s dynamic shared-memory limit once per device (slot = small id of the kernel);
 //   device_num_sms:  multiprocessor count of the current device.
-enum { kSlotConvTc = 0, kSlotWgradMt = 1, kSlotWgrad = 2, kNumSmemSlots = 8 };
+enum { kSlotConvTc = 0, kSlotWgradMt = 1, kSlotWgrad = 2, kSlotConvTc2 = 3, kNumSmemSlots = 8 };
 int ensure_dyn_smem(const void* func, int bytes, int slot);
 int device_num_sms(int* num_sms);
 
@@ -49,6 +49,7 @@ struct TcPhase : PhaseGeom {
   int max_ctas;                // 0 = #SMs
   int no_vs;                   // 1 = never use the vertical-strip mode (A/B testing)
   int no_hs;                   // 1 = never use the plane-fed halo-strip mode (A/B testing)
+  int no_cta2;                 // 1 = never pair CTAs (cta_group::2)
   // merged output-parity phases of a ConvTranspose2d (nacc > 1): tap t accumulates into accumulator tap_acc[t]; accumulator a
   // is written at output base acc_ybase[a] with statistics slice base acc_slice[a].  nacc = 0 / 1: a single accumulator.
   int nacc;
