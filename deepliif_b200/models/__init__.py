@@ -138,7 +138,7 @@ def _plan_nets(opt, seg_weights, mod_only, seg_only):
 
 
 def run_batch_device(tiles_dev, nets, opt, seg_weights=None, mod_only=False, micro_batch=8, n_streams=3, seg_only=False,
-                     want_parts=True):
+                     want_parts=True, variance=None):
     """uint8 tiles [T,ts,ts,3] ON THE DEVICE -> dict[name -> uint8 [T,ts,ts,3] on the device] with the reference's result
     keys (G1.., G{S}, and — with want_parts — the per-modality seg outputs G{S}k), skipping empty tiles exactly like
     run_wrapper (:399-443).  Nothing returns to the host here except the 3 integers per tile of the is_empty statistic.
@@ -153,7 +153,7 @@ def run_batch_device(tiles_dev, nets, opt, seg_weights=None, mod_only=False, mic
     if T == 0:
         return out
     # is_empty(): gray-level variance per tile, computed on the device from the uint8 batch (exact integer sums)
-    var = ops.tile_gray_variance(tiles_dev)
+    var = ops.tile_gray_variance(tiles_dev) if variance is None else variance
     live = [i for i in range(T) if var[i] >= EMPTY_TILE_VARIANCE]
     dead = sorted(set(range(T)) - set(live))
     if dead:
@@ -270,6 +270,132 @@ def infer_tiles(img, tile_size, overlap_size, nets, opt, seg_weights=None, mod_o
             v = np.stack([np.asarray(Image.fromarray(t).resize((tile_size, tile_size))) for t in v])
         results[k] = Image.fromarray(grid.stitch(v))
     return results
+
+
+class _PendingImage:
+    """Results of one image, still on their way: uint8 tiles in a pinned host buffer behind a CUDA event."""
+    __slots__ = ("grid", "keys", "host", "event", "tile_size", "scale_size", "meta")
+
+
+def _stitch_pending(pend):
+    pend.event.synchronize()
+    full_np = pend.host.numpy()
+    results = {}
+    for j, k in enumerate(pend.keys):
+        v = full_np[:, j]
+        if pend.tile_size != pend.scale_size:
+            v = np.stack([np.asarray(Image.fromarray(t).resize((pend.tile_size, pend.tile_size))) for t in v])
+        results[k] = Image.fromarray(pend.grid.stitch(v))
+    return results
+
+
+def infer_images(images, tile_size, overlap_size, nets, opt, seg_weights=None, mod_only=False, seg_only=False, micro_batch=8,
+                 n_streams=3, want_parts=False, depth=3):
+    """Pipelined `infer_tiles` over a sequence of PIL images (the per-image loop of `deepliif test`, cli.py:893-919, and
+    the WSI sweep of BASELINE config 3): yields (index, dict[net key -> stitched PIL image]) in order (on non-zero ranks of
+    a torchrun launch: (index, None)).
+
+    Three things overlap instead of alternating: (i) the host tiles image k+1 (each rank only its own shard, straight
+    into a pinned buffer) and uploads it on a side stream — where the is_empty statistic is also computed, so its small
+    device-to-host read does not wait for the generators — while the GPU runs image k; (ii) the uint8 results of image k
+    are gathered (one NCCL gather) and copied to a pinned buffer asynchronously; (iii) a stitcher thread on rank 0 turns
+    finished buffers into images while the next ones are in flight.  `depth` buffers rotate."""
+    import queue
+    import threading
+    import torch.distributed as dist
+    from .. import sharding
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size() if distributed else 1
+    rank = dist.get_rank() if distributed else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    todo, done = queue.Queue(), queue.Queue()
+    free = threading.Semaphore(depth)        # staging slots: taken by the main thread, returned when the image is stitched
+
+    def stitcher():
+        while True:
+            item = todo.get()
+            if item is None:
+                return
+            idx, pend = item
+            try:
+                done.put((idx, _stitch_pending(pend) if pend is not None else None))
+            except Exception as e:           # surfaced by the consumer
+                done.put((idx, e))
+            free.release()
+
+    th = threading.Thread(target=stitcher, daemon=True)
+    th.start()
+    n_sub = 0
+    n_out = 0
+
+    def drain(block):
+        nonlocal n_out
+        out = []
+        while n_out < n_sub:
+            try:
+                idx, res = done.get(block=block and not out)
+            except queue.Empty:
+                break
+            if isinstance(res, Exception):
+                raise res
+            out.append((idx, res)); n_out += 1
+        return out
+
+    slot = 0
+    for idx, img in enumerate(images):
+        free.acquire()                       # at most `depth` images between tiling and stitching: their buffers are distinct
+        grid = TileGrid(np.asarray(img.convert("RGB")), tile_size, overlap_size)
+        T = len(grid)
+        mine_idx = sharding.shard_indices(T, rank, world)
+        ts = grid.ts
+        if tile_size != opt.scale_size:
+            mine = grid.tiles(mine_idx)
+            mine = np.stack([np.asarray(Image.fromarray(t).resize((opt.scale_size, opt.scale_size))) for t in mine]) \
+                if len(mine) else np.zeros((0, opt.scale_size, opt.scale_size, 3), np.uint8)
+            ts = opt.scale_size
+        tag = ("in", slot % depth)
+        if mine_idx:
+            stage = _pinned(tag, (len(mine_idx), ts, ts, 3))
+            if tile_size != opt.scale_size:
+                stage.copy_(torch.from_numpy(np.ascontiguousarray(mine)))
+            else:
+                grid.tiles(mine_idx, out=stage.numpy())
+            with torch.cuda.stream(side):
+                dev_in = stage.to(dev, non_blocking=True)
+                var = ops.tile_gray_variance(dev_in)              # syncs the SIDE stream only
+            main.wait_stream(side)
+            dev_in.record_stream(main)
+        else:
+            dev_in = torch.zeros((0, ts, ts, 3), dtype=torch.uint8, device=dev)
+            var = np.zeros((0,))
+        local = run_batch_device(dev_in, nets, opt, seg_weights, mod_only, micro_batch, n_streams, seg_only, want_parts,
+                                 variance=var)
+        keys = sorted(local.keys())
+        stacked = torch.stack([local[k] for k in keys], dim=1) if mine_idx else \
+            torch.zeros((0, len(keys), ts, ts, 3), dtype=torch.uint8, device=dev)
+        full = sharding.gather_to_rank0(stacked, T, to_numpy=False) if distributed else stacked
+        pend = None
+        if rank == 0:
+            pend = _PendingImage()
+            pend.grid, pend.keys, pend.tile_size, pend.scale_size = grid, keys, tile_size, opt.scale_size
+            pend.host = _pinned(("out", slot % depth), tuple(full.shape))
+            pend.host.copy_(full, non_blocking=True)
+            pend.event = torch.cuda.Event()
+            pend.event.record(main)
+        todo.put((idx, pend))
+        n_sub += 1
+        slot += 1
+        for item in drain(block=False):
+            yield item
+    todo.put(None)
+    for item in drain(block=True):
+        yield item
+    while n_out < n_sub:
+        for item in drain(block=True):
+            yield item
+    th.join()
 
 
 def inference(img, tile_size, overlap_size, model_path, use_torchserve=False, eager_mode=True, color_dapi=False,

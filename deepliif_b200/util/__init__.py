@@ -163,10 +163,18 @@ class TileGrid:
     def __len__(self):
         return len(self.origins)
 
-    def tiles(self):
-        """uint8 [T, ts, ts, 3]"""
+    def tiles(self, indices=None, out=None):
+        """uint8 [T, ts, ts, 3] (all tiles, or the tiles `indices` only — a rank's shard; `out`: optional destination,
+        e.g. a pinned staging buffer, filled in place)."""
         ts = self.ts
-        return np.stack([self.img[y:y + ts, x:x + ts] for x, y in self.origins])
+        sel = self.origins if indices is None else [self.origins[i] for i in indices]
+        if out is None:
+            if not sel:
+                return np.zeros((0, ts, ts, self.img.shape[2]), self.img.dtype)
+            return np.stack([self.img[y:y + ts, x:x + ts] for x, y in sel])
+        for k, (x, y) in enumerate(sel):
+            out[k] = self.img[y:y + ts, x:x + ts]
+        return out
 
     def stitch(self, result_tiles):
         """result_tiles: uint8 [T, ts, ts, C] -> uint8 [orig_h, orig_w, C]"""

@@ -373,3 +373,33 @@ def test_serialize_command_writes_a_packed_directory_that_test_reads(tmp_path):
     assert set(got) == set(base)
     for k in base:
         assert np.array_equal(np.asarray(got[k]), np.asarray(base[k])), k
+
+
+def test_infer_images_pipeline_equals_per_image_inference(tmp_path):
+    """models.infer_images (tiling / upload / stitching pipelined across images, side-stream is_empty) returns, image by
+    image and in order, exactly what infer_tiles returns — including an image with an empty (constant) tile."""
+    from deepliif_b200.models import get_opt, infer_images, infer_tiles, init_nets
+    mdir, _ = _write_model_dir(tmp_path, net_g="resnet_2blocks", net_gs="unet_128", n_blocks=2)
+    g_shapes = nets.resnet_param_shapes(3, 3, 64, 2, "batch", True, "zero")
+    s_shapes = nets.unet_param_shapes(7, 64, 3, 3, "batch")
+    for k, sd in {**{f"G{i}": nets.make_state_dict(g_shapes, 50 + i, "stress") for i in range(1, 5)},
+                  **{f"GS{i}": nets.make_state_dict(s_shapes, 60 + i, "stress") for i in range(5)}}.items():
+        torch.save(sd, os.path.join(mdir, f"latest_net_{k}.pth"))
+    init_nets.cache_clear()
+    opt = get_opt(mdir)
+    opt.scale_size = 256
+    netd = init_nets(mdir, True, opt)
+    rng = np.random.default_rng(31)
+    imgs = []
+    for (h, w) in ((300, 520), (256, 256), (700, 300), (512, 512), (260, 900)):
+        a = (rng.random((h, w, 3)) * 255).astype(np.uint8)
+        imgs.append(Image.fromarray(a))
+    blank = np.full((300, 520, 3), 200, np.uint8); blank[:, 260:] = (rng.random((300, 260, 3)) * 255).astype(np.uint8)
+    imgs.append(Image.fromarray(blank))                                          # left tile is empty (variance 0)
+    ref = [infer_tiles(im, 256, 16, netd, opt, seg_weights=opt.seg_weights, want_parts=False) for im in imgs]
+    got = list(infer_images(imgs, 256, 16, netd, opt, seg_weights=opt.seg_weights, want_parts=False, depth=2))
+    assert [i for i, _ in got] == list(range(len(imgs)))
+    for (_, g_), r_ in zip(got, ref):
+        assert sorted(g_) == sorted(r_)
+        for k in r_:
+            assert np.array_equal(np.asarray(g_[k]), np.asarray(r_[k])), k
