@@ -16,7 +16,7 @@ int set_cuda_error(const char* where);     // records where + cudaGetErrorString
 // Per-device, mutex-guarded launch facts (the only process-wide mutable state of the library).
 //   ensure_dyn_smem: raise `func`'s dynamic shared-memory limit once per device (slot = small id of the kernel);
 //   device_num_sms:  multiprocessor count of the current device.
-enum { kSlotConvTc = 0, kSlotWgradMt = 1, kSlotWgrad = 2, kSlotConvTc2 = 3, kNumSmemSlots = 8 };
+enum { kSlotConvTc = 0, kSlotWgradMt = 1, kSlotWgrad = 2, kSlotConvTc2 = 3, kSlotHeadConv = 4, kSlotStemConv = 5, kNumSmemSlots = 8 };
 int ensure_dyn_smem(const void* func, int bytes, int slot);
 int device_num_sms(int* num_sms);
 

@@ -285,6 +285,7 @@ class ResnetEngine(_EngineBase):
         # followed by the shifted-sum finish; else the fp32 direct kernel.
         wh, bh = g(f"model.{idx}.weight"), g(f"model.{idx}.bias")
         self.head_tc = backend == "tc" and wh.shape[0] <= 4 and wh.shape[3] <= 8 and wh.shape[1] % 64 == 0
+        self.head_stream = False
         if self.head_tc:
             co, ci, R, S = wh.shape
             wv = torch.zeros((32, ci, R, 1), dtype=torch.float32, device=device)
@@ -293,6 +294,10 @@ class ResnetEngine(_EngineBase):
             self.head = ConvLayer(wv, None, pad=0, prec=prec, backend="tc", n_tile=32)
             self.head_bias = bh.detach().to(torch.float32).contiguous() if bh is not None else None
             self.head_S, self.head_co = S, co
+            # row-streaming head kernel (dlb_head_conv_fwd): 64 -> co <= 3, 7 x 7, split bf16
+            self.head_stream = (_env_flag("DLB_HEAD_STREAM", True) and ci == 64 and R == 7 and S == 7 and co <= 3
+                                and prec.split and prec.fmt == FMT_BF16)
+            self.head_wpk = ops.head_conv_pack(wh) if self.head_stream else None
         else:
             self.head = ConvLayer(wh, bh, pad=3, backend="direct")
 
@@ -438,6 +443,9 @@ class ResnetEngine(_EngineBase):
             h, w = h * 2, w * 2
             sc, sh = self._stats(y, self.up_norm[i], ws)
             cur = Lazy(y, sc, sh, ACT_RELU)
+        if self.head_stream and cur.residual is None and h >= 8 and w >= 8:
+            return ops.head_conv(cur.x, cur.scale, cur.shift, cur.act, self.head_wpk, self.head_bias, self.head_co, self.pad_mode,
+                                 ACT_TANH)
         z, _, _ = self._consume(self.head, cur, N, h, w, border=3, fuse_stats=False, allow=(1, 2) if self.fuse_head else ())
         return ops.head_finish(z, self.head_bias, w, self.head_S, self.head_co, ACT_TANH)
 

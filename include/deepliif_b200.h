@@ -125,6 +125,22 @@ int dlb_conv_tc_fwd_fused(const dlb_conv_desc* d, const dlb_fused_src* src, cons
                           const float* bias, float* y, int fmt, int split, int n_tile, void* stats_ws,
                           size_t stats_ws_bytes, dlb_stream_t stream);
 
+/* ---- generator head in one kernel --------------------------------------------------------------------------
+ * Replaces nn.ReflectionPad2d(3) | nn.ZeroPad2d(3) + nn.Conv2d(64, CO, 7) + nn.Tanh (reference networks.py:438-444)
+ * together with the producer's normalisation + ReLU (networks.py:434-436), on the tensor cores:
+ *   y[n, co, h, w] = out_act(bias[co] + sum_{ci,kh,kw} a[n, pad(h+kh-3), pad(w+kw-3), ci] * w[co, ci, kh, kw]),
+ *   a = act(x * scale[n, ci] + shift[n, ci])          (scale / shift NULL: a = act(x))
+ * x: the producer's raw fp32 NHWC [N, H, W, 64] output; y: fp32 NCHW [N, CO, H, W]; border_mode DLB_PAD_ZERO / _REFLECT
+ * pads `a` (not x).  Split precision (bf16 hi + lo, three MMA passes), fp32 accumulation.  Row-streaming kernel: the
+ * horizontal taps are the GEMM's K (shifted operand windows), the vertical taps are summed in the epilogue's registers;
+ * nothing but x is read and nothing but y is written.  Needs C == 64, CO <= 3, H, W >= 8.
+ * dlb_head_conv_pack_weights: w fp32 [CO][64][7][7] (PyTorch layout) -> dlb_head_conv_weight_bytes() bytes, once per model. */
+size_t dlb_head_conv_weight_bytes(void);
+int dlb_head_conv_pack_weights(const float* w, int CO, int C, int R, int S, void* out, dlb_stream_t stream);
+int dlb_head_conv_fwd(const float* x, const float* scale, const float* shift, int act, int N, int H, int W, int C,
+                      const void* w_packed, const float* bias, int CO, int border_mode, int out_act, float* y_nchw,
+                      dlb_stream_t stream);
+
 /* fp32 CUDA-core convolution for the layers tensor cores cannot tile (Cin = 3 stem, networks.py:386-397;
  * Cout = 3 head + Tanh, :438-444; PatchGAN first/last convs, :638, :659).  Fuses the producer's
  * normalisation + activation on the input side: x' = act_in(x * in_scale[n,c] + in_shift[n,c]) (zero /

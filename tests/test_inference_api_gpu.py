@@ -130,7 +130,7 @@ def test_cli_train_then_test_round_trip(tmp_path):
     ck = tmp_path / "ck"
     r = CliRunner().invoke(cli, ["train", "--dataroot", str(root), "--name", "exp", "--checkpoints-dir", str(ck), "--gpu-ids", "0",
                                  "--batch-size", "2", "--net-g", "resnet_2blocks", "--net-gs", "unet_128", "--n-epochs", "1",
-                                 "--n-epochs-decay", "0", "--save-epoch-freq", "1", "--print-freq", "1", "--num-threads", "0",
+                                 "--n-epochs-decay", "0", "--save-epoch-freq", "1", "--print-freq", "1", "--num-threads", "2",
                                  "--preprocess", "resize_and_crop", "--load-size", "144", "--crop-size", "128",
                                  "--seed", "0"])
     assert r.exit_code == 0, r.output[-3000:]

@@ -337,3 +337,47 @@ def test_conv_tc_stem_is_bit_identical_to_window_pack_then_conv(ops, prec, N, C,
     if split:
         ref = F.conv2d(F.pad(x.double(), (3, 3, 3, 3), mode="reflect" if pad_mode else "constant"), w.double(), b.double()).float()
         assert (nchw(y.cpu()) - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+
+
+HEAD_CASES = [
+    # N, H, W, CO, border, act, with_norm
+    (1, 8, 8, 3, "zero", "relu", True),            # smallest map: every row is a border row
+    (2, 16, 40, 3, "reflect", "relu", True),
+    (3, 33, 130, 3, "zero", "relu", True),          # two column strips (130 = 128 + 2), CTA ranges spanning strips / images
+    (2, 37, 300, 3, "reflect", "relu", True),       # three strips, odd height
+    (1, 64, 128, 1, "reflect", "none", False),      # CO = 1, identity source
+    (1, 128, 256, 3, "zero", "lrelu", True),
+]
+
+
+@pytest.mark.parametrize("case", HEAD_CASES, ids=lambda c: f"n{c[0]}_{c[1]}x{c[2]}_co{c[3]}_{c[4]}_{c[5]}")
+@pytest.mark.parametrize("out_act", ["tanh", "none"])
+def test_head_conv_stream_vs_fp64_reference(ops, case, out_act):
+    """dlb_head_conv_fwd (row-streaming head: horizontal taps in the MMA, vertical taps in the epilogue) against
+    pad(act(x*scale+shift)) -> conv2d -> bias -> act evaluated in fp64.  Split bf16 (three passes), fp32 accumulation over
+    3136 products: max-abs <= 5e-5 for O(1) outputs (the network gate is 1e-3)."""
+    N, H, W, CO, border, act, with_norm = case
+    acts = {"relu": ops.ACT_RELU, "none": ops.ACT_NONE, "lrelu": ops.ACT_LRELU02}
+    x = _rand((N, H, W, 64), 3)
+    w = _rand((CO, 64, 7, 7), 4, 0.04)
+    b = _rand((CO,), 5, 0.2)
+    sc = (_rand((N, 64), 6) * 0.5 + 1.0) if with_norm else None
+    sh = _rand((N, 64), 7, 0.3) if with_norm else None
+    a = x.double()
+    if with_norm:
+        a = a * sc.double()[:, None, None, :] + sh.double()[:, None, None, :]
+    a = {"relu": torch.relu, "none": lambda t: t, "lrelu": lambda t: F.leaky_relu(t, 0.2)}[act](a)
+    a = a.permute(0, 3, 1, 2)
+    a = F.pad(a, (3, 3, 3, 3), mode="reflect" if border == "reflect" else "constant")
+    ref = F.conv2d(a, w.double(), b.double())
+    if out_act == "tanh":
+        ref = torch.tanh(ref)
+    wpk = ops.head_conv_pack(w.cuda())
+    y = ops.head_conv(x.cuda(), sc.cuda() if with_norm else None, sh.cuda() if with_norm else None, acts[act], wpk, b.cuda(), CO,
+                      ops.PAD_REFLECT if border == "reflect" else ops.PAD_ZERO,
+                      ops.ACT_TANH if out_act == "tanh" else ops.ACT_NONE)
+    torch.cuda.synchronize()
+    err = (y.cpu().double() - ref).abs().max().item()
+    print(f"head_conv {case} {out_act}: max|d| {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
+    assert y.shape == (N, CO, H, W)
+    assert err <= 5e-5

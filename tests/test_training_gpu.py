@@ -284,6 +284,42 @@ def test_dropout_forward_backward_share_the_mask():
     assert (g1 - g2).abs().max().item() < 1e-6
 
 
+def test_unet_training_applies_dropout_on_the_inner_blocks():
+    """UnetGenerator(use_dropout=True) (reference networks.py:536, 604-605): Dropout(0.5) closes the num_downs-5 inner
+    ngf*8 blocks in training.  The train engine draws a fresh mask per forward (outputs differ), restoring the torch seed
+    restores the mask, the backward reuses the forward's mask (finite gradients for every parameter), and a generator
+    without dropout has no drop levels."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from deepliif_b200 import engine_train
+    nd = 7                                                        # two dropout levels: 4 and 5
+    sd = nets.make_state_dict(nets.unet_param_shapes(nd, 64, 3, 3, "batch"), 13, "stress")
+    eng = engine_train.UnetTrainEngine(sd, num_downs=nd, norm="batch", norm_mode="batch", use_dropout=True)
+    assert eng.drop_levels == {4, 5}
+    assert engine_train.UnetTrainEngine(sd, num_downs=nd, norm="batch", norm_mode="batch").drop_levels == set()
+    x = _rand((2, 3, 128, 128), 5).cuda()
+    torch.manual_seed(11); y1, c1 = eng.forward_train(x)
+    y2, _ = eng.forward_train(x)
+    torch.manual_seed(11); y3, _ = eng.forward_train(x)
+    assert (y1 - y2).abs().max().item() > 1e-4 and torch.equal(y1, y3)
+    y0, _ = engine_train.UnetTrainEngine(sd, num_downs=nd, norm="batch", norm_mode="batch").forward_train(x)
+    assert (y1 - y0).abs().max().item() > 1e-4
+    g, _ = eng.backward(c1, _rand((2, 3, 128, 128), 6).cuda())
+    expected = {k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    assert set(g) == expected and all(torch.isfinite(v).all() for v in g.values())
+    # the module wrapper forwards the flag (define_G(use_dropout=True) in training)
+    from deepliif_b200 import training
+    from deepliif_b200.models import networks
+    training.install()
+    net = networks.define_G(3, 3, 64, "unet_128", "batch", True, gpu_ids=[0]).train()
+    torch.manual_seed(3); a = net(x)
+    b = net(x)
+    assert (a - b).abs().max().item() > 1e-5
+    net.eval()
+    with torch.no_grad():
+        assert torch.equal(net(x), net(x))
+
+
 def test_resnet_training_with_dropout_runs_and_is_seeded():
     """use_dropout=True (the reference default, `not opt.no_dropout`): state_dict indices shift by the Dropout module;
     two forward passes differ unless the torch seed is restored."""
