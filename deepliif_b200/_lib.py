@@ -58,6 +58,9 @@ SIGNATURES = {
     "dlb_norm_apply": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _vp, _vp]),
     "dlb_stem_window_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dlb_head_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dlb_stem_conv_weight_bytes": (_sz, []),
+    "dlb_stem_conv_pack_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "dlb_stem_conv_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dlb_head_conv_weight_bytes": (_sz, []),
     "dlb_head_conv_pack_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "dlb_head_conv_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),

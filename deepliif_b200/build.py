@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdeepliif_b200.so")
-SOURCES = ["api.cu", "conv_tc.cu", "head_conv.cu", "conv_wgrad.cu", "conv_direct.cu", "norm.cu", "norm_bwd.cu", "optim.cu", "pixel.cu", "cells.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "head_conv.cu", "stem_conv.cu", "conv_wgrad.cu", "conv_direct.cu", "norm.cu", "norm_bwd.cu", "optim.cu", "pixel.cu", "cells.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

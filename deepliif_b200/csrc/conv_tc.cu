@@ -390,8 +390,9 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // the whole warp runs the loop (convergent: descriptors may live in uniform registers), one elected lane issues
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       const int k_iters = p.ntaps * (p.kchunks[0] + (p.nsrc > 1 ? p.kchunks[1] : 0));
@@ -432,29 +433,29 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
                   if (p.planes == 2) {
                     const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
                     const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                    umma_f16_2sm(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                    umma_f16_2sm(d_tmem, da_hi, db_lo, p.idesc, 1);
-                    umma_f16_2sm(d_tmem, da_hi, db_hi, p.idesc, 1);
+                    umma_f16_2sm_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                    umma_f16_2sm_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
+                    umma_f16_2sm_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
                   } else {
-                    umma_f16_2sm(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                    umma_f16_2sm_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                   }
                 } else if (p.planes == 2) {
                   const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
                   const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                  umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                  umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
-                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+                  umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                  umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
+                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
                 } else {
-                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                 }
                 accumulate = 1;
               }
-              if constexpr (CTA2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+              if constexpr (CTA2) umma_commit_2sm_elect(&empty_bar[s]); else umma_commit_elect(&empty_bar[s]);
               if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            if constexpr (CTA2) umma_commit_2sm(&afree_bar[buf]); else umma_commit(&afree_bar[buf]);   // strip buffer reusable once these MMAs retire
+            if constexpr (CTA2) umma_commit_2sm_elect(&afree_bar[buf]); else umma_commit_elect(&afree_bar[buf]);   // strip buffer reusable once these MMAs retire
           }
-          if constexpr (CTA2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+          if constexpr (CTA2) umma_commit_2sm_elect(&tfull_bar[acc]); else umma_commit_elect(&tfull_bar[acc]);
           acc ^= 1; if (acc == 0) acc_ph ^= 1;
         }
       } else if (p.vs) {
@@ -482,19 +483,19 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
                 if (p.planes == 2) {
                   const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + aoff + k * 32);
                   const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                  umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                  umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
-                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+                  umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
+                  umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
+                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
                 } else {
-                  umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                 }
                 accumulate = 1;
               }
             }
-            umma_commit(&empty_bar[s]);
+            umma_commit_elect(&empty_bar[s]);
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
-          umma_commit(&tfull_bar[acc]);
+          umma_commit_elect(&tfull_bar[acc]);
           acc ^= 1; if (acc == 0) acc_ph ^= 1;
         }
       } else
@@ -517,18 +518,18 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             if (p.planes == 2) {
               const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
               const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-              umma_f16(d_tmem, da_lo, db_hi, p.idesc, accumulate);   // small terms first
-              umma_f16(d_tmem, da_hi, db_lo, p.idesc, 1);
-              umma_f16(d_tmem, da_hi, db_hi, p.idesc, 1);
+              umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);   // small terms first
+              umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
+              umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
             } else {
-              umma_f16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+              umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
             }
             accumulate = 1;
           }
-          umma_commit(&empty_bar[s]);                 // smem stage free once these MMAs retire
+          umma_commit_elect(&empty_bar[s]);                 // smem stage free once these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
+        umma_commit_elect(&tfull_bar[acc]);                 // accumulator complete -> epilogue
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }

@@ -252,6 +252,27 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_2sm_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\t.reg .pred e;\n\tmov.b16 m, 3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      :
+      : "r"(smem_u32(bar))
+      : "memory");
+}
+
 // K-major, 128-byte-swizzled operand tile: rows of 128 B (64 x 16-bit), 8-row atoms 1024 B apart.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) descriptor version = 1 (sm_100)

@@ -250,6 +250,7 @@ class ResnetEngine(_EngineBase):
         # stem: on the tensor cores through the horizontal-window operand (K = 7 taps x 8 channel lanes = 64),
         # else (validation backend / exotic channel counts) on the fp32 direct kernel.  head: direct kernel.
         w1 = g("model.1.weight")
+        self.stem_stream = False
         self.stem_tc = backend == "tc" and w1.shape[1] <= 8 and w1.shape[3] <= 8 and w1.shape[0] % 32 == 0
         if self.stem_tc:
             co, ci, R, S = w1.shape
@@ -258,6 +259,10 @@ class ResnetEngine(_EngineBase):
             wk.view(co, 8, 8, R)[:, :S, :ci, :] = w1.to(torch.float32).permute(0, 3, 1, 2)
             self.stem = ConvLayer(wk, g("model.1.bias"), pad=0, prec=prec, backend="tc", n_tile=n_tile)
             self.stem_S, self.stem_in_nc = S, ci
+            # row-streaming stem kernel (dlb_stem_conv_fwd): C <= 4 -> 64, 7 x 7, split bf16
+            self.stem_stream = (_env_flag("DLB_STEM_STREAM", True) and co == 64 and ci <= 4 and R == 7 and S == 7
+                                and prec.split and prec.fmt == FMT_BF16)
+            self.stem_wpk = ops.stem_conv_pack(w1) if self.stem_stream else None
         else:
             self.stem = ConvLayer(w1, g("model.1.bias"), pad=3, backend="direct")
         self.stem_norm = nrm("model.2")
@@ -408,7 +413,10 @@ class ResnetEngine(_EngineBase):
             if taps is not None:
                 taps[name] = a
 
-        if self.fuse_stem and self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
+        if self.stem_stream and H >= 8 and W >= 8:
+            ws = ops.stats_workspace(N, H * W, self.stem.cout, x.device)
+            y = ops.stem_conv(x, self.stem_wpk, self.stem.bias, self.stem.cout, self.pad_mode, stats_ws=ws)
+        elif self.fuse_stem and self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
             ws = ops.stats_workspace(N, H * W, self.stem.cout, x.device)
             y = ops.conv_tc_stem(x, 3, self.stem_S, self.pad_mode, self.stem.cout, self.stem.w_hi, self.stem.w_lo, self.stem.bias,
                                  self.prec.fmt, self.prec.split, self.stem.n_tile, stats_ws=ws)

@@ -12,7 +12,7 @@ from ._lib import (ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_FP16
                    ConvDesc, FusedSrc, check)
 
 __all__ = ["ConvDesc", "conv_desc", "conv_out_shape", "pack_weights_tc", "pack_weights_direct", "conv_tc", "conv_tc_fused", "conv_tc_fused_mode", "conv_tc_stem",
-           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "adam_hyper", "adam_step_dev", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "head_conv", "head_conv_pack", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
+           "conv_direct", "norm_stats", "norm_finalize", "stats_workspace", "norm_bwd", "conv_wgrad", "head_bwd_pack", "channel_sum", "adam_step", "adam_hyper", "adam_step_dev", "norm_apply", "stem_window_pack", "reflect_fold", "stem_window_bwd", "head_finish", "head_conv", "head_conv_pack", "stem_conv", "stem_conv_pack", "tile_gray_variance", "u8_to_f32", "f32_to_u8", "seg_finish", "LAUNCHES",
            "FMT_BF16", "FMT_FP16", "ACT_NONE", "ACT_RELU", "ACT_LRELU02", "ACT_TANH", "PAD_ZERO", "PAD_REFLECT"]
 
 # kernel-launch counter (bench.py reports gpu_launches from this)
@@ -383,6 +383,30 @@ def head_finish(z, bias, W, S, CO, act=ACT_TANH):
     assert WZ == W + S - 1 and z.shape[3] == 32
     out = torch.empty((N, CO, H, W), dtype=torch.float32, device=z.device)
     check(_lib.load().dlb_head_finish(_p(z), _p(bias), N, H, W, S, CO, act, _p(out), _stream()), "dlb_head_finish")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def stem_conv_pack(w):
+    """w fp32 [64, C<=4, 7, 7] (PyTorch layout) -> the packed split-precision weight image of dlb_stem_conv_fwd."""
+    w = w.detach().to(torch.float32).contiguous()
+    _need_cuda(w)
+    co, ci, R, S = w.shape
+    lib = _lib.load()
+    out = torch.empty((lib.dlb_stem_conv_weight_bytes(),), dtype=torch.uint8, device=w.device)
+    check(lib.dlb_stem_conv_pack_weights(_p(w), co, ci, R, S, _p(out), _stream()), "dlb_stem_conv_pack_weights")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def stem_conv(x_nchw, w_packed, bias, cout, border_mode, stats_ws=None):
+    """Pad(3) + Conv2d(C <= 4 -> 64, 7) (+ bias) from the fp32 NCHW input; fp32 NHWC [N, H, W, 64] out and, with stats_ws,
+    the partial statistics for norm_finalize.  One row-streaming tensor-core kernel (dlb_stem_conv_fwd)."""
+    _need_cuda(x_nchw, w_packed, bias)
+    N, Cc, H, W = x_nchw.shape
+    out = torch.empty((N, H, W, cout), dtype=torch.float32, device=x_nchw.device)
+    check(_lib.load().dlb_stem_conv_fwd(_p(x_nchw), N, Cc, H, W, _p(w_packed), _p(bias), cout, border_mode, _p(out), _p(stats_ws),
+                                        stats_ws.numel() * 4 if stats_ws is not None else 0, _stream()), "dlb_stem_conv_fwd")
     LAUNCHES["count"] += 1
     return out
 

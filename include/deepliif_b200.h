@@ -141,6 +141,21 @@ int dlb_head_conv_fwd(const float* x, const float* scale, const float* shift, in
                       const void* w_packed, const float* bias, int CO, int border_mode, int out_act, float* y_nchw,
                       dlb_stream_t stream);
 
+/* ---- generator stem in one kernel --------------------------------------------------------------------------
+ * Replaces nn.ReflectionPad2d(3) | nn.ZeroPad2d(3) + nn.Conv2d(C, 64, 7) (reference networks.py:386-397) on the tensor
+ * cores, from the fp32 NCHW network input [N, C <= 4, H, W]:
+ *   y[n, h, w, co] = bias[co] + sum_{c,kh,kw} pad(x)[n, c, h+kh-3, w+kw-3] * w[co, c, kh, kw]        fp32 NHWC [N, H, W, 64]
+ * and, when stats_ws is given (dlb_norm_stats_workspace bytes for (N, H*W, 64)), the partial normalisation statistics of y
+ * for dlb_norm_finalize (one slice per 128-pixel row tile).  Row-streaming kernel without an im2col operand: every input
+ * pixel is one 16-byte slot [hi(c), lo(c)] in shared memory and the MMA reads the horizontal filter window of an output
+ * pixel in place through a non-swizzled K-major descriptor with overlapping core matrices (LBO 16 B, SBO 128 B);
+ * split precision in one pass (128 accumulator columns, halves added in the epilogue).  Needs H, W >= 8.
+ * dlb_stem_conv_pack_weights: w fp32 [64][C][7][7] (PyTorch layout) -> dlb_stem_conv_weight_bytes() bytes, once per model. */
+size_t dlb_stem_conv_weight_bytes(void);
+int dlb_stem_conv_pack_weights(const float* w, int Cout, int C, int R, int S, void* out, dlb_stream_t stream);
+int dlb_stem_conv_fwd(const float* x_nchw, int N, int C, int H, int W, const void* w_packed, const float* bias, int Cout,
+                      int border_mode, float* y, void* stats_ws, size_t stats_ws_bytes, dlb_stream_t stream);
+
 /* fp32 CUDA-core convolution for the layers tensor cores cannot tile (Cin = 3 stem, networks.py:386-397;
  * Cout = 3 head + Tanh, :438-444; PatchGAN first/last convs, :638, :659).  Fuses the producer's
  * normalisation + activation on the input side: x' = act_in(x * in_scale[n,c] + in_shift[n,c]) (zero /

@@ -381,3 +381,40 @@ def test_head_conv_stream_vs_fp64_reference(ops, case, out_act):
     print(f"head_conv {case} {out_act}: max|d| {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
     assert y.shape == (N, CO, H, W)
     assert err <= 5e-5
+
+
+STEM_CASES = [
+    # N, C, H, W, border, bias
+    (1, 3, 8, 8, "zero", True),
+    (2, 3, 16, 40, "reflect", True),
+    (3, 3, 33, 130, "zero", False),                 # two column strips, CTA ranges spanning strips / images
+    (2, 4, 37, 300, "reflect", True),               # 4 input channels, three strips, odd height
+    (1, 1, 64, 128, "reflect", False),
+    (1, 3, 128, 256, "zero", True),
+]
+
+
+@pytest.mark.parametrize("case", STEM_CASES, ids=lambda c: f"n{c[0]}_c{c[1]}_{c[2]}x{c[3]}_{c[4]}")
+def test_stem_conv_stream_vs_fp64_reference_and_its_statistics(ops, case):
+    """dlb_stem_conv_fwd (row-streaming stem: no-swizzle window operand, one-pass split precision) against Pad(3) +
+    Conv2d(C, 64, 7) in fp64: max-abs <= 3e-5 x max|ref| (147 products, fp32 accumulation); and the statistics slices it
+    writes finalize to the statistics of its stored output."""
+    N, C, H, W, border, with_bias = case
+    x = _rand((N, C, H, W), 101)
+    w = _rand((64, C, 7, 7), 102, 0.1)
+    b = _rand((64,), 103, 0.1) if with_bias else None
+    ref = F.conv2d(F.pad(x.double(), (3, 3, 3, 3), mode="reflect" if border == "reflect" else "constant"), w.double(),
+                   b.double() if with_bias else None)
+    wpk = ops.stem_conv_pack(w.cuda())
+    ws = ops.stats_workspace(N, H * W, 64, "cuda")
+    y = ops.stem_conv(x.cuda(), wpk, b.cuda() if with_bias else None, 64, ops.PAD_REFLECT if border == "reflect" else ops.PAD_ZERO,
+                      stats_ws=ws)
+    s1, h1 = ops.norm_finalize(ws, N, H * W, 64, None, None, False)
+    s2, h2 = ops.norm_stats(y, None, None, False)
+    torch.cuda.synchronize()
+    err = (nchw(y.cpu()).double() - ref).abs().max().item()
+    print(f"stem_conv {case}: max|d| {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
+    assert y.shape == (N, H, W, 64)
+    assert err <= 3e-5 * ref.abs().max().item()
+    assert (s1 - s2).abs().max().item() <= 2e-6 * s2.abs().max().item()
+    assert (h1 - h2).abs().max().item() <= 5e-6 * max(1.0, h2.abs().max().item())
