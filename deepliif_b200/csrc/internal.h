@@ -79,6 +79,10 @@ struct TcPhase : PhaseGeom {
 bool encode_tiled_map(CUtensorMap* map, const void* base, int is_bf16, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box);
 
+// fp32 tiled map (zero OOB fill / clipped stores); swizzle128: 128-byte swizzle (inner box extent 32 floats), else none.
+bool encode_f32_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle128 = 0);
+
 // Returns the phase's execution mode: 0 tap mode, 1 vertical strip (resident weights), 2 halo strip (fa only).
 int tc_plan_tiles(const PhaseGeom& g, int nsrc, const int* cin, int cout, int split, int n_tile_req, int* tile_w,
                   int* tile_h, int* tile_n, int* n_tile_out, int fa = 0, int allow_hp = 1);

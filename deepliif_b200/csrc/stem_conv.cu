@@ -13,7 +13,7 @@
 //   D[:, 0:64]  = x_hi*w_hi + x_lo*w_hi      D[:, 64:128] = x_hi*w_lo      out = D[:, 0:64] + D[:, 64:128]  (epilogue).
 // Per output row: 28 x tcgen05.mma M128 N128 K16.
 //
-// A CTA walks down a 128-pixel-wide column strip: 4 converter warps keep a 16-row ring of packed rows ahead of the MMA
+// A CTA walks down a 128-pixel-wide column strip: 2 converter warps keep a 16-row ring of packed rows ahead of the MMA
 // warp (3 x 134 floats per row: plain coalesced loads, zero / reflected border resolved here), the MMA warp issues a row
 // as soon as the rows r-3..r+3 are packed, 4 epilogue warps add the halves (+ bias), store 128 px x 64 ch fp32 NHWC and
 // write one statistics slice (count, sum, M2 about the slice mean per channel) per row tile.
@@ -28,21 +28,25 @@
 namespace dlb {
 namespace {
 
-constexpr int kScThreads = 448;                      // warp 0 weights, 1 MMA, 2-5 / 6-9 epilogue (even / odd rows), 10-13 converters
+constexpr int kScThreads = 384;                      // warp 0 weights, 1 MMA, 2-5 / 6-9 epilogue (even / odd rows), 10-11 converters
+                                                     // (384 threads: ptxas then allows 168 registers, the epilogue keeps 64 sums live)
 constexpr int kScTW = 128;
 constexpr int kScS = 7, kScHalo = 3;
 constexpr int kScSlots = 136;                        // slots per packed row: 128 + 7 window + 1
 constexpr uint32_t kScRowBytes = kScSlots * 16;      // 2176
 constexpr int kScNR = 16;                            // packed-row ring
-constexpr int kScConvWarps = 4;
+constexpr int kScConvWarps = 2;
 constexpr uint32_t kScWTile = 128 * 128;             // one kh weight tile: 128 rows (64 co x {main, w_lo}) x K = 64
 constexpr uint32_t kScWBytes = kScS * kScWTile;      // 114688
-constexpr uint32_t kScOffRing = kScWBytes;
+constexpr uint32_t kScTileBytes = 2 * 128 * 128;      // one output row tile: 2 halves of 32 channels x 128 px x 128 B (SW128)
+constexpr uint32_t kScOffTile = kScWBytes;           // [2 epilogue groups], 1024-byte aligned
+constexpr uint32_t kScOffRing = kScOffTile + 2 * kScTileBytes;
 constexpr uint32_t kScOffBar = kScOffRing + kScNR * kScRowBytes;
 constexpr uint32_t kScOffStat = kScOffBar + 512;
 constexpr uint32_t kScSmem = kScOffStat + 2 * (4 * 32 * 8 + 64) + 1024;
 
 struct StemParams {
+  CUtensorMap ymap;                // y as [N*H][W][64] fp32, box {32, 128, 1}, 128-byte swizzle (output tile stores)
   const float* x; const uint8_t* wpk; const float* bias; float* y;
   int N, C, H, W, border_mode, strips;
   long long rows_total;
@@ -92,7 +96,7 @@ __device__ __forceinline__ float sc_colsum32(float (&a)[32], int lane) {
   return a[0];
 }
 
-__global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const StemParams p) {
+__global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t sc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sW = smem;
@@ -184,6 +188,12 @@ __global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const StemPara
     const int px = q * 32 + lane;
     float2* st_x = st_x_all + grp * 128;
     float* st_n = st_n_all + grp * 16;
+    const bool leader = q == 0 && lane == 0;
+    uint8_t* const tile_ptr = smem + kScOffTile + grp * kScTileBytes;
+    const uint32_t tile = smem_u32(tile_ptr);
+    auto group_sync = [&]() {
+      if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+    };
     uint32_t ot = 0;
     long long cur = beg; Piece pc;
     while (next_piece(p, cur, end, pc)) {
@@ -197,67 +207,95 @@ __global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const StemPara
         mbar_wait_sleep(&tfull[t], (ot >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 128u;
-        float* const yp = p.y + ((static_cast<long long>(pc.n) * p.H + r) * p.W + col) * 64;
         const long long st_row = static_cast<long long>(pc.n) * p.st_S_cap + static_cast<long long>(r) * p.strips + pc.s;
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
+        // both 32-channel groups are summed into registers first and the accumulator is handed back before the stores and
+        // the statistics butterflies, so the MMAs of row r + 2 start ~2k cycles earlier
+        float a0[32], a1[32];
+        {
           uint32_t v[32], v2[32];
-          tmem_ld_32x32(taddr + c, v);
-          tmem_ld_32x32(taddr + 64 + c, v2);
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_32x32(taddr + 64, v2);
           tmem_ld_wait();
-          if (c == 32) {                       // both halves of this accumulator are in registers: hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[t]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a0[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          tmem_ld_32x32(taddr + 32, v);
+          tmem_ld_32x32(taddr + 96, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a1[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[t]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + 32 + j));
+            a0[j] += b0.x; a0[j + 1] += b0.y; a0[j + 2] += b0.z; a0[j + 3] += b0.w;
+            a1[j] += b1.x; a1[j + 1] += b1.y; a1[j + 2] += b1.z; a1[j + 3] += b1.w;
           }
-          float a[32];
+        }
+        // output tile -> shared memory in the layout of a 128-byte-swizzled TMA box (row = pixel, 16-byte chunk j of the row at
+        // j ^ (px & 7): four wavefronts per warp store), then ONE elected thread stores both halves with TMA: 128-byte lines
+        // instead of 2048 scattered 16-byte sectors per row tile through the LSU (measured: the LSU was the stem's bound)
+        if (leader) bulk_wait_group_read0();                  // the previous tile of this group has left shared memory
+        group_sync();
+        {
+          const uint32_t rowa = tile + static_cast<uint32_t>(px) * 128u, sw = static_cast<uint32_t>(px & 7);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c + j));
-              a[j] += b.x; a[j + 1] += b.y; a[j + 2] += b.z; a[j + 3] += b.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t off = ((static_cast<uint32_t>(j) ^ sw) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + off), "f"(a0[4 * j]), "f"(a0[4 * j + 1]),
+                         "f"(a0[4 * j + 2]), "f"(a0[4 * j + 3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + 16384u + off), "f"(a1[4 * j]), "f"(a1[4 * j + 1]),
+                         "f"(a1[4 * j + 2]), "f"(a1[4 * j + 3]) : "memory");
           }
-          if (valid) {
+        }
+        fence_proxy_async();
+        auto stats = [&](float (&a)[32], const int c, const bool first) {
+          float w[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + c + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+          for (int j = 0; j < 32; ++j) w[j] = valid ? a[j] : 0.f;
+          const float sum = sc_colsum32(w, lane);
+          const float mean = cntf > 0.f ? sum / cntf : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = a[j] - __shfl_sync(0xffffffffu, mean, j);
+            w[j] = valid ? d * d : 0.f;
           }
-          if (p.st_partial != nullptr) {
-            float w[32];
+          const float m2 = sc_colsum32(w, lane);
+          st_x[q * 32 + lane] = make_float2(sum, m2);
+          if (lane == 0) st_n[q] = cntf;
+          group_sync();
+          if (first && leader) {                               // every thread's tile writes are fenced and behind the barrier
+            tma_store_3d(&p.ymap, reinterpret_cast<const void*>(tile_ptr), 0, pc.c0, pc.n * p.H + r);
+            tma_store_3d(&p.ymap, reinterpret_cast<const void*>(tile_ptr + 16384), 32, pc.c0, pc.n * p.H + r);
+            bulk_commit_group();
+          }
+          if (q == 0) {
+            float nt = 0.f, st = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = valid ? a[j] : 0.f;
-            const float sum = sc_colsum32(w, lane);
-            const float mean = cntf > 0.f ? sum / cntf : 0.f;
+            for (int k = 0; k < 4; ++k) { nt += st_n[k]; st += st_x[k * 32 + lane].x; }
+            const float mt = nt > 0.f ? st / nt : 0.f;
+            float m2t = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = a[j] - __shfl_sync(0xffffffffu, mean, j);
-              w[j] = valid ? d * d : 0.f;
-            }
-            const float m2 = sc_colsum32(w, lane);
-            st_x[q * 32 + lane] = make_float2(sum, m2);
-            if (lane == 0) st_n[q] = cntf;
-            if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
-            if (q == 0) {
-              float nt = 0.f, st = 0.f;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { nt += st_n[k]; st += st_x[k * 32 + lane].x; }
-              const float mt = nt > 0.f ? st / nt : 0.f;
-              float m2t = 0.f;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (st_n[k] > 0.f) { const float d = st_x[k * 32 + lane].x / st_n[k] - mt; m2t += st_x[k * 32 + lane].y + st_n[k] * d * d; }
+            for (int k = 0; k < 4; ++k)
+              if (st_n[k] > 0.f) { const float d = st_x[k * 32 + lane].x / st_n[k] - mt; m2t += st_x[k * 32 + lane].y + st_n[k] * d * d; }
+            if (p.st_partial != nullptr) {
               p.st_partial[st_row * 64 + c + lane] = make_float2(st, m2t);
               if (c == 0 && lane == 0) p.st_cnt[st_row] = nt;
             }
-            if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
           }
-        }
+          group_sync();
+        };
+        stats(a0, 0, true);
+        stats(a1, 32, false);
       }
     }
+    if (leader) bulk_wait_group0();                           // the last tiles are in global memory before the CTA exits
   } else {
-    // ===================== converters: warp cw packs the rows seq = cw (mod 4) =====================
+    // ===================== converters: warp cw packs the rows seq = cw (mod 2) =====================
     const int cw = warp - 10;
     const bool refl = p.border_mode == DLB_PAD_REFLECT;
     const long long plane = static_cast<long long>(p.H) * p.W;
@@ -293,7 +331,7 @@ __global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const StemPara
             v[k][ch] = (src[k] >= 0 && ch < p.C && lane + 32 * k < kScSlots) ? __ldg(xr + ch * plane + src[k]) : 0.f;
         }
         const uint32_t slot = sq % kScNR;
-        mbar_wait(&afree[slot], ((sq / kScNR) & 1u) ^ 1u);
+        mbar_wait_sleep(&afree[slot], ((sq / kScNR) & 1u) ^ 1u);     // far ahead of the MMAs most of the time: sleep, not poll
         const uint32_t rowa = smem_u32(sR + slot * kScRowBytes);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -359,7 +397,8 @@ extern "C" int dlb_stem_conv_fwd(const float* x_nchw, int N, int C, int H, int W
   if (Cout != 64 || C < 1 || C > 4) return set_error("dlb_stem_conv_fwd: needs C <= 4 and Cout == 64");
   if (H < 8 || W < 8 || N < 1) return set_error("dlb_stem_conv_fwd: needs H, W >= 8");
   if (border_mode != DLB_PAD_ZERO && border_mode != DLB_PAD_REFLECT) return set_error("dlb_stem_conv_fwd: bad border mode");
-  if (reinterpret_cast<uintptr_t>(w_packed) & 15) return set_error("dlb_stem_conv_fwd: w_packed must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return set_error("dlb_stem_conv_fwd: w_packed and y must be 16-byte aligned");
   int sms = 0;
   if (int rc = device_num_sms(&sms)) return rc;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(stem_conv_kernel), static_cast<int>(kScSmem), kSlotStemConv)) return rc;
@@ -369,6 +408,12 @@ extern "C" int dlb_stem_conv_fwd(const float* x_nchw, int N, int C, int H, int W
   p.N = N; p.C = C; p.H = H; p.W = W; p.border_mode = border_mode;
   p.strips = (W + kScTW - 1) / kScTW;
   p.rows_total = static_cast<long long>(N) * p.strips * H;
+  {
+    const uint64_t dims[3] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(N) * H};
+    const uint64_t strides[2] = {256, static_cast<uint64_t>(W) * 256};
+    const uint32_t box[3] = {32, 128, 1};
+    if (!encode_f32_map(&p.ymap, y, 3, dims, strides, box, 1)) return DLB_ERR_INVALID;
+  }
   if (stats_ws != nullptr) {
     const StatsLayout L = stats_layout(N, H * W, Cout);
     if (stats_ws_bytes < L.total) return set_error("dlb_stem_conv_fwd: statistics workspace too small");
