@@ -111,6 +111,12 @@ struct alignas(64) TcParams {
   // global-load latency sits inside the conversion.  Zero border only (TMA out-of-bounds fill = the zero padding).
   int vt, vt_half_rows;
   CUtensorMap a_f32;
+  // epilogue through shared memory, behind the stage ring at ets_off.  ets == 1: one 16 KB transpose buffer, the epilogue warps
+  // copy it out with coalesced stores.  ets == 2: two buffers, one thread stores each as a TMA box: y_map[a] = the fp32 output of
+  // accumulator a as a tiled map {cout, OW, OH, N} (pixel strides = the phase's ys_w / ys_h), box {32, tile_w, tile_h, tile_n},
+  // 128-byte swizzle — nothing of the store touches the LSU, which the fused-operand converters need for their loads.
+  CUtensorMap y_map[4];
+  int ets, ets_off;
   // halo-strip mode with TMA staging (ht): a dedicated producer thread (warp 14) streams the fp32 strip of every chunk
   // (box 64 ch x cols x rows) into a two-slot staging ring; the converters transform smem -> smem.  This is what makes the
   // fused operand pay off for layers with little MMA work per strip (ConvTranspose phases).  Single plain source, zero border.
@@ -553,6 +559,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
     // ===================== epilogue: TMEM -> registers -> (+bias) -> fp32 NHWC =====================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_ph = 0;
+    const int ets_lw = 31 - __clz(p.tile_w), ets_lh = 31 - __clz(p.tile_h);
+    uint32_t ets_g = 0;                               // 32-channel groups written so far (ets == 2: buffer ets_g & 1)
     const int m = q * 32 + lane;
     const int w_l = m % p.tile_w;
     const int h_l = (m / p.tile_w) % p.tile_h;
@@ -590,7 +598,95 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
           }
         }
-        if (valid && cvalid) {
+        if (p.ets) {
+          // ---- epilogue through shared memory: a thread owns one pixel (256 B .. 1 KB apart from its neighbours'), so direct
+          // stores are 32 half-used sectors per warp instruction and the LSU becomes the bound of every layer with little MMA
+          // work per output byte (measured: ~2 cycles per sector, 2k cycles per 32-channel group).  The group is transposed
+          // through one 16 KB buffer instead (row = pixel m, 16-byte chunk j at j ^ (m & 7): conflict-free both ways), stored
+          // as full 128-byte lines, and its statistics are taken from the same buffer (lane = channel: 32 conflict-free
+          // loads, register adds) instead of two 31-shuffle butterflies.
+          uint8_t* const bufp = smem + p.ets_off + (p.ets == 2 ? (ets_g & 1u) * 16384u : 0u);
+          const uint32_t buf = smem_u32(bufp);
+          ++ets_g;
+          if (p.ets == 2) {
+            if (q == 0 && lane == 0) bulk_wait_group_read1();          // the TMA store that last used this buffer has read it
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+          }
+          const uint32_t rowa = buf + static_cast<uint32_t>(m) * 128u, sw = static_cast<uint32_t>(m & 7);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((static_cast<uint32_t>(j) ^ sw) << 4)), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+          if (p.ets == 2) fence_proxy_async();
+          asm volatile("bar.sync 3, 128;" ::: "memory");            // the whole group is in the buffer
+          if (p.ets == 2) {
+            if (q == 0 && lane == 0 && cvalid) {                      // out-of-range pixels / images are clipped by the tensor map
+              tma_store_4d(&p.y_map[ai], bufp, tc.cout0 + c, tc.w0, tc.h0, tc.n0);
+              bulk_commit_group();
+            }
+          } else if (cvalid) {
+            float* const yc = p.y + (p.nacc > 1 ? p.acc_ybase[ai] : p.y_base) + tc.cout0 + c + (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = q * 32 + i * 4 + (lane >> 3);
+              uint32_t x0, x1, x2, x3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                           : "r"(buf + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((lane & 7) ^ (row & 7)) << 4)) : "memory");
+              const int rw = row & (p.tile_w - 1), rh = (row >> ets_lw) & (p.tile_h - 1), rn = row >> (ets_lw + ets_lh);
+              const int n2 = tc.n0 + rn, h2 = tc.h0 + rh, w2 = tc.w0 + rw;
+              if (n2 < p.N && h2 < p.OH && w2 < p.OW)
+                *reinterpret_cast<uint4*>(yc + n2 * p.ys_n + h2 * p.ys_h + w2 * p.ys_w) = make_uint4(x0, x1, x2, x3);
+            }
+          }
+          if (p.st_partial != nullptr && cvalid) {
+            // lane = channel c + lane over this warp's 32 pixel rows (row & 7 == i & 7): (count, sum, M2 about the mean)
+            const uint32_t cb = buf + static_cast<uint32_t>(q * 32) * 128u + static_cast<uint32_t>(lane & 3) * 4u;
+            // the additions follow the tree of the shuffle butterfly (rows i and i + 16, then + 8, 4, 2, 1), so both epilogues
+            // produce bit-identical statistics and a tile's result does not depend on which one its launch shape selects
+            float xs[32], tr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cb + static_cast<uint32_t>(i) * 128u +
+                                                                    (static_cast<uint32_t>((lane >> 2) ^ (i & 7)) << 4)) : "memory");
+              xs[i] = x;
+              tr[i] = ((vmask >> i) & 1u) ? x : 0.f;
+            }
+#pragma unroll
+            for (int sp = 16; sp >= 1; sp >>= 1) {
+#pragma unroll
+              for (int i = 0; i < sp; ++i) tr[i] = tr[i] + tr[i + sp];
+            }
+            const float sum = tr[0];
+            const float cntf = static_cast<float>(__popc(vmask));
+            const float mean = cntf > 0.f ? sum / cntf : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float d = xs[i] - mean; tr[i] = ((vmask >> i) & 1u) ? d * d : 0.f; }
+#pragma unroll
+            for (int sp = 16; sp >= 1; sp >>= 1) {
+#pragma unroll
+              for (int i = 0; i < sp; ++i) tr[i] = tr[i] + tr[i + sp];
+            }
+            const float m2 = tr[0];
+            st_x[q][lane] = make_float2(sum, m2);
+            if (lane == 0) st_n[q] = cntf;
+          }
+          asm volatile("bar.sync 3, 128;" ::: "memory");            // buffer and partials read / written by everyone
+          if (p.st_partial != nullptr && cvalid && q == 0) {
+            float nt = 0.f, st = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { nt += st_n[k]; st += st_x[k][lane].x; }
+            const float mt = nt > 0.f ? st / nt : 0.f;
+            float m2t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (st_n[k] > 0.f) { const float d = st_x[k][lane].x / st_n[k] - mt; m2t += st_x[k][lane].y + st_n[k] * d * d; }
+            p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(st, m2t);
+            if (tc.cout0 == 0 && c == 0 && lane == 0) p.st_cnt[st_row] = nt;
+          }
+          // (the next group's first barrier orders this merge's reads of st_x before the next partials are written)
+          continue;
+        } else if (valid && cvalid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o;
@@ -642,6 +738,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
       }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
+    if (p.ets == 2 && q == 0 && lane == 0) bulk_wait_group0();   // the last boxes have left shared memory and reached global memory
   } else if (p.fa && warp < 14) {
     // ===================== operand converters (fused-operand mode) =====================
     // 256 threads; thread = (q: one float4 = 4 channels of the 64-channel chunk, pr: pixel row group).  A warp-wide
@@ -1366,7 +1463,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     for (int nb = 2; nb <= 4; ++nb) {
       const long long need = static_cast<long long>(nb) * p.planes * p.hs_plane_bytes +
                              (nb == 2 ? 2LL : 4LL) * p.planes * n_tile * 128 + 1024;
-      if (need <= kMaxDynSmem) p.hs_nbuf = nb;
+      if (need + 16384 + 1024 <= kMaxDynSmem) p.hs_nbuf = nb;       // room for the epilogue's transpose buffer (below)
     }
     for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - hs_dh0) * p.hs_cols + (ph.tap_dw[t] - hs_dw0)) * 128;
   }
@@ -1419,12 +1516,37 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   const int stage_bytes = use_hs ? p.planes * b_bytes
                                  : (use_vs ? p.planes * p.vs_rows * tile_w * 128 + (ph.fa == 2 ? kStemPatchBytes : 0)
                                            : p.planes * (kABytes + b_bytes));
-  int stages = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes;
+  // epilogue through shared memory (statistics from the buffer): plane-fed launches copy the buffer out with coalesced stores
+  // (17 KB); fused-operand launches store it by TMA (33 KB), leaving the LSU to the converters.  Only where the buffers can be
+  // spared without making the pipeline shallower than 3 stages.  DLB_EPI_SMEM=0 switches it off, =1 plane-fed launches only.
+  static const int ets_env = []() { const char* e = getenv("DLB_EPI_SMEM"); return e != nullptr ? atoi(e) : 2; }();
+  int ets_mode = (ets_env >= 1 && !ph.fa) ? 1 : ((ets_env >= 2 && ph.fa) ? 2 : 0);
+  if ((ph.ys_w % 4) || (ph.ys_h % 4) || (ph.ys_n % 4) || (ph.cout % 32) || (p.nacc <= 1 && ph.y_base % 4)) ets_mode = 0;
+  for (int a = 0; a < p.nacc && p.nacc > 1; ++a) if (ph.acc_ybase[a] % 4) ets_mode = 0;
+  const int ets_need = ets_mode == 2 ? 2 * 16384 + 1024 : 16384 + 1024;
+  {
+    const int cap = ph.max_stages > 0 ? ph.max_stages : kMaxStages;
+    int s_without = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes; if (s_without > cap) s_without = cap;
+    int s_with = (kMaxDynSmem - 1024 - bres_bytes - ets_need) / stage_bytes; if (s_with > cap) s_with = cap;
+    if (s_with < 2 || (s_with < 3 && s_with < s_without)) ets_mode = 0;
+  }
+  int stages = (kMaxDynSmem - 1024 - bres_bytes - (ets_mode ? ets_need : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (ph.max_stages > 0 && stages > ph.max_stages) stages = ph.max_stages;
   if (stages < 2) return set_error("conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
-  const int smem_bytes = bres_bytes + stages * stage_bytes + 1024;
+  p.ets = ets_mode;
+  p.ets_off = ets_mode ? (bres_bytes + stages * stage_bytes + 1023) / 1024 * 1024 : 0;
+  if (ets_mode == 2) {
+    for (int a = 0; a < p.nacc; ++a) {
+      const long long base = p.nacc > 1 ? ph.acc_ybase[a] : ph.y_base;
+      const uint64_t dims[4] = {(uint64_t)ph.cout, (uint64_t)ph.OW, (uint64_t)ph.OH, (uint64_t)ph.N};
+      const uint64_t strides[3] = {(uint64_t)ph.ys_w * 4, (uint64_t)ph.ys_h * 4, (uint64_t)ph.ys_n * 4};
+      const uint32_t box[4] = {32, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_n};
+      if (!encode_f32_map(&p.y_map[a], ph.y + base, 4, dims, strides, box, 1)) return -1;
+    }
+  }
+  const int smem_bytes = (ets_mode ? p.ets_off + (ets_mode == 2 ? 2 : 1) * 16384 : bres_bytes + stages * stage_bytes) + 1024;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;
