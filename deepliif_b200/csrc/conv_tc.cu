@@ -48,7 +48,7 @@ constexpr int kThreadsFa = kThreads + 32 * kConvWarps + 32;   // + warp 14: fp32
 constexpr int kStemPatchBytes = 4 * 24 * 16 * 4;   // fused stem: fp32 input patch [4 ch][<= 24 rows][16 cols] per strip stage
 constexpr int kHsMaxPx = 192;          // halo-strip mode: at most this many strip pixels (3x3: 18 x 10 = 180; 2x2 taps: 17 x 9)
 constexpr int kSmemLimit = 232448;     // 227 KB per CTA (static + dynamic)
-constexpr int kStaticSmem = 1024;      // barriers (static __shared__), rounded up
+constexpr int kStaticSmem = 2560;      // barriers + the epilogue groups' statistics scratch (ptxas: 2352 B)
 constexpr int kMaxDynSmem = kSmemLimit - kStaticSmem - 1024;
 
 struct alignas(64) TcParams {
@@ -117,6 +117,9 @@ struct alignas(64) TcParams {
   // 128-byte swizzle — nothing of the store touches the LSU, which the fused-operand converters need for their loads.
   CUtensorMap y_map[4];
   int ets, ets_off;
+  // epi2: plane-fed launches carry a second group of four epilogue warps (warps 6-9); the 32-channel units of a tile alternate
+  // between the groups (own transpose buffer, statistics scratch and named barriers each)
+  int epi2;
   // halo-strip mode with TMA staging (ht): a dedicated producer thread (warp 14) streams the fp32 strip of every chunk
   // (box 64 ch x cols x rows) into a two-slot staging ring; the converters transform smem -> smem.  This is what makes the
   // fused operand pay off for layers with little MMA work per strip (ConvTranspose phases).  Single plain source, zero border.
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(8) uint64_t sfull_bar[2];    // vt mode: staging slot filled by TMA
   __shared__ __align__(8) uint64_t sempty_bar[2];   // vt mode: staging slot read by every converter warp
-  __shared__ float2 st_x[4][32];               // per-epilogue-warp (sum, M2) of one 32-channel group, merged per tile
-  __shared__ float st_n[4];
+  __shared__ float2 st_x_all[2][4][32];        // per epilogue group and warp: (sum, M2) of one 32-channel unit, merged per tile
+  __shared__ float st_n_all[2][4];
 
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
     }
     for (int b = 0; b < 2; ++b) { mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], kConvWarps); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], CTA2 ? 8 : 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], (CTA2 || p.epi2) ? 8 : 4); }
     mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
@@ -555,9 +558,15 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 || (p.epi2 && warp < 10)) {
     // ===================== epilogue: TMEM -> registers -> (+bias) -> fp32 NHWC =====================
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;                  // epilogue group (1 only with epi2)
+    float2 (*st_x)[32] = st_x_all[grp];
+    float* st_n = st_n_all[grp];
+    auto group_sync = [&]() {                         // the four warps of this group (ids 2 / 3 are used by group 0's two paths)
+      if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+    };
     int acc = 0; uint32_t acc_ph = 0;
     const int ets_lw = 31 - __clz(p.tile_w), ets_lh = 31 - __clz(p.tile_h);
     uint32_t ets_g = 0;                               // 32-channel groups written so far (ets == 2: buffer ets_g & 1)
@@ -584,6 +593,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
       const long long st_row = static_cast<long long>(tc.n0) * p.st_S_cap + (p.nacc > 1 ? p.acc_slice[ai] : p.st_slice_base) +
                                (th_i * p.tiles_w + tw_i);
       for (int c = 0; c < p.n_tile; c += 32) {
+        if (p.epi2 && (((ai * (p.n_tile >> 5) + (c >> 5)) & 1) != grp)) continue;      // the other group's unit
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
@@ -605,12 +615,12 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
           // through one 16 KB buffer instead (row = pixel m, 16-byte chunk j at j ^ (m & 7): conflict-free both ways), stored
           // as full 128-byte lines, and its statistics are taken from the same buffer (lane = channel: 32 conflict-free
           // loads, register adds) instead of two 31-shuffle butterflies.
-          uint8_t* const bufp = smem + p.ets_off + (p.ets == 2 ? (ets_g & 1u) * 16384u : 0u);
+          uint8_t* const bufp = smem + p.ets_off + (p.ets == 2 ? (ets_g & 1u) * 16384u : static_cast<uint32_t>(grp) * 16384u);
           const uint32_t buf = smem_u32(bufp);
           ++ets_g;
           if (p.ets == 2) {
             if (q == 0 && lane == 0) bulk_wait_group_read1();          // the TMA store that last used this buffer has read it
-            asm volatile("bar.sync 3, 128;" ::: "memory");
+            group_sync();
           }
           const uint32_t rowa = buf + static_cast<uint32_t>(m) * 128u, sw = static_cast<uint32_t>(m & 7);
 #pragma unroll
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((static_cast<uint32_t>(j) ^ sw) << 4)), "r"(v[4 * j]),
                          "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
           if (p.ets == 2) fence_proxy_async();
-          asm volatile("bar.sync 3, 128;" ::: "memory");            // the whole group is in the buffer
+          group_sync();            // the whole group is in the buffer
           if (p.ets == 2) {
             if (q == 0 && lane == 0 && cvalid) {                      // out-of-range pixels / images are clipped by the tensor map
               tma_store_4d(&p.y_map[ai], bufp, tc.cout0 + c, tc.w0, tc.h0, tc.n0);
@@ -671,7 +681,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             st_x[q][lane] = make_float2(sum, m2);
             if (lane == 0) st_n[q] = cntf;
           }
-          asm volatile("bar.sync 3, 128;" ::: "memory");            // buffer and partials read / written by everyone
+          group_sync();            // buffer and partials read / written by everyone
           if (p.st_partial != nullptr && cvalid && q == 0) {
             float nt = 0.f, st = 0.f;
 #pragma unroll
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
           const float m2 = warp_colsum32(a, lane);
           st_x[q][lane] = make_float2(sum, m2);
           if (lane == 0) st_n[q] = cntf;
-          asm volatile("bar.sync 2, 128;" ::: "memory");            // the four epilogue warps
+          if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");            // the four epilogue warps
           if (q == 0) {
             // merge in warp-quarter order (fixed => deterministic): n = sum n_q, S = sum S_q, M2 = sum (M2_q + n_q (mean_q - mean)^2)
             float nt = 0.f, st = 0.f;
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             p.st_partial[st_row * p.cout_total + tc.cout0 + c + lane] = make_float2(st, m2t);
             if (tc.cout0 == 0 && c == 0 && lane == 0) p.st_cnt[st_row] = nt;
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");            // st_x is reused by the next channel group
+          if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");            // st_x is reused by the next channel group
         }
       }
       }
@@ -1452,6 +1462,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - dh0) * p.hs_cols + (ph.tap_dw[t] - dw0)) * 128;
     }
   }
+  const bool epi2_wanted = []() { const char* e = getenv("DLB_EPI2"); return e != nullptr && e[0] == '1'; }();
   if (use_hs && !ph.fa) {
     // plane-fed halo strips: the strip of a chunk is one TMA box per plane (tensor maps above)
     p.hs = 1; p.hp = 1;
@@ -1463,7 +1474,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     for (int nb = 2; nb <= 4; ++nb) {
       const long long need = static_cast<long long>(nb) * p.planes * p.hs_plane_bytes +
                              (nb == 2 ? 2LL : 4LL) * p.planes * n_tile * 128 + 1024;
-      if (need + 16384 + 1024 <= kMaxDynSmem) p.hs_nbuf = nb;       // room for the epilogue's transpose buffer (below)
+      if (need + (epi2_wanted ? 2 : 1) * 16384 + 1024 <= kMaxDynSmem) p.hs_nbuf = nb;   // room for the epilogue's transpose buffer(s) (below)
     }
     for (int t = 0; t < ph.ntaps; ++t) p.hs_off[t] = ((ph.tap_dh[t] - hs_dh0) * p.hs_cols + (ph.tap_dw[t] - hs_dw0)) * 128;
   }
@@ -1523,7 +1534,11 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   int ets_mode = (ets_env >= 1 && !ph.fa) ? 1 : ((ets_env >= 2 && ph.fa) ? 2 : 0);
   if ((ph.ys_w % 4) || (ph.ys_h % 4) || (ph.ys_n % 4) || (ph.cout % 32) || (p.nacc <= 1 && ph.y_base % 4)) ets_mode = 0;
   for (int a = 0; a < p.nacc && p.nacc > 1; ++a) if (ph.acc_ybase[a] % 4) ets_mode = 0;
-  const int ets_need = ets_mode == 2 ? 2 * 16384 + 1024 : 16384 + 1024;
+  // second epilogue group: measured +0.4 % on the headline step and on UNet-256 (the narrow layers are bound by the MMA issue
+  // rate, ~60 cycles per N = 64 MMA, not by their epilogue), so it is off unless DLB_EPI2=1
+  static const bool epi2_env = []() { const char* e = getenv("DLB_EPI2"); return e != nullptr && e[0] == '1'; }();
+  p.epi2 = (epi2_env && !ph.fa && p.nacc * (n_tile / 32) >= 2) ? 1 : 0;
+  const int ets_need = (ets_mode == 2 || p.epi2) ? 2 * 16384 + 1024 : 16384 + 1024;
   {
     const int cap = ph.max_stages > 0 ? ph.max_stages : kMaxStages;
     int s_without = (kMaxDynSmem - 1024 - bres_bytes) / stage_bytes; if (s_without > cap) s_without = cap;
@@ -1546,7 +1561,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
       if (!encode_f32_map(&p.y_map[a], ph.y + base, 4, dims, strides, box, 1)) return -1;
     }
   }
-  const int smem_bytes = (ets_mode ? p.ets_off + (ets_mode == 2 ? 2 : 1) * 16384 : bres_bytes + stages * stage_bytes) + 1024;
+  const int smem_bytes = (ets_mode ? p.ets_off + ((ets_mode == 2 || p.epi2) ? 2 : 1) * 16384 : bres_bytes + stages * stage_bytes) + 1024;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_c;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (ph.max_ctas > 0 && grid > ph.max_ctas) grid = ph.max_ctas;
@@ -1572,12 +1587,13 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     }
     return 0;
   }
-  conv_tc_kernel_t<false><<<grid, ph.fa ? kThreadsFa : kThreads, smem_bytes, stream>>>(p);
+  const int threads = ph.fa ? kThreadsFa : (p.epi2 ? kThreads + 128 : kThreads);
+  conv_tc_kernel_t<false><<<grid, threads, smem_bytes, stream>>>(p);
   {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       char buf[200];
-      snprintf(buf, sizeof(buf), "conv_tc_kernel launch (grid %d, threads %d, smem %d): %s", grid, ph.fa ? kThreadsFa : kThreads,
+      snprintf(buf, sizeof(buf), "conv_tc_kernel launch (grid %d, threads %d, smem %d): %s", grid, threads,
                smem_bytes, cudaGetErrorString(e));
       set_error(buf);
       return DLB_ERR_CUDA;
