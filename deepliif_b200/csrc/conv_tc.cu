@@ -432,30 +432,20 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
               const uint32_t d_tmem = d_set + static_cast<uint32_t>(a_i * p.n_tile);
               uint32_t accumulate = (started >> a_i) & 1u;
               started |= 1u << a_i;
-#pragma unroll
-              for (int k = 0; k < kKC / 16; ++k) {
-                const uint64_t da_hi = make_sw128_kmajor_desc_sbo(strip_hi + aoff + k * 32, sbo);
-                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
-                if constexpr (CTA2) {
-                  // M = 256 across the pair: the hardware takes rows 0-127 of A (and of B) from this CTA's shared memory and
-                  // rows 128-255 from the same offsets in the peer's
-                  if (p.planes == 2) {
-                    const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
-                    const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                    umma_f16_2sm_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                    umma_f16_2sm_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
-                    umma_f16_2sm_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
-                  } else {
-                    umma_f16_2sm_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                  }
-                } else if (p.planes == 2) {
-                  const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff + k * 32, sbo);
-                  const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                  umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                  umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
-                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
+              {
+                // one K = 64 chunk of this tap: four K = 16 steps issued from one asm block (ptx.cuh)
+                const uint64_t da_hi = make_sw128_kmajor_desc_sbo(strip_hi + aoff, sbo);
+                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = make_sw128_kmajor_desc_sbo(strip_lo + aoff, sbo);
+                  const uint64_t db_lo = make_sw128_kmajor_desc(b_lo);
+                  // CTA2: M = 256 across the pair — the hardware takes rows 0-127 of A (and of B) from this CTA's shared memory
+                  // and rows 128-255 from the same offsets in the peer's
+                  if constexpr (CTA2) umma_f16_2sm_k64x3_elect(d_tmem, da_hi, da_lo, db_hi, db_lo, p.idesc, accumulate);
+                  else umma_f16_k64x3_elect(d_tmem, da_hi, da_lo, db_hi, db_lo, p.idesc, accumulate);
                 } else {
-                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                  if constexpr (CTA2) umma_f16_2sm_k64_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                  else umma_f16_k64_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                 }
                 accumulate = 1;
               }
@@ -485,19 +475,14 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
               const uint32_t aoff = static_cast<uint32_t>(p.vs_row_off[tap]) * p.tile_w * 128u;   // whole image rows
               const uint32_t b_hi = bres + static_cast<uint32_t>((tap * kch0 + kc) * p.planes) * b_bytes;
               const uint32_t b_lo = b_hi + b_bytes;
-#pragma unroll
-              for (int k = 0; k < kKC / 16; ++k) {
-                const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + aoff + k * 32);
-                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
-                if (p.planes == 2) {
-                  const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + aoff + k * 32);
-                  const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-                  umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);
-                  umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
-                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
-                } else {
-                  umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                }
+              {
+                const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + aoff);
+                const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+                if (p.planes == 2)
+                  umma_f16_k64x3_elect(d_tmem, da_hi, make_sw128_kmajor_desc(a_lo + aoff), db_hi, make_sw128_kmajor_desc(b_lo), p.idesc,
+                                       accumulate);
+                else
+                  umma_f16_k64_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -520,19 +505,13 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
           const uint32_t a_lo = a_hi + kABytes;
           const uint32_t b_hi = a_hi + p.planes * kABytes;
           const uint32_t b_lo = b_hi + b_bytes;
-#pragma unroll
-          for (int k = 0; k < kKC / 16; ++k) {
-            const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
-            const uint64_t db_hi = make_sw128_kmajor_desc(b_hi + k * 32);
-            if (p.planes == 2) {
-              const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
-              const uint64_t db_lo = make_sw128_kmajor_desc(b_lo + k * 32);
-              umma_f16_elect(d_tmem, da_lo, db_hi, p.idesc, accumulate);   // small terms first
-              umma_f16_elect(d_tmem, da_hi, db_lo, p.idesc, 1);
-              umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, 1);
-            } else {
-              umma_f16_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-            }
+          {
+            const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+            const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+            if (p.planes == 2)                      // small terms first inside every K = 16 step
+              umma_f16_k64x3_elect(d_tmem, da_hi, make_sw128_kmajor_desc(a_lo), db_hi, make_sw128_kmajor_desc(b_lo), p.idesc, accumulate);
+            else
+              umma_f16_k64_elect(d_tmem, da_hi, db_hi, p.idesc, accumulate);
             accumulate = 1;
           }
           umma_commit_elect(&empty_bar[s]);                 // smem stage free once these MMAs retire

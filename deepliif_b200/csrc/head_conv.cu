@@ -91,6 +91,32 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
+// One horizontal tap (K = 64: four K = 16 steps) from one asm block: a_hi x [w_hi | w_lo] (N = 64) then a_lo x w_hi (N = 32, the
+// first 32 rows of the same weight tile) per step; the descriptors cross to uniform registers once and step by 32 bytes there.
+__device__ __forceinline__ void hc_mma_tap(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t w, uint32_t idesc64, uint32_t idesc32,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 ah, al, wb;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 ah, %1;\n\tmov.b64 al, %2;\n\tmov.b64 wb, %3;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, wb, %4, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, wb, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 wb, wb, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, wb, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, wb, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 wb, wb, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, wb, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, wb, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 wb, wb, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, wb, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, wb, %5, t;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(w), "r"(idesc64), "r"(idesc32), "r"(accumulate)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(kHcThreads, 1) head_conv_kernel(const HeadParams p) {
   extern __shared__ uint8_t hc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -162,16 +188,11 @@ __global__ void __launch_bounds__(kHcThreads, 1) head_conv_kernel(const HeadPara
           const uint64_t da_hi = make_sw128_kmajor_desc_sbo(smem_u32(sA + b * 2 * kHcPlaneBytes), 1024);
           const uint64_t da_lo = da_hi + (kHcPlaneBytes >> 4);
           const uint32_t d_tmem = tmem_base + t * 64u;
-#pragma unroll 1
-          for (int kw = 0; kw < kHcS; ++kw) {
-            const uint64_t ah = da_hi + ((kw * 128) >> 4), al = da_lo + ((kw * 128) >> 4), wb = db0 + ((kw * kHcWTile) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // a_hi x [w_hi | w_lo] -> columns 0..63; a_lo x w_hi -> columns 0..31 (the epilogue adds the two halves)
-              umma_f16_elect(d_tmem, ah + 2 * k, wb + 2 * k, idesc64, (kw | k) != 0);
-              umma_f16_elect(d_tmem, al + 2 * k, wb + 2 * k, idesc32, 1);
-            }
-          }
+          for (int kw = 0; kw < kHcS; ++kw)
+            // a_hi x [w_hi | w_lo] -> columns 0..63; a_lo x w_hi -> columns 0..31 (the epilogue adds the two halves)
+            hc_mma_tap(d_tmem, da_hi + ((kw * 128) >> 4), da_lo + ((kw * 128) >> 4), db0 + ((kw * kHcWTile) >> 4), idesc64, idesc32,
+                       kw != 0);
           umma_commit_elect(&afree[b]);
           umma_commit_elect(&tfull[t]);
         }

@@ -184,6 +184,99 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a,
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One K = 64 chunk (four K = 16 steps: start-address fields + 2 = 32 bytes each) issued from ONE asm block: the operands cross
+// from vector to uniform registers once per block instead of once per MMA, and the descriptor increments stay in the
+// uniform datapath.  x3: split precision (lo*hi, hi*lo, hi*hi per step, small terms first); x1: single plane.
+__device__ __forceinline__ void umma_f16_k64x3_elect(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+      uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 ah, al, bh, bl;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 ah, %1;\n\tmov.b64 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm_k64x3_elect(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+      uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 ah, al, bh, bl;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 ah, %1;\n\tmov.b64 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "add.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\tadd.s64 bh, bh, 2;\n\tadd.s64 bl, bl, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bl, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, t;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_k64_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 a, %1;\n\tmov.b64 b, %2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, p;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm_k64_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 a, %1;\n\tmov.b64 b, %2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, t;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, t;\n\t"
+      "add.s64 a, a, 2;\n\tadd.s64 b, b, 2;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, t;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"

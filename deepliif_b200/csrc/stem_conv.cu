@@ -163,11 +163,8 @@ __global__ void __launch_bounds__(kScThreads, 1) stem_conv_kernel(const __grid_c
           const uint32_t sq = seq0 + static_cast<uint32_t>(ri - pc.ia);
           const uint64_t da = da0 + (((sq % kScNR) * kScRowBytes) >> 4);
           const uint64_t db = db0 + ((kh * kScWTile) >> 4);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            umma_f16_elect(d_tmem, da + 2 * j, db + 2 * j, idesc, accumulate);
-            accumulate = 1;
-          }
+          umma_f16_k64_elect(d_tmem, da, db, idesc, accumulate);   // the four K = 16 steps (two taps each) from one asm block
+          accumulate = 1;
         }
         umma_commit_elect(&tfull[t]);
         // rows above r - 3 are not read again: release row r - 3 (all remaining rows after the last output row)
