@@ -561,6 +561,19 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
       mbar_wait_sleep(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      // ets == 1: the eight buffer rows this thread copies out (row_i = q*32 + i*4 + lane/8): element offset of their pixel in y
+      // and whether it lies inside the output — once per tile, not per 32-channel unit (host guarantees 32-bit offsets)
+      uint32_t co_off[8]; uint32_t co_ok = 0;
+      if (p.ets == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = q * 32 + i * 4 + (lane >> 3);
+          const int rw = row & (p.tile_w - 1), rh = (row >> ets_lw) & (p.tile_h - 1), rn = row >> (ets_lw + ets_lh);
+          const int n2 = tc.n0 + rn, h2 = tc.h0 + rh, w2 = tc.w0 + rw;
+          co_off[i] = static_cast<uint32_t>(n2 * p.ys_n + h2 * p.ys_h + w2 * p.ys_w);
+          if (t < total_tiles && n2 < p.N && h2 < p.OH && w2 < p.OW) co_ok |= 1u << i;
+        }
+      }
       // slice of the statistics workspace this warp's 32 rows belong to (tile_n == 1 when stats are fused)
       const int th_i = tc.h0 / p.tile_h, tw_i = tc.w0 / p.tile_w;
       for (int ai = 0; ai < p.nacc; ++ai) {                // merged ConvTranspose phases: one accumulator per output parity
@@ -601,10 +614,11 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             if (q == 0 && lane == 0) bulk_wait_group_read1();          // the TMA store that last used this buffer has read it
             group_sync();
           }
-          const uint32_t rowa = buf + static_cast<uint32_t>(m) * 128u, sw = static_cast<uint32_t>(m & 7);
+          // the buffer is 1024-byte aligned, so "row base + swizzled chunk" is an XOR of bits 4-6: one LOP3 per store
+          const uint32_t rowx = (buf + static_cast<uint32_t>(m) * 128u) ^ (static_cast<uint32_t>(m & 7) << 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((static_cast<uint32_t>(j) ^ sw) << 4)), "r"(v[4 * j]),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowx ^ (static_cast<uint32_t>(j) << 4)), "r"(v[4 * j]),
                          "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
           if (p.ets == 2) fence_proxy_async();
           group_sync();            // the whole group is in the buffer
@@ -615,29 +629,31 @@ __global__ void __launch_bounds__(kThreadsFa, 1) conv_tc_kernel_t(const __grid_c
             }
           } else if (cvalid) {
             float* const yc = p.y + (p.nacc > 1 ? p.acc_ybase[ai] : p.y_base) + tc.cout0 + c + (lane & 7) * 4;
+            // row_i & 7 = ((i & 1) * 4 + lane / 8): two swizzle phases, the rest of the address is an immediate
+            const uint32_t cbase = buf + static_cast<uint32_t>(q * 32 + (lane >> 3)) * 128u;
+            const uint32_t ce = cbase + (static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4);
+            const uint32_t cod = cbase + (static_cast<uint32_t>((lane & 7) ^ (4 + (lane >> 3))) << 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = q * 32 + i * 4 + (lane >> 3);
               uint32_t x0, x1, x2, x3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                           : "r"(buf + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((lane & 7) ^ (row & 7)) << 4)) : "memory");
-              const int rw = row & (p.tile_w - 1), rh = (row >> ets_lw) & (p.tile_h - 1), rn = row >> (ets_lw + ets_lh);
-              const int n2 = tc.n0 + rn, h2 = tc.h0 + rh, w2 = tc.w0 + rw;
-              if (n2 < p.N && h2 < p.OH && w2 < p.OW)
-                *reinterpret_cast<uint4*>(yc + n2 * p.ys_n + h2 * p.ys_h + w2 * p.ys_w) = make_uint4(x0, x1, x2, x3);
+                           : "r"(((i & 1) ? cod : ce) + static_cast<uint32_t>(i) * 512u) : "memory");
+              if ((co_ok >> i) & 1u) *reinterpret_cast<uint4*>(yc + co_off[i]) = make_uint4(x0, x1, x2, x3);
             }
           }
           if (p.st_partial != nullptr && cvalid) {
             // lane = channel c + lane over this warp's 32 pixel rows (row & 7 == i & 7): (count, sum, M2 about the mean)
-            const uint32_t cb = buf + static_cast<uint32_t>(q * 32) * 128u + static_cast<uint32_t>(lane & 3) * 4u;
+            // row q*32 + i, chunk (lane / 4) ^ (i & 7): the XOR touches bits 4-6 only, the row offset i * 128 stays an immediate
+            const uint32_t cb = buf + static_cast<uint32_t>(q * 32) * 128u + (static_cast<uint32_t>(lane >> 2) << 4) +
+                                static_cast<uint32_t>(lane & 3) * 4u;
             // the additions follow the tree of the shuffle butterfly (rows i and i + 16, then + 8, 4, 2, 1), so both epilogues
             // produce bit-identical statistics and a tile's result does not depend on which one its launch shape selects
             float xs[32], tr[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float x;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cb + static_cast<uint32_t>(i) * 128u +
-                                                                    (static_cast<uint32_t>((lane >> 2) ^ (i & 7)) << 4)) : "memory");
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"((cb ^ (static_cast<uint32_t>(i & 7) << 4)) + static_cast<uint32_t>(i) * 128u)
+                           : "memory");
               xs[i] = x;
               tr[i] = ((vmask >> i) & 1u) ? x : 0.f;
             }
@@ -1513,6 +1529,8 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
   int ets_mode = (ets_env >= 1 && !ph.fa) ? 1 : ((ets_env >= 2 && ph.fa) ? 2 : 0);
   if ((ph.ys_w % 4) || (ph.ys_h % 4) || (ph.ys_n % 4) || (ph.cout % 32) || (p.nacc <= 1 && ph.y_base % 4)) ets_mode = 0;
   for (int a = 0; a < p.nacc && p.nacc > 1; ++a) if (ph.acc_ybase[a] % 4) ets_mode = 0;
+  // the copy-out keeps 32-bit element offsets per thread
+  if (ets_mode == 1 && (static_cast<long long>(ph.N) + 1) * ph.ys_n + static_cast<long long>(ph.OH + 32) * ph.ys_h >= (1LL << 31)) ets_mode = 0;
   // second epilogue group: measured +0.4 % on the headline step and on UNet-256 (the narrow layers are bound by the MMA issue
   // rate, ~60 cycles per N = 64 MMA, not by their epilogue), so it is off unless DLB_EPI2=1
   static const bool epi2_env = []() { const char* e = getenv("DLB_EPI2"); return e != nullptr && e[0] == '1'; }();
