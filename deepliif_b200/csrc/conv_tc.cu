@@ -16,12 +16,16 @@
 // 16-bit planes (hi [, lo]).  One elected producer thread issues TMA tiled loads (5-D tensor map over
 // the activation: the halo / zero padding is the TMA out-of-bounds fill, the stride-2 case is a
 // (2C, W/2, 2, H/2, N) view of the same memory) into 128B-swizzled shared-memory stages guarded by
-// full/empty mbarriers.  One elected MMA thread issues tcgen05.mma (M=128, N=n_tile, K=16, fp32
-// accumulate in TMEM).  In split precision ("x3") every K step issues three MMAs
-// hi*hi + hi*lo + lo*hi, which restores ~fp32 products from 16-bit operands (the
-// 1e-3 parity gate cannot be met by single-pass TF32/BF16).  The accumulator is double-buffered in
-// TMEM (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of tile i+1.  Four epilogue
-// warps read TMEM with tcgen05.ld (one output pixel per thread), add the bias and store fp32 NHWC.
+// full/empty mbarriers.  The MMA warp runs convergent and one elected lane issues tcgen05.mma (M=128,
+// N=n_tile, K=16, fp32 accumulate in TMEM), one asm block per 64-channel chunk so that the
+// descriptors live in uniform registers (ptx.cuh).  In split precision ("x3") every K step issues
+// three MMAs hi*hi + hi*lo + lo*hi, which restores ~fp32 products from 16-bit operands (SURVEY.md
+// §8d: the 1e-3 parity gate cannot be met by single-pass TF32/BF16).  The accumulator is
+// double-buffered in TMEM (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of tile
+// i+1.  Four epilogue warps read TMEM with tcgen05.ld (one output pixel per thread), add the bias
+// and write fp32 NHWC through a shared-memory transpose buffer (TcParams::ets: coalesced 128-byte
+// lines, or TMA box stores on the fused-operand launches; direct stores where the buffer does not
+// fit), taking the normalisation statistics of the tile on the way.
 // The kernel is persistent: grid = min(#tiles, #SMs), static round-robin tile schedule (tiles have
 // identical cost).
 #include <cuda_bf16.h>

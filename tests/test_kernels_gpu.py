@@ -418,3 +418,54 @@ def test_stem_conv_stream_vs_fp64_reference_and_its_statistics(ops, case):
     assert err <= 3e-5 * ref.abs().max().item()
     assert (s1 - s2).abs().max().item() <= 2e-6 * s2.abs().max().item()
     assert (h1 - h2).abs().max().item() <= 5e-6 * max(1.0, h2.abs().max().item())
+
+
+_EPILOGUE_SCRIPT = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+from deepliif_b200 import ops
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g) * 2 - 1) * scale).cuda()
+h = hashlib.sha256()
+x = rnd((2, 32, 32, 128), 6)
+xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+for (cout, k, st, pad, tr, op) in ((64, 3, 1, 1, False, 0), (128, 3, 2, 1, False, 0), (64, 3, 2, 1, True, 1), (128, 3, 2, 1, True, 1)):
+    d = ops.conv_desc(2, 32, 32, [128], cout, k, k, st, pad, tr, op)
+    w = rnd((128, cout, k, k) if tr else (cout, 128, k, k), 7, 0.05)
+    w_hi, w_lo = ops.pack_weights_tc(d, w, ops.FMT_BF16, True)
+    oh, ow = ops.conv_out_shape(d)
+    ws = ops.stats_workspace(2, oh * ow, cout, x.device)
+    y = ops.conv_tc(d, [xh], [xl], w_hi, w_lo, rnd((cout,), 8, 0.1), ops.FMT_BF16, True, 0, stats_ws=ws)
+    s1, h1 = ops.norm_finalize(ws, 2, oh * ow, cout, None, None, False)
+    for t in (y, s1, h1):
+        h.update(t.cpu().numpy().tobytes())
+raw = rnd((2, 32, 32, 256), 9)
+d = ops.conv_desc(2, 32, 32, [256], 256, 3, 3, 1, 1, False, 0)
+w_hi, w_lo = ops.pack_weights_tc(d, rnd((256, 256, 3, 3), 10, 0.03), ops.FMT_BF16, True)
+ws = ops.stats_workspace(2, 1024, 256, raw.device)
+y = ops.conv_tc_fused(d, [dict(x=raw, scale=rnd((2, 256), 11) * 0.3 + 1, shift=rnd((2, 256), 12, 0.3), act=ops.ACT_RELU)], w_hi, w_lo,
+                      None, ops.FMT_BF16, True, 0, stats_ws=ws)
+s1, h1 = ops.norm_finalize(ws, 2, 1024, 256, None, None, False)
+for t in (y, s1, h1):
+    h.update(t.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_conv_tc_epilogue_variants_are_bit_identical(ops):
+    """The epilogue through shared memory (coalesced copy-out on plane-fed launches, TMA box stores on the fused-operand
+    CTA-pair launch; statistics summed in the butterfly's tree order) writes the same bytes — outputs AND finalized
+    statistics — as the direct-store / shuffle-butterfly epilogue.  The variant is chosen once per process
+    (DLB_EPI_SMEM), so each runs in its own interpreter."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for mode in ("0", "1", "2"):
+        env = dict(os.environ, DLB_EPI_SMEM=mode)
+        out = subprocess.run([sys.executable, "-c", _EPILOGUE_SCRIPT % root], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[mode] = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0]
+    print(digests)
+    assert digests["0"] == digests["1"] == digests["2"]
