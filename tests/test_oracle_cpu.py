@@ -222,3 +222,48 @@ def test_image_variance_gray_drops_saturated_pixels_like_the_reference():
         got = image_variance_gray(im)
         assert abs(got - float(v)) < 1e-9 * max(1.0, abs(float(v)))
         assert (got < 9) == bool(e)
+
+
+def test_ctypes_signatures_match_the_header_prototypes(lib_built):
+    """Every prototype in include/deepliif_b200.h against the ctypes table the host code calls through: same number of
+    arguments and the same argument class (pointer / int / float / unsigned 64-bit incl. size_t / signed 64-bit) in every position — a binding
+    that drifts from the header corrupts the call frame silently."""
+    import ctypes as C
+    from deepliif_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "include", "deepliif_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dlb_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)
+    assert len(protos) >= 40
+
+    def klass_c(decl):
+        d = " ".join(decl.split())
+        if "*" in d or "dlb_stream_t" in d:
+            return "ptr"
+        if "size_t" in d:
+            return "u64"                  # ctypes aliases c_size_t and c_ulonglong on LP64
+        if "float" in d:
+            return "float"
+        if "unsigned long long" in d:
+            return "u64"
+        if "long long" in d:
+            return "i64"
+        if re.search(r"\bint\b", d):
+            return "int"
+        raise AssertionError(f"unclassified parameter: {decl!r}")
+
+    def klass_py(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_size_t: "u64", C.c_float: "float", C.c_ulonglong: "u64", C.c_longlong: "i64", C.c_int: "int"}[t]
+
+    seen = set()
+    for ret, name, params in protos:
+        seen.add(name)
+        params = params.strip()
+        cparams = [] if params in ("", "void") else [p for p in params.split(",")]
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert len(cparams) == len(argtypes), (name, len(cparams), len(argtypes))
+        for i, (cp, at) in enumerate(zip(cparams, argtypes)):
+            assert klass_c(cp) == klass_py(at), (name, i, cp.strip(), at)
+    assert seen == set(_lib.SIGNATURES)
