@@ -1570,8 +1570,7 @@ int launch_conv_tc_phase(const TcPhase& ph, cudaStream_t stream) {
     // clusters of two CTAs (consecutive blockIdx.x = consecutive tiles); an even grid, at most one CTA per SM
     grid = (grid + 1) & ~1;
     if (grid > num_sms) grid = num_sms & ~1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreadsFa, 1, 1); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
