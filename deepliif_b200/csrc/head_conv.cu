@@ -1,4 +1,4 @@
-// Row-streaming tensor-core convolution for the generator head: ReflectionPad2d(3) / ZeroPad2d(3) + Conv2d(64, CO <= 4, 7)
+// Row-streaming tensor-core convolution for the generator head: ReflectionPad2d(3) / ZeroPad2d(3) + Conv2d(64, CO <= 3, 7)
 // + bias + Tanh (reference networks.py:438-444), reading the producer's RAW fp32 NHWC output and evaluating its
 // normalisation + activation while loading, writing the network output fp32 NCHW.  One kernel replaces
 // dlb_norm_apply / dlb_conv_tc_fwd_fused (vertical-strip mode) + dlb_head_finish for this layer.

@@ -15,8 +15,9 @@
 //
 // A CTA walks down a 128-pixel-wide column strip: 2 converter warps keep a 16-row ring of packed rows ahead of the MMA
 // warp (3 x 134 floats per row: plain coalesced loads, zero / reflected border resolved here), the MMA warp issues a row
-// as soon as the rows r-3..r+3 are packed, 4 epilogue warps add the halves (+ bias), store 128 px x 64 ch fp32 NHWC and
-// write one statistics slice (count, sum, M2 about the slice mean per channel) per row tile.
+// as soon as the rows r-3..r+3 are packed, 2 x 4 epilogue warps (even / odd rows) add the halves (+ bias), hand the TMEM
+// accumulator back, stage the 128 px x 64 ch fp32 tile in swizzled shared memory for two TMA box stores and write one
+// statistics slice (count, sum, M2 about the slice mean per channel) per row tile.
 // Work split: all N x strips x H strip rows form one sequence cut into gridDim.x contiguous ranges.
 // Algorithmic bytes: 4*C read per input pixel + 256 written per output pixel.
 #include <cuda_bf16.h>
