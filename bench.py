@@ -369,7 +369,8 @@ def main():
                                    % B, "norm": args.norm, "padding": "zero", "micro_batch": args.micro_batch, "streams": args.streams,
                        "cuda_graph": use_graph,
                        "fused_operand": {k: os.environ.get(k, "default") for k in ("DLB_FUSED", "DLB_FUSE_RESIDUAL", "DLB_FUSE_STEM",
-                                                                                      "DLB_FUSE_UP", "DLB_FUSE_HEAD")},
+                                                                                      "DLB_FUSE_UP", "DLB_FUSE_HEAD", "DLB_STEM_STREAM",
+                                                                                      "DLB_HEAD_STREAM", "DLB_EPI_SMEM", "DLB_EPI2", "DLB_CTA2")},
                        "host_enqueue_ms_per_step": t_host * 1e3 / args.steps,
                        "parallelism": "tile-sharded dp%d, no collective" % world,
                        "l2": "3 rotating input batches (%.0f MB each) + multi-GB activations per step >> 126 MB L2" % (B * 3 * HW * HW * 4 / 1e6),
