@@ -413,7 +413,7 @@ class ResnetEngine(_EngineBase):
             if taps is not None:
                 taps[name] = a
 
-        if self.stem_stream and H >= 8 and W >= 8:
+        if self.stem_stream and H >= 8 and W >= 8 and (W >= 32 or H <= 256):   # (one statistics slice per row tile must fit the workspace)
             ws = ops.stats_workspace(N, H * W, self.stem.cout, x.device)
             y = ops.stem_conv(x, self.stem_wpk, self.stem.bias, self.stem.cout, self.pad_mode, stats_ws=ws)
         elif self.fuse_stem and self.stem_in_nc <= 4 and H >= 16 and W >= 8 and self.stem_S == 7:
